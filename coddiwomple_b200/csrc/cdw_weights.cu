@@ -1,0 +1,519 @@
+// cdw_weights.cu — K2 (incremental work / log-weight update, log-sum-exp + ESS reduction), K3a (integer cdf scan +
+// vectorised search for multinomial / systematic resampling), K3b (coalesced particle gather) for sm_100a.
+//
+// Reference semantics: TargetFactory.compute_incremental_work (coddiwomple/distribution_factories.py:124-129),
+// nESS / vanilla_floor_threshold (coddiwomple/utils.py:41-72), Resampler.resample (coddiwomple/resamplers.py:61-133),
+// MultinomialResampler._resample (coddiwomple/resamplers.py:254-272).
+//
+// Exactness: ancestors come from an INTEGER cdf (weights quantised with det_exp + rint, uint64 prefix sum, integer
+// search), so they are independent of summation order, block schedule and GPU count, and equal oracle/resampling.py
+// bit for bit.
+#include "cdw_common.h"
+
+namespace cdw {
+
+constexpr int kBlock = 256;
+constexpr int kItems = 8;
+constexpr int kTile = kBlock * kItems;
+constexpr int kMaxStatBlocks = 2048;
+
+// workspace header (uint64 words)
+enum { WS_TICKET = 0, WS_T1 = 1, WS_SHIFT = 2, WS_TOTAL = 3, WS_HEADER_WORDS = 8 };
+
+struct WsView {
+    unsigned long long* hdr;
+    double* part_e;
+    double* part_e2;
+    unsigned long long* tile_sum;
+    unsigned long long* tile_off;
+};
+
+__host__ __device__ inline long long n_tiles_for(long long n) { return (n + kTile - 1) / kTile; }
+
+__host__ __device__ inline WsView ws_view(void* ws, long long n) {
+    WsView v;
+    unsigned char* b = (unsigned char*)ws;
+    v.hdr = (unsigned long long*)b; b += sizeof(unsigned long long) * WS_HEADER_WORDS;
+    v.part_e = (double*)b; b += sizeof(double) * kMaxStatBlocks;
+    v.part_e2 = (double*)b; b += sizeof(double) * kMaxStatBlocks;
+    v.tile_sum = (unsigned long long*)b; b += sizeof(unsigned long long) * n_tiles_for(n);
+    v.tile_off = (unsigned long long*)b;
+    return v;
+}
+
+__device__ __forceinline__ double pow2(int e) { return bits_to_double((uint64_t)(e + 1023) << 52); }
+
+__device__ __forceinline__ unsigned long long quantise(double w, double wmin, double scale) {
+    double e = det_exp(CDW_ADD(wmin, -w));
+    return __double2ull_rn(CDW_MUL(e, scale));
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T* sh /*[kBlock/32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    T r = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = op(r, sh[w]);
+    return r;  // same value in every thread, combined in a fixed order
+}
+
+// ------------------------------------------------------------------------------------------------ K2 pass 1
+__global__ void __launch_bounds__(kBlock) weight_update_kernel(const double* __restrict__ u_new, const double* __restrict__ aux,
+                                                               const double* __restrict__ proposal, const double* __restrict__ cum,
+                                                               long long n, double* __restrict__ inc_out, double* __restrict__ w_out,
+                                                               unsigned long long* wmin_key) {
+    __shared__ unsigned long long sh[kBlock / 32];
+    unsigned long long m = ~0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double inc = u_new[i] + (aux ? aux[i] : 0.0);
+        if (proposal) inc += proposal[i];
+        double w = (cum ? cum[i] : 0.0) + inc;
+        if (inc_out) inc_out[i] = inc;
+        w_out[i] = w;
+        unsigned long long k = ordered_key(w);
+        m = k < m ? k : m;
+    }
+    m = block_reduce(m, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, sh);
+    if (threadIdx.x == 0 && wmin_key && m != ~0ull) atomicMin(wmin_key, m);
+}
+
+// ------------------------------------------------------------------------------------------------ K2 pass 2
+__global__ void __launch_bounds__(kBlock) weight_stats_kernel(const double* __restrict__ w, long long n, double threshold,
+                                                              const unsigned long long* __restrict__ wmin_key, double* stats, WsView ws,
+                                                              int s1) {
+    __shared__ double shd[kBlock / 32];
+    __shared__ unsigned long long shu[kBlock / 32];
+    __shared__ bool is_last;
+    const double wmin = ordered_key_inverse(*wmin_key);
+    const double scale1 = pow2(s1);
+    double se = 0.0, se2 = 0.0;
+    unsigned long long t1 = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double e = det_exp(CDW_ADD(wmin, -w[i]));
+        se += e;
+        se2 += e * e;
+        t1 += __double2ull_rn(CDW_MUL(e, scale1));
+    }
+    se = block_reduce(se, [](double a, double b) { return a + b; }, shd);
+    se2 = block_reduce(se2, [](double a, double b) { return a + b; }, shd);
+    t1 = block_reduce(t1, [](unsigned long long a, unsigned long long b) { return a + b; }, shu);
+    if (threadIdx.x == 0) {
+        ws.part_e[blockIdx.x] = se;
+        ws.part_e2[blockIdx.x] = se2;
+        atomicAdd(&ws.hdr[WS_T1], t1);
+        __threadfence();
+        unsigned long long ticket = atomicAdd(&ws.hdr[WS_TICKET], 1ull);
+        is_last = ticket == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double sum_e = 0.0, sum_e2 = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) {  // fixed order: run-to-run deterministic
+            sum_e += ((volatile double*)ws.part_e)[b];
+            sum_e2 += ((volatile double*)ws.part_e2)[b];
+        }
+        unsigned long long T1 = ((volatile unsigned long long*)ws.hdr)[WS_T1];
+        int bitlen = 64 - __clzll((long long)T1);
+        int shift = 60 - bitlen;
+        shift = shift < 0 ? 0 : shift;
+        ws.hdr[WS_SHIFT] = (unsigned long long)(s1 + shift);
+        double ness = (sum_e * sum_e) / ((double)n * sum_e2);
+        stats[CDW_STAT_WMIN] = wmin;
+        stats[CDW_STAT_SUM_E] = sum_e;
+        stats[CDW_STAT_SUM_E2] = sum_e2;
+        stats[CDW_STAT_NESS] = ness;
+        stats[CDW_STAT_MEAN] = wmin - log(sum_e) + log((double)n);
+        stats[CDW_STAT_RESAMPLE] = (threshold < 0.0 || ness <= threshold) ? 1.0 : 0.0;
+        stats[CDW_STAT_TOTAL] = 0.0;
+        stats[CDW_STAT_NNAN] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3a: integer cdf
+__device__ __forceinline__ void load_tile_q(const double* __restrict__ w, long long n, long long base, double wmin, double scale,
+                                            unsigned long long (&q)[kItems]) {
+    const long long i0 = base + (long long)threadIdx.x * kItems;
+    if (i0 + kItems <= n) {
+        const double2* p = (const double2*)(w + i0);  // i0 is a multiple of 8 -> 64-byte aligned
+#pragma unroll
+        for (int k = 0; k < kItems / 2; ++k) {
+            double2 v = __ldg(p + k);
+            q[2 * k] = quantise(v.x, wmin, scale);
+            q[2 * k + 1] = quantise(v.y, wmin, scale);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) q[k] = (i0 + k < n) ? quantise(w[i0 + k], wmin, scale) : 0ull;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) cdf_tile_sums_kernel(const double* __restrict__ w, long long n, const double* __restrict__ stats,
+                                                               WsView ws) {
+    if (stats[CDW_STAT_RESAMPLE] == 0.0) return;
+    __shared__ unsigned long long sh[kBlock / 32];
+    const double wmin = stats[CDW_STAT_WMIN];
+    const double scale = pow2((int)ws.hdr[WS_SHIFT]);
+    for (long long tile = blockIdx.x; tile < n_tiles_for(n); tile += gridDim.x) {
+        unsigned long long q[kItems];
+        load_tile_q(w, n, tile * kTile, wmin, scale, q);
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) s += q[k];
+        s = block_reduce(s, [](unsigned long long a, unsigned long long b) { return a + b; }, sh);
+        if (threadIdx.x == 0) ws.tile_sum[tile] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024) cdf_scan_tiles_kernel(long long n, double* stats, WsView ws) {
+    if (stats[CDW_STAT_RESAMPLE] == 0.0) return;
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_sh;
+    const long long nt = n_tiles_for(n);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (long long base = 0; base < nt; base += 1024) {
+        long long i = base + threadIdx.x;
+        unsigned long long v = i < nt ? ws.tile_sum[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long t = warp_tot[lane], s = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long u = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += u;
+            }
+            warp_tot[lane] = s - t;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_sh;
+        const unsigned long long excl = carry + warp_tot[warp] + incl - v;
+        if (i < nt) ws.tile_off[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_sh = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ws.hdr[WS_TOTAL] = carry_sh;
+        stats[CDW_STAT_TOTAL] = (double)carry_sh;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __restrict__ w, long long n, const double* __restrict__ stats,
+                                                               WsView ws, unsigned long long* __restrict__ cdf) {
+    if (stats[CDW_STAT_RESAMPLE] == 0.0) return;
+    __shared__ unsigned long long warp_tot[kBlock / 32];
+    const double wmin = stats[CDW_STAT_WMIN];
+    const double scale = pow2((int)ws.hdr[WS_SHIFT]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long tile = blockIdx.x; tile < n_tiles_for(n); tile += gridDim.x) {
+        unsigned long long q[kItems];
+        load_tile_q(w, n, tile * kTile, wmin, scale, q);
+#pragma unroll
+        for (int k = 1; k < kItems; ++k) q[k] += q[k - 1];
+        const unsigned long long tot = q[kItems - 1];
+        unsigned long long incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long off = ws.tile_off[tile] + incl - tot;
+        for (int wi = 0; wi < warp; ++wi) off += warp_tot[wi];
+        const long long i0 = tile * kTile + (long long)threadIdx.x * kItems;
+        if (i0 + kItems <= n) {
+            ulonglong2* o2 = (ulonglong2*)(cdf + i0);
+#pragma unroll
+            for (int k = 0; k < kItems / 2; ++k) o2[k] = make_ulonglong2(q[2 * k] + off, q[2 * k + 1] + off);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kItems; ++k)
+                if (i0 + k < n) cdf[i0 + k] = q[k] + off;
+        }
+    }
+}
+
+// vectorised search: ancestor = first j with cdf[j] > floor(u * T)  (== searchsorted(cdf, target, side='right'))
+__global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* __restrict__ w, const double* __restrict__ uniforms,
+                                                        long long n, const double* __restrict__ stats, WsView ws,
+                                                        const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
+                                                        double* __restrict__ cum_out, int* __restrict__ anc) {
+    const bool resample = stats[CDW_STAT_RESAMPLE] != 0.0;
+    const double mean = stats[CDW_STAT_MEAN];
+    const unsigned long long total = resample ? ws.hdr[WS_TOTAL] : 0ull;
+    const double u0 = (resample && kind == CDW_RESAMPLE_SYSTEMATIC) ? uniforms[0] : 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (!resample) {
+            if (anc) anc[i] = (int)i;
+            if (cum_out) cum_out[i] = w[i];  // null update: cum += inc (resamplers.py:136-156)
+            continue;
+        }
+        double u = kind == CDW_RESAMPLE_SYSTEMATIC ? __ddiv_rn(__dadd_rn((double)i, u0), (double)n) : uniforms[i];
+        const unsigned long long target = fixed_target(u, total);
+        long long lo = 0, hi = n - 1;  // invariant: answer in [lo, hi]; cdf[n-1] == total > target
+        while (lo < hi) {
+            long long mid = (lo + hi) >> 1;
+            if (__ldg(cdf + mid) > target) hi = mid; else lo = mid + 1;
+        }
+        anc[i] = (int)lo;
+        if (cum_out) {
+            double c = cum_in ? cum_in[i] : 0.0;
+            cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3b: gather
+__global__ void __launch_bounds__(kBlock) gather_kernel(const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                                                        const int* __restrict__ anc, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+                                                        const double* __restrict__ aux_in, double* __restrict__ aux_out,
+                                                        const int* __restrict__ label_in, int* __restrict__ label_out, long long n, int A) {
+    const long long total = n * A;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / A;
+        const int a = (int)(idx - p * A);
+        const long long src = anc[p];
+        pos_out[idx] = __ldg(pos_in + src * A + a);
+        if (vel_in) vel_out[idx] = __ldg(vel_in + src * A + a);
+        if (a == 0) {
+            if (aux_in) aux_out[p] = aux_in[src];
+            if (label_in) label_out[p] = label_in[src];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) gather_peer_kernel(const float4* const* __restrict__ peer_pos, const float4* const* __restrict__ peer_vel,
+                                                             const double* const* __restrict__ peer_aux, const int* const* __restrict__ peer_label,
+                                                             long long n_per_rank, const int* __restrict__ anc, float4* __restrict__ pos_out,
+                                                             float4* __restrict__ vel_out, double* __restrict__ aux_out, int* __restrict__ label_out,
+                                                             long long n, int A) {
+    const long long total = n * A;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / A;
+        const int a = (int)(idx - p * A);
+        const long long g = anc[p];
+        const int r = (int)(g / n_per_rank);
+        const long long src = g - (long long)r * n_per_rank;
+        pos_out[idx] = peer_pos[r][src * A + a];  // NVLink load when r is a peer (P2P-mapped pointer)
+        if (peer_vel) vel_out[idx] = peer_vel[r][src * A + a];
+        if (a == 0) {
+            if (peer_aux) aux_out[p] = peer_aux[r][src];
+            if (peer_label) label_out[p] = peer_label[r][src];
+        }
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void philox_uniforms_kernel(unsigned long long seed, unsigned long long stream_id, long long n, double* out) {
+    const long long pairs = (n + 1) / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x) {
+        u4 c;
+        c.x = (uint32_t)i; c.y = (uint32_t)((unsigned long long)i >> 32); c.z = (uint32_t)stream_id; c.w = 0x5EEDu;
+        u4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        unsigned long long a = (((unsigned long long)r.x << 32) | r.y) >> 11, b = (((unsigned long long)r.z << 32) | r.w) >> 11;
+        out[2 * i] = (double)a * 1.1102230246251565e-16;
+        if (2 * i + 1 < n) out[2 * i + 1] = (double)b * 1.1102230246251565e-16;
+    }
+}
+
+template <typename T>
+__global__ void fma_peak_kernel(T* out, int iters) {
+    T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T m = (T)0.999, c = (T)0.001;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+static int blocks_for(long long n, int per_block, int cap) {
+    long long b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace cdw
+
+using namespace cdw;
+
+extern "C" size_t cdw_weight_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return sizeof(unsigned long long) * WS_HEADER_WORDS + 2 * sizeof(double) * kMaxStatBlocks +
+           2 * sizeof(unsigned long long) * (size_t)(n_tiles_for(n) + 1);
+}
+
+extern "C" int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
+                                 double* inc_out, double* w_out, uint64_t* wmin_key, cdw_stream stream) {
+    CDW_REQUIRE(u_new && w_out && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    int grid = blocks_for(n, kBlock * 4, sm_count() * 8);
+    weight_update_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(u_new, aux, proposal, cum, n, inc_out, w_out, (unsigned long long*)wmin_key);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
+                                void* workspace, size_t workspace_bytes, cdw_stream stream) {
+    CDW_REQUIRE(w && wmin_key && stats && workspace && n > 0, "null argument or n == 0");
+    CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
+    CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+    WsView ws = ws_view(workspace, n);
+    CDW_CUDA(cudaMemsetAsync(ws.hdr, 0, sizeof(unsigned long long) * WS_HEADER_WORDS, (cudaStream_t)stream));
+    int b = 0;
+    while ((1ll << b) < n) ++b;  // ceil(log2 n)
+    int grid = blocks_for(n, kBlock * 4, sm_count() * 8);
+    if (grid > kMaxStatBlocks) grid = kMaxStatBlocks;
+    weight_stats_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(w, n, floor_threshold, (const unsigned long long*)wmin_key, stats, ws, 61 - b);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats, const double* cum_in,
+                                    double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace, size_t workspace_bytes,
+                                    cdw_stream stream) {
+    CDW_REQUIRE(w && stats && anc_out && cdf_out && workspace && n > 0, "null argument or n == 0");
+    CDW_REQUIRE(kind == CDW_RESAMPLE_MULTINOMIAL || kind == CDW_RESAMPLE_SYSTEMATIC, "unknown resampler kind");
+    CDW_REQUIRE(uniforms, "uniforms are required");
+    CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
+    CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+    WsView ws = ws_view(workspace, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nt = n_tiles_for(n);
+    int grid_t = (int)(nt < (long long)sm_count() * 16 ? nt : (long long)sm_count() * 16);
+    cdf_tile_sums_kernel<<<grid_t, kBlock, 0, st>>>(w, n, stats, ws);
+    cdf_scan_tiles_kernel<<<1, 1024, 0, st>>>(n, (double*)stats, ws);
+    cdf_tile_scan_kernel<<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out);
+    int grid_s = blocks_for(n, kBlock, sm_count() * 16);
+    search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
+                                    const double* aux_in, double* aux_out, const int32_t* label_in, int32_t* label_out, int64_t n,
+                                    int32_t n_atoms, cdw_stream stream) {
+    CDW_REQUIRE(pos_in && pos_out && anc && n >= 0 && n_atoms > 0, "null argument");
+    CDW_REQUIRE(pos_in != pos_out && (!vel_in || (vel_out && vel_in != vel_out)), "gather needs distinct in/out buffers");
+    CDW_REQUIRE((!aux_in || aux_out) && (!label_in || label_out), "missing output");
+    if (n == 0) return CDW_OK;
+    int grid = blocks_for(n * n_atoms, kBlock, sm_count() * 16);
+    gather_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const float4*)pos_in, (const float4*)vel_in, anc, (float4*)pos_out, (float4*)vel_out,
+                                                            aux_in, aux_out, label_in, label_out, n, n_atoms);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_gather_particles_peer(const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
+                                         const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, const int32_t* anc,
+                                         float* pos_out, float* vel_out, double* aux_out, int32_t* label_out, int64_t n_local, int32_t n_atoms,
+                                         cdw_stream stream) {
+    CDW_REQUIRE(peer_pos && pos_out && anc && n_ranks > 0 && n_per_rank > 0 && n_local >= 0 && n_atoms > 0, "null argument");
+    CDW_REQUIRE((!peer_vel || vel_out) && (!peer_aux || aux_out) && (!peer_label || label_out), "missing output");
+    if (n_local == 0) return CDW_OK;
+    int grid = blocks_for(n_local * n_atoms, kBlock, sm_count() * 16);
+    gather_peer_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const float4* const*)peer_pos, (const float4* const*)peer_vel, peer_aux, peer_label,
+                                                                 n_per_rank, anc, (float4*)pos_out, (float4*)vel_out, aux_out, label_out, n_local, n_atoms);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_fill_u64(uint64_t* ptr, uint64_t value, int64_t n, cdw_stream stream) {
+    CDW_REQUIRE(ptr && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    fill_u64_kernel<<<blocks_for(n, 256, 1024), 256, 0, (cudaStream_t)stream>>>((unsigned long long*)ptr, value, n);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_philox_uniforms(uint64_t seed, uint64_t stream_id, int64_t n, double* out, cdw_stream stream) {
+    CDW_REQUIRE(out && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    philox_uniforms_kernel<<<blocks_for((n + 1) / 2, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(seed, stream_id, n, out);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_ipc_get_handle(const void* dev_ptr, void* handle64_host) {
+    CDW_REQUIRE(dev_ptr && handle64_host, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CDW_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_host, (void*)dev_ptr));
+    return CDW_OK;
+}
+extern "C" int cdw_ipc_open_handle(const void* handle64_host, void** dev_ptr_out) {
+    CDW_REQUIRE(handle64_host && dev_ptr_out, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    CDW_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return CDW_OK;
+}
+extern "C" int cdw_ipc_close_handle(void* dev_ptr) {
+    CDW_REQUIRE(dev_ptr, "null argument");
+    CDW_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return CDW_OK;
+}
+extern "C" int cdw_device_malloc(size_t bytes, void** out) {
+    CDW_REQUIRE(out && bytes > 0, "null argument");
+    CDW_CUDA(cudaMalloc(out, bytes));
+    return CDW_OK;
+}
+extern "C" int cdw_device_free(void* ptr) {
+    if (ptr) CDW_CUDA(cudaFree(ptr));
+    return CDW_OK;
+}
+
+extern "C" int cdw_fma_peak(int fp64, int iters, double* tflops_out, double* ms_out) {
+    CDW_REQUIRE(tflops_out && iters > 0, "null argument");
+    const int sms = sm_count(), blocks = sms * 8, threads = 512;
+    void* buf = nullptr;
+    CDW_CUDA(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CDW_CUDA(cudaEventCreate(&e0));
+    CDW_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CDW_CUDA(cudaEventRecord(e0));
+        if (fp64) fma_peak_kernel<double><<<blocks, threads>>>((double*)buf, iters);
+        else fma_peak_kernel<float><<<blocks, threads>>>((float*)buf, iters);
+        CDW_CUDA(cudaEventRecord(e1));
+        CDW_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CDW_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return CDW_OK;
+}

@@ -1,0 +1,218 @@
+/* cdw.h — C ABI of libcdw_b200.so: the B200-native SMC annealing hot path of choderalab/coddiwomple.
+ *
+ * The reference (pure Python) has no FFI for this path; it reaches OpenMM through openmmtools objects.  Each entry
+ * point below replaces the reference interface cited beside it (paths relative to the reference checkout) and is what
+ * a ctypes binding in the reference would call (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative CDW_E* code; cdw_last_error() gives a thread-local message;
+ *   - all array arguments are CALLER-OWNED DEVICE pointers (e.g. torch tensors' data_ptr()) unless marked "host";
+ *     nothing is retained past the call except by cdw_system_create (which copies its host tables to the device);
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and never synchronises, so the
+ *     calls can be captured into a CUDA graph; results are ordered on that stream;
+ *   - particle coordinates / velocities are rows of float4: pos[p][a] = (x, y, z, unused) in nm, nm/ps;
+ *   - energies are kJ/mol unless a `beta`/`kT` argument says they are reduced (units of kT);
+ *   - a cdw_system handle is immutable after creation and may be shared by threads; other state is the caller's.
+ */
+#ifndef CDW_H
+#define CDW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDW_VERSION 1
+
+#define CDW_OK 0
+#define CDW_EINVAL (-1)   /* bad argument */
+#define CDW_ECUDA (-2)    /* CUDA runtime error (message in cdw_last_error) */
+#define CDW_ENOMEM (-3)
+#define CDW_EUNSUPPORTED (-4)
+
+typedef struct cdw_system cdw_system; /* opaque, device-resident force field of ONE replica */
+typedef void* cdw_stream;             /* cudaStream_t */
+
+/* Host-side description of one replica's potential: the OpenMM System of the reference lowered to term tables.
+ * Every lambda-dependent parameter is AFFINE in one global parameter:  value = c0 + lambda[slot] * c1  (slot < 0 ->
+ * constant c0), which covers every alchemical form in the reference's hybrid systems
+ * (coddiwomple/data/perses_data/*.factory.pkl: `_hybrid_system` XML) and the harmonic test system
+ * (coddiwomple/tests/utils.py:27-72).  All pointers are HOST pointers, copied by cdw_system_create. */
+typedef struct cdw_system_desc {
+    int32_t n_atoms;
+    int32_t n_lambda;            /* number of global parameters (lambda vector length) */
+    const double* masses;        /* [n_atoms] amu */
+
+    /* harmonic bonds  E = K/2 (r-L)^2       (HarmonicBondForce, CustomBondForce "(K/2)*(r-length)^2") */
+    int32_t n_bonds;
+    const int32_t* bond_atoms;   /* [n_bonds][2] */
+    const int32_t* bond_slot;    /* [n_bonds]    */
+    const double* bond_par;      /* [n_bonds][4] = K0, K1, L0, L1 */
+
+    /* harmonic angles E = K/2 (theta-T)^2   (HarmonicAngleForce, CustomAngleForce) */
+    int32_t n_angles;
+    const int32_t* angle_atoms;  /* [n_angles][3], vertex in the middle */
+    const int32_t* angle_slot;
+    const double* angle_par;     /* [n_angles][4] = K0, K1, T0, T1 */
+
+    /* periodic torsions E = k (1 + cos(n phi - phase))   (PeriodicTorsionForce; each half of CustomTorsionForce) */
+    int32_t n_torsions;
+    const int32_t* torsion_atoms; /* [n_torsions][4] */
+    const int32_t* torsion_slot;
+    const int32_t* torsion_n;     /* integer periodicity 0..6 */
+    const double* torsion_par;    /* [n_torsions][3] = k0, k1, phase */
+
+    /* NonbondedForce (NoCutoff): per-atom (q, sigma, epsilon) + ParticleOffsets; exceptions + ExceptionOffsets */
+    const double* nb_atom_par;     /* [n_atoms][3] */
+    int32_t n_atom_offsets;
+    const int32_t* atom_off_idx;   /* [n][2] = atom, slot */
+    const double* atom_off_par;    /* [n][3] = dq, dsigma, depsilon */
+    int32_t n_exceptions;
+    const double* exc_par;         /* [n_exceptions][3] = chargeProd, sigma, epsilon */
+    int32_t n_exc_offsets;
+    const int32_t* exc_off_idx;    /* [n][2] = exception, slot */
+    const double* exc_off_par;     /* [n][3] */
+
+    /* unified pair list: every atom pair with a possibly non-zero nonbonded or soft-core contribution */
+    int32_t n_pairs;
+    const int32_t* pair_atoms;     /* [n_pairs][2] */
+    const int32_t* pair_nb;        /* [n_pairs] -1: none, -2: mixing rule from nb_atom_par, >=0: exception index */
+    const int32_t* pair_sc_class;  /* [n_pairs] -1: none, 0: core, 1: touches a unique-new atom, 2: unique-old */
+    const double* pair_sc_par;     /* [n_pairs][4] = sigmaA, epsilonA, sigmaB, epsilonB (already mixed per pair) */
+    /* perses soft-core LJ v2 (CustomNonbondedForce "U_sterics = select(step(r - r_LJ), ...)") global slots */
+    int32_t slot_sterics_core, slot_sterics_insert, slot_sterics_delete, slot_softcore_alpha;
+
+    /* external harmonic wells E = K/2 ((x-x0)^2 + y^2 + z^2) + U0   (openmmtools HarmonicOscillator) */
+    int32_t n_ext;
+    const int32_t* ext_atom;       /* [n_ext] */
+    const int32_t* ext_slot;       /* [n_ext][3] = slot of K, x0, U0 */
+    const double* ext_par;         /* [n_ext][6] = K0, K1, x00, x01, U00, U01 */
+
+    /* holonomic distance constraints */
+    int32_t n_constraints;
+    const int32_t* cons_atoms;     /* [n_constraints][2] */
+    const double* cons_dist;       /* [n_constraints] nm */
+} cdw_system_desc;
+
+/* Langevin "V R O R V" parameters — OMMLI.__init__ (coddiwomple/openmm/integrators.py:75-131) */
+typedef struct cdw_langevin_params {
+    double dt;              /* ps */
+    double gamma;           /* collision rate, 1/ps */
+    double kT;              /* kJ/mol */
+    double constraint_tol;  /* relative distance tolerance (setConstraintTolerance) */
+    int32_t n_steps;        /* integrator steps per call (OMMBIP.apply n_steps, default 1) */
+    uint32_t flags;         /* CDW_FLAG_* */
+} cdw_langevin_params;
+
+#define CDW_FLAG_RANDOMIZE_VELOCITIES 1u /* Context.setVelocitiesToTemperature before stepping (propagators.py:137-138) */
+#define CDW_FLAG_TRACK_WORKS 2u          /* accumulate shadow_work / proposal_work (integrators.py:315,336,350) */
+
+#define CDW_RESAMPLE_MULTINOMIAL 0
+#define CDW_RESAMPLE_SYSTEMATIC 1
+
+/* layout of the `stats` block written by cdw_weight_stats / read by cdw_resample_decide (doubles) */
+#define CDW_STAT_WMIN 0      /* min_i W_i                                  */
+#define CDW_STAT_SUM_E 1     /* sum_i exp(-(W_i - Wmin))                   */
+#define CDW_STAT_SUM_E2 2    /* sum_i exp(-2 (W_i - Wmin))                 */
+#define CDW_STAT_NESS 3      /* (sum e)^2 / (P sum e^2)   (utils.py:41-64) */
+#define CDW_STAT_MEAN 4      /* -logsumexp(-W) + log P   (resamplers.py:107) */
+#define CDW_STAT_RESAMPLE 5  /* 1.0 if this iteration resamples else 0.0   */
+#define CDW_STAT_TOTAL 6     /* integer cdf total T as a double (diagnostic) */
+#define CDW_STAT_NNAN 7      /* number of particles whose move was reverted (NaN guard) */
+#define CDW_STATS_LEN 8
+
+int cdw_version(void);
+const char* cdw_last_error(void);
+/* sm_count / compute capability of the current device; fails (CDW_ECUDA) when no CUDA device is usable */
+int cdw_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* replaces: OpenMMPDFState.__init__ building the ThermodynamicState + Context (openmm/states.py:50-86) */
+int cdw_system_create(const cdw_system_desc* desc, cdw_system** out);
+int cdw_system_destroy(cdw_system* sys);
+int cdw_system_n_atoms(const cdw_system* sys);
+int cdw_system_n_lambda(const cdw_system* sys);
+
+/* K1. replaces: OpenMMPDFState.reduced_potential (openmm/states.py:116-136), batched over P replicas.
+ * u_out[p] = beta * U(pos[p]; lambda).  lambda: device pointer to n_lambda doubles. */
+int cdw_reduced_potential(const cdw_system* sys, const float* pos, int64_t n_particles, const double* lambda,
+                          double beta, double* u_out, cdw_stream stream);
+
+/* energy (kJ/mol) and forces (float4 rows, kJ/mol/nm) — what `f` / `energy` are inside the CustomIntegrator
+ * (openmm/integrators.py:301,327); exposed for the Euler-Maruyama proposal and for tests. */
+int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_t n_particles, const double* lambda,
+                      double* energy_out, float* force_out, cdw_stream stream);
+
+/* K4 (+K3b on load, +K2 first half).  One SMC iteration's per-particle work, fused:
+ *     slot p loads (x, v, aux, label) of its ancestor anc[p] (NULL = identity)           resamplers.py:123-129,189-200
+ *     E1,F1 at (x, lambda);  inc[p] = E1/kT + aux ;  W[p] = cum[p] + inc[p]             distribution_factories.py:98-131
+ *     n_steps of BAOAB with SHAKE/RATTLE and Philox noise                               integrators.py:297-350
+ *     E2 at the new x;  aux_out[p] = -E2/kT                                             openmm/coddiwomple.py:326-327
+ *     NaN guard: a non-finite E2 reverts (x, v) and sets nan_flags[p]                   openmm/propagators.py:163-190
+ * pos_in/vel_in and pos_out/vel_out must be different buffers when anc != NULL.
+ * Optional outputs (NULL to skip): inc_out, w_out, aux_out, label_out, u_first_out, u_last_out (reduced, /kT),
+ * shadow_out, proposal_out (reduced), nan_flags, wmin_key (one uint64, atomically min-ed with the order-preserving
+ * key of W; initialise to ~0ull).  Optional inputs: anc, aux_in, cum_in, label_in.
+ * Noise counters: particle gid = gid0 + p, step = step0 + s. */
+int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
+                      int64_t n_particles, const int32_t* anc, const double* aux_in, const double* cum_in,
+                      const int32_t* label_in, const double* lambda, const cdw_langevin_params* params, uint64_t seed,
+                      uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out, int32_t* label_out,
+                      double* u_first_out, double* u_last_out, double* shadow_out, double* proposal_out,
+                      int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream);
+
+/* replaces: OMMBIP.apply (openmm/propagators.py:89-219) for a batch, in place.  Thin wrapper over the kernel above. */
+int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_particles, const double* lambda,
+              const cdw_langevin_params* params, uint64_t seed, uint64_t step0, int64_t gid0, double* u_first_out,
+              double* u_last_out, double* shadow_out, double* proposal_out, int32_t* nan_flags, cdw_stream stream);
+
+/* K2. replaces: TargetFactory.compute_incremental_work's sum (distribution_factories.py:124-129) + nESS
+ * (utils.py:41-64) + the normaliser of Resampler.resample (resamplers.py:102-107).
+ * cdw_weight_update: inc[p] = u_new[p] + aux[p] (+ proposal[p] if not NULL); w_out[p] = cum[p] + inc[p]; min W -> wmin_key.
+ * cdw_weight_stats : second pass over W: sum e, sum e^2, integer total; the last block finalises stats[] including
+ *                    the resampling decision (threshold < 0: always resample, as observable=None does). */
+int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
+                      double* inc_out, double* w_out, uint64_t* wmin_key, cdw_stream stream);
+size_t cdw_weight_workspace_bytes(int64_t n);
+int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
+                     void* workspace, size_t workspace_bytes, cdw_stream stream);
+
+/* K3a. replaces: MultinomialResampler._resample (resamplers.py:254-272); systematic is new.
+ * Uses the exactly-associative integer cdf; cdf_out[n] uint64 is caller-provided scratch/output.
+ * uniforms: n doubles in [0,1) (multinomial) or 1 double (systematic).  If stats[CDW_STAT_RESAMPLE] == 0 the kernels
+ * write the identity ancestors and cum_out = W (the null update, resamplers.py:136-156); otherwise
+ * cum_out[p] = cum_in[p] + (mean - cum_in[p]) (resamplers.py:196-197). */
+int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats,
+                         const double* cum_in, double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace,
+                         size_t workspace_bytes, cdw_stream stream);
+
+/* K3b. replaces: the per-particle deepcopy loop of Resampler.resample (resamplers.py:123-129,193). */
+int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
+                         const double* aux_in, double* aux_out, const int32_t* label_in, int32_t* label_out,
+                         int64_t n_particles, int32_t n_atoms, cdw_stream stream);
+
+/* multi-GPU variant of K3b: anc holds GLOBAL ancestor ids; rank r owns [r*n_per_rank, (r+1)*n_per_rank);
+ * peer_pos/peer_vel/peer_aux/peer_label: device arrays of n_ranks base pointers (peer-mapped via CUDA IPC). */
+int cdw_gather_particles_peer(const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
+                              const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, const int32_t* anc,
+                              float* pos_out, float* vel_out, double* aux_out, int32_t* label_out, int64_t n_local,
+                              int32_t n_atoms, cdw_stream stream);
+
+/* utilities */
+int cdw_fill_u64(uint64_t* ptr, uint64_t value, int64_t n, cdw_stream stream);
+/* Philox uniforms with 53 random bits (same stream as oracle/rng.py:uniforms53) */
+int cdw_philox_uniforms(uint64_t seed, uint64_t stream_id, int64_t n, double* out, cdw_stream stream);
+/* CUDA IPC plumbing for the peer gather (handles are 64 opaque bytes) */
+int cdw_ipc_get_handle(const void* dev_ptr, void* handle64_host);
+int cdw_ipc_open_handle(const void* handle64_host, void** dev_ptr_out);
+int cdw_ipc_close_handle(void* dev_ptr);
+int cdw_device_malloc(size_t bytes, void** out);
+int cdw_device_free(void* ptr);
+/* FP64 / FP32 FMA-pipe micro-benchmark used for the roofline denominator: returns achieved TFLOP/s */
+int cdw_fma_peak(int fp64, int iters, double* tflops_out, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDW_H */

@@ -1,0 +1,159 @@
+"""BAOAB Langevin propagation with distance constraints, vectorised over particles.  TEST INFRASTRUCTURE ONLY.
+
+Restates the integrator program `OMMLI` emits for splitting "V R O R V" (coddiwomple/openmm/integrators.py:207-217,
+297-350; pretty-printed listing in troubleshooting/openmm_smc.ipynb JSON lines 153-192) as driven by `OMMBIP.apply`
+(coddiwomple/openmm/propagators.py:127-219):
+
+    V: v += (dt/2) f/m ; constrain velocities                                  integrators.py:317-336
+    R: x += (dt/2) v ; x1 = x ; constrain positions ; v += (x-x1)/(dt/2) ; constrain velocities   :297-315
+    O: v = a v + b sqrt(kT/m) xi ; constrain velocities                         :338-350
+       a = exp(-gamma dt), b = sqrt(1 - exp(-2 gamma dt))                       :158-159
+    bookkeeping: shadow_work += dKE (V) / d(KE+PE) (R) ; proposal_work -= dKE (O)   :315,336,350
+
+`addConstrainPositions/Velocities` are OpenMM built-ins (un-vendored): restated as SHAKE (Gauss-Seidel sweeps in
+constraint order, relative distance tolerance as OpenMM's (1 +- tol)^2 window) and its velocity analogue.  Noise is
+Philox (oracle/rng.py) because OpenMM's generator is not reproducible outside OpenMM: parity with the reference's
+trajectories is statistical only; parity with the CUDA kernel is numerical (same counters -> same normals).
+
+Arithmetic mirrors the kernel contract: fp64 everywhere inside a call; positions are rounded to fp32
+after the last drift of the call (before the closing force evaluation) and velocities on return, because particles
+are stored as float4 between calls.
+"""
+import numpy as np
+
+from . import rng
+
+MAX_SHAKE_ITERS = 500
+
+
+def _shake(x, xref, inv_m, constraints, tol):
+    lower, upper = 1.0 - 2.0 * tol + tol * tol, 1.0 + 2.0 * tol + tol * tol
+    for _ in range(MAX_SHAKE_ITERS):
+        any_update = False
+        for (i, j, d) in constraints:
+            s = x[:, i] - x[:, j]
+            r2 = (s * s).sum(-1)
+            d2 = d * d
+            bad = (r2 < lower * d2) | (r2 > upper * d2)
+            if not bad.any():
+                continue
+            any_update = True
+            r0 = xref[:, i] - xref[:, j]
+            g = (d2 - r2) / (2.0 * (inv_m[i] + inv_m[j]) * (s * r0).sum(-1))
+            g = np.where(bad, g, 0.0)[:, None]
+            x[:, i] += g * inv_m[i] * r0
+            x[:, j] -= g * inv_m[j] * r0
+        if not any_update:
+            return
+    raise RuntimeError("oracle SHAKE did not converge")
+
+
+def _rattle_v(x, v, inv_m, constraints, tol):
+    for _ in range(MAX_SHAKE_ITERS):
+        any_update = False
+        for (i, j, d) in constraints:
+            s = x[:, i] - x[:, j]
+            dot = (s * (v[:, i] - v[:, j])).sum(-1)
+            d2 = d * d
+            bad = np.abs(dot) > tol * d2
+            if not bad.any():
+                continue
+            any_update = True
+            g = np.where(bad, -dot / ((inv_m[i] + inv_m[j]) * (s * s).sum(-1)), 0.0)[:, None]
+            v[:, i] += g * inv_m[i] * s
+            v[:, j] -= g * inv_m[j] * s
+        if not any_update:
+            return
+    raise RuntimeError("oracle velocity constraints did not converge")
+
+
+def kinetic_energy(v, masses):
+    return 0.5 * (masses[None, :, None] * v * v).sum((1, 2))
+
+
+def maxwell_boltzmann(x, masses, constraints, kT, seed, gids, step, tol=1e-6):
+    """Context.setVelocitiesToTemperature as used by propagators.py:137-138: v ~ N(0, kT/m), then velocity constraints."""
+    xi = rng.normals(seed, gids, step, len(masses), rng.KIND_MAXWELL_BOLTZMANN)
+    v = np.sqrt(kT / masses)[None, :, None] * xi
+    if constraints:
+        _rattle_v(np.asarray(x, dtype=np.float64), v, 1.0 / masses, constraints, tol)
+    return v
+
+
+def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed, gids, step0, tol=1e-6,
+          randomize_velocities=False, track_works=False, round_fp32=True):
+    """n_steps of "V R O R V".  energy_forces(x) -> (U[P] kJ/mol, F[P,A,3]).
+
+    Returns dict(x, v, u_first, u_last, shadow_work, proposal_work, nan) with energies in kJ/mol; `nan[p]` marks
+    particles whose closing energy was not finite — their (x, v) are reverted to the input, which is what
+    propagators.py:166-186 does with the default n_restart_attempts = 0.
+    """
+    x0 = np.array(x, dtype=np.float64)
+    x = x0.copy()
+    masses = np.asarray(masses, dtype=np.float64)
+    inv_m = 1.0 / masses
+    P, A = x.shape[0], x.shape[1]
+    v0 = np.array(v, dtype=np.float64)  # a reverted move returns the caller's state (propagators.py:184)
+    if randomize_velocities:
+        v = maxwell_boltzmann(x, masses, constraints, kT, seed, gids, step0, tol)
+    v = np.array(v, dtype=np.float64)
+    a = np.exp(-gamma * dt)
+    b = np.sqrt(1.0 - np.exp(-2.0 * gamma * dt))
+    sig = np.sqrt(kT / masses)[None, :, None]
+    h = 0.5 * dt
+    shadow = np.zeros(P)
+    proposal = np.zeros(P)
+    U, F = energy_forces(x)
+    u_first = U.copy()
+    for s in range(n_steps):
+        # V
+        ke0 = kinetic_energy(v, masses) if track_works else None
+        v = v + h * F * inv_m[None, :, None]
+        if constraints:
+            _rattle_v(x, v, inv_m, constraints, tol)
+        if track_works:
+            shadow += kinetic_energy(v, masses) - ke0
+        for half in (0, 1):
+            # R
+            if track_works:
+                e0 = kinetic_energy(v, masses) + (U if half == 0 else U_mid)
+            xref = x.copy()
+            x = x + h * v
+            x1 = x.copy()
+            if constraints:
+                _shake(x, xref, inv_m, constraints, tol)
+                v = v + (x - x1) / h
+                _rattle_v(x, v, inv_m, constraints, tol)
+            if half == 1 and s == n_steps - 1 and round_fp32:
+                x = x.astype(np.float32).astype(np.float64)
+            if track_works or half == 1:
+                if half == 0:
+                    U_mid = energy_forces(x)[0]
+                else:
+                    U, F = energy_forces(x)
+            if track_works:
+                shadow += kinetic_energy(v, masses) + (U_mid if half == 0 else U) - e0
+            if half == 0:
+                # O
+                ke0 = kinetic_energy(v, masses) if track_works else None
+                xi = rng.normals(seed, gids, step0 + s, A, rng.KIND_O_STEP)
+                v = a * v + b * sig * xi
+                if constraints:
+                    _rattle_v(x, v, inv_m, constraints, tol)
+                if track_works:
+                    proposal -= kinetic_energy(v, masses) - ke0
+        # closing V
+        ke0 = kinetic_energy(v, masses) if track_works else None
+        v = v + h * F * inv_m[None, :, None]
+        if constraints:
+            _rattle_v(x, v, inv_m, constraints, tol)
+        if track_works:
+            shadow += kinetic_energy(v, masses) - ke0
+    u_last = U.copy()
+    nan = ~np.isfinite(u_last) if n_steps > 0 else np.zeros(P, dtype=bool)
+    if nan.any():
+        x[nan] = x0[nan]
+        v[nan] = v0[nan]
+    if round_fp32:
+        v = v.astype(np.float32).astype(np.float64)
+    return dict(x=x, v=v, u_first=u_first, u_last=u_last, shadow_work=shadow, proposal_work=proposal, nan=nan)

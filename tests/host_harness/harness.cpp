@@ -1,0 +1,121 @@
+// harness.cpp — TEST-ONLY host build of the per-replica device algorithm (cdw_replica.cuh compiled by g++ with the
+// lane loops run sequentially).  It lets the CPU test-suite check lambda lowering, term energies/forces, the
+// scratch-slot force gather, SHAKE/RATTLE, BAOAB and the Philox/det_exp/fixed-point helpers against the fp64 oracle
+// on the build host, where there is no GPU.  It is NOT part of the product: coddiwomple_b200 never loads it and has
+// no CPU fallback.
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../coddiwomple_b200/csrc/cdw_pack.h"
+#include "../../coddiwomple_b200/csrc/cdw_replica.cuh"
+
+using namespace cdw;
+
+struct hh_system {
+    std::vector<unsigned char> blob;
+    SysDev dev;
+};
+
+static std::string g_err;
+
+extern "C" const char* hh_last_error() { return g_err.c_str(); }
+
+extern "C" int hh_system_create(const cdw_system_desc* d, hh_system** out) {
+    hh_system* s = new hh_system();
+    int rc = pack_system(d, s->blob, s->dev, g_err);
+    if (rc != CDW_OK) {
+        delete s;
+        return rc;
+    }
+    rebase_system(s->dev, s->blob.data());
+    *out = s;
+    return CDW_OK;
+}
+
+extern "C" int hh_system_destroy(hh_system* s) {
+    delete s;
+    return 0;
+}
+
+extern "C" int hh_system_info(const hh_system* s, int* n_slots, int* n_clusters, size_t* smem_energy, size_t* smem_step) {
+    *n_slots = s->dev.n_slots;
+    *n_clusters = s->dev.n_clusters;
+    *smem_energy = make_layout(s->dev, false, kWarps).total;
+    *smem_step = make_layout(s->dev, true, kWarps).total;
+    return 0;
+}
+
+static int run(const hh_system* s, PropArgs& a, bool forces) {
+    const Layout L = make_layout(s->dev, forces, 1);
+    std::vector<unsigned char> smem(L.total + 64, 0);
+    unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));
+    const Tables T = table_pointers(L, base);
+    build_tables(s->dev, T, a.lambda, forces ? a.kT : 1.0, forces);
+    const WarpMem W = warp_pointers(L, base, 0);
+    unsigned long long mn = ~0ull;
+    for (long long p = 0; p < a.n; ++p) {
+        if (forces) {
+            unsigned long long k = replica_step(s->dev, T, W, L.ns_pad, a, p);
+            mn = k < mn ? k : mn;
+        } else {
+            replica_potential(s->dev, T, W, a, p);
+        }
+    }
+    if (forces && a.wmin_key && mn < *a.wmin_key) *a.wmin_key = mn;
+    return 0;
+}
+
+extern "C" int hh_reduced_potential(const hh_system* s, const float* pos, int64_t n, const double* lambda, double beta, double* u_out) {
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.beta = beta; a.energy_out = u_out;
+    return run(s, a, false);
+}
+
+extern "C" int hh_energy_forces(const hh_system* s, const float* pos, int64_t n, const double* lambda, double* energy_out, float* force_out) {
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.kT = 1.0; a.tol = 1e-6;
+    a.energy_out = energy_out; a.force_out = (float4*)force_out;
+    return run(s, a, true);
+}
+
+extern "C" int hh_smc_propagate(const hh_system* s, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out, int64_t n,
+                                const int32_t* anc, const double* aux_in, const double* cum_in, const int32_t* label_in, const double* lambda,
+                                const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
+                                double* aux_out, int32_t* label_out, double* u_first_out, double* u_last_out, double* shadow_out,
+                                double* proposal_out, int32_t* nan_flags, uint64_t* wmin_key) {
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out;
+    a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.label_in = label_in; a.lambda = lambda;
+    a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
+    a.seed = seed; a.step0 = step0; a.gid0 = gid0;
+    a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
+    a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
+    return run(s, a, true);
+}
+
+extern "C" void hh_det_exp(const double* x, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = det_exp(x[i]);
+}
+
+extern "C" void hh_fixed_target(const double* u, int64_t n, uint64_t total, uint64_t* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = fixed_target(u[i], total);
+}
+
+extern "C" void hh_ordered_key(const double* x, int64_t n, uint64_t* key, double* back) {
+    for (int64_t i = 0; i < n; ++i) {
+        key[i] = ordered_key(x[i]);
+        back[i] = ordered_key_inverse(key[i]);
+    }
+}
+
+extern "C" void hh_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4) {
+    u4 c; c.x = c0; c.y = c1; c.z = c2; c.w = c3;
+    u4 r = philox4x32_10(c, k0, k1);
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+
+extern "C" void hh_normals(uint64_t seed, uint64_t gid, uint32_t step, uint32_t atom, uint32_t kind, double* out3) {
+    normals3(seed, gid, step, atom, kind, out3[0], out3[1], out3[2]);
+}
