@@ -1,0 +1,314 @@
+"""Device-resident SMC state and the fused annealing loop.
+
+This is the B200 replacement for the body of the reference's hot loop
+(`mcmc_smc_resampler`, coddiwomple/openmm/coddiwomple.py:312-331): where the reference walks a Python list of
+`Particle` objects and calls OpenMM once per particle, all particles live on the GPU as struct-of-arrays and every
+iteration is a fixed sequence of kernel launches on one stream with no host synchronisation (the resampling
+decision nESS <= threshold is taken on the device).  PyTorch is used for allocation, streams and
+`torch.distributed` only; all arithmetic is in libcdw_b200.so (include/cdw.h).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .system import SystemSpec, kT_in_md_units, spec_from_xml
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.CdwError("coddiwomple_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class DeviceSystem:
+    """One replica's force field on the device (cdw_system handle). Replaces the OpenMM Context of
+    OpenMMPDFState (coddiwomple/openmm/states.py:84-86)."""
+
+    def __init__(self, system):
+        _require_cuda()
+        if isinstance(system, DeviceSystem):
+            raise TypeError("already a DeviceSystem")
+        self.spec = as_spec(system)
+        self.lib = _lib.load()
+        desc, keep = _lib.make_desc(self.spec)
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.cdw_system_create(C.byref(desc), C.byref(self.handle)), "cdw_system_create")
+        del keep
+        self.n_atoms = self.spec.n_atoms
+        self.n_lambda = self.spec.n_lambda
+
+    def lambda_table(self, parameter_sequence, device="cuda"):
+        """[T][n_lambda] fp64 device table for a list of {name: value} dicts (reference: parameter_sequence)."""
+        rows = [self.spec.lambda_vector(p) for p in parameter_sequence]
+        return torch.from_numpy(np.stack(rows)).to(device)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.cdw_system_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def as_spec(system):
+    """Accept a SystemSpec, an OpenMM System XML string, or (when OpenMM is installed) an openmm.System."""
+    if isinstance(system, SystemSpec):
+        return system
+    if isinstance(system, str):
+        return spec_from_xml(system)
+    if hasattr(system, "spec") and isinstance(system.spec, SystemSpec):
+        return system.spec
+    try:  # an openmm.System object: serialise it (cannot be exercised where OpenMM is absent)
+        try:
+            from openmm import XmlSerializer
+        except ImportError:
+            from simtk.openmm import XmlSerializer
+        return spec_from_xml(XmlSerializer.serialize(system))
+    except ImportError as e:
+        raise TypeError(f"cannot interpret {type(system)} as a system: pass OpenMM System XML or a SystemSpec") from e
+
+
+def positions_to_rows(positions, device="cuda", pinned=False):
+    """(P, A, 3) host array (nm) -> (P, A, 4) float32 rows."""
+    x = np.asarray(positions, dtype=np.float32)
+    if x.ndim == 2:
+        x = x[None]
+    rows = torch.zeros(x.shape[0], x.shape[1], 4, dtype=torch.float32, pin_memory=pinned)
+    rows[..., :3] = torch.from_numpy(np.ascontiguousarray(x))
+    return rows.to(device, non_blocking=pinned) if device is not None else rows
+
+
+class LangevinParameters:
+    """OMMLI's numbers in MD units (coddiwomple/openmm/integrators.py:75-131, 147-169)."""
+
+    def __init__(self, temperature=300.0, collision_rate=1.0, timestep=0.002, constraint_tolerance=1e-6, n_steps=1):
+        self.temperature = float(temperature)
+        self.collision_rate = float(collision_rate)
+        self.timestep = float(timestep)
+        self.constraint_tolerance = float(constraint_tolerance)
+        self.n_steps = int(n_steps)
+
+    @property
+    def kT(self):
+        return kT_in_md_units(self.temperature)
+
+    def as_struct(self, flags=0, n_steps=None):
+        return _lib.LangevinParams(self.timestep, self.collision_rate, self.kT, self.constraint_tolerance,
+                                   self.n_steps if n_steps is None else int(n_steps), int(flags))
+
+
+class ParticleEnsemble:
+    """All particles of one SMC run (or one rank's shard of them) as device-resident struct-of-arrays.
+
+    Mirrors the per-particle fields of `Particle` (coddiwomple/particles.py:11-53): cumulative_work -> cum[P],
+    auxiliary_work -> aux[P], ancestry[-1] -> label[P], state -> pos/vel[P][A] float4 rows, iteration -> scalar.
+    pos/vel/aux/label are double-buffered: the resampling copy of the reference (resamplers.py:123-129) is the
+    gather-on-load of the next propagate call.
+    """
+
+    def __init__(self, system, n_particles, gid0=0, device=None, record_history=False):
+        _require_cuda()
+        self.system = system if isinstance(system, DeviceSystem) else DeviceSystem(system)
+        self.lib = self.system.lib
+        self.P = int(n_particles)
+        self.A = self.system.n_atoms
+        self.gid0 = int(gid0)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        d, P, A = self.device, self.P, self.A
+        self.pos = torch.zeros(2, P, A, 4, dtype=torch.float32, device=d)
+        self.vel = torch.zeros(2, P, A, 4, dtype=torch.float32, device=d)
+        self.aux = torch.zeros(2, P, dtype=torch.float64, device=d)
+        self.label = torch.arange(P, dtype=torch.int32, device=d).repeat(2, 1) + self.gid0
+        self.cum = torch.zeros(P, dtype=torch.float64, device=d)
+        self.inc = torch.zeros(P, dtype=torch.float64, device=d)
+        self.W = torch.zeros(P, dtype=torch.float64, device=d)
+        self.anc = torch.arange(P, dtype=torch.int32, device=d)
+        self.nan_flags = torch.zeros(P, dtype=torch.int32, device=d)
+        self.wmin_key = torch.zeros(1, dtype=torch.int64, device=d)
+        self.uniforms = torch.zeros(max(P, 1), dtype=torch.float64, device=d)
+        self.cdf = torch.zeros(P, dtype=torch.int64, device=d)
+        self.ws_bytes = int(self.lib.cdw_weight_workspace_bytes(P))
+        self.workspace = torch.zeros((self.ws_bytes + 7) // 8, dtype=torch.int64, device=d)
+        self.cur = 0
+        self.pending_gather = False  # anc has not been applied to (pos, vel, aux, label) yet
+        self.iteration = 0
+        self.record_history = record_history
+        self.history = []
+
+    # ------------------------------------------------------------------ state access
+    def set_positions(self, positions, velocities=None):
+        rows = positions if torch.is_tensor(positions) else positions_to_rows(positions, self.device)
+        assert tuple(rows.shape) == (self.P, self.A, 4), rows.shape
+        self.pos[self.cur].copy_(rows, non_blocking=True)
+        if velocities is not None:
+            vrows = velocities if torch.is_tensor(velocities) else positions_to_rows(velocities, self.device)
+            self.vel[self.cur].copy_(vrows, non_blocking=True)
+        else:
+            self.vel[self.cur].zero_()
+        self.pending_gather = False
+
+    def materialize(self):
+        """Apply a pending resampling gather (K3b) so that pos/vel/aux/label hold the resampled particles."""
+        if self.pending_gather:
+            c, n = self.cur, 1 - self.cur
+            _lib.check(self.lib.cdw_gather_particles(_lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.anc), _lib.ptr(self.pos[n]),
+                                                    _lib.ptr(self.vel[n]), _lib.ptr(self.aux[c]), _lib.ptr(self.aux[n]), _lib.ptr(self.label[c]),
+                                                    _lib.ptr(self.label[n]), self.P, self.A, _lib.current_stream()), "cdw_gather_particles")
+            self.cur = n
+            self.pending_gather = False
+
+    @property
+    def positions(self):
+        self.materialize()
+        return self.pos[self.cur][..., :3]
+
+    @property
+    def velocities(self):
+        self.materialize()
+        return self.vel[self.cur][..., :3]
+
+    @property
+    def auxiliary_work(self):
+        self.materialize()
+        return self.aux[self.cur]
+
+    @property
+    def labels(self):
+        self.materialize()
+        return self.label[self.cur]
+
+    # ------------------------------------------------------------------ kernels
+    def reduced_potential(self, lam_row, beta):
+        """K1 on the current positions: u[p] = beta U(x_p; lambda)."""
+        self.materialize()
+        u = torch.empty(self.P, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.cdw_reduced_potential(self.system.handle, _lib.ptr(self.pos[self.cur]), self.P, _lib.ptr(lam_row), float(beta),
+                                                 _lib.ptr(u), _lib.current_stream()), "cdw_reduced_potential")
+        return u
+
+    def equip_initial(self, lam_row, beta):
+        """aux = -u_0(x_0); cum = 0 (ProposalFactory.equip_initial_sample, distribution_factories.py:180-220)."""
+        u0 = self.reduced_potential(lam_row, beta)
+        self.aux[self.cur].copy_(-u0)
+        self.cum.zero_()
+        self.iteration = 0
+        return u0
+
+    def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None):
+        """Fused K3b-on-load + K1 + K4 + first half of K2 (include/cdw.h: cdw_smc_propagate).  Advances `iteration`."""
+        self.iteration += 1
+        c, n = self.cur, 1 - self.cur
+        flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0) | (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
+        prm = langevin.as_struct(flags)
+        self.wmin_key.fill_(-1)  # ~0ull
+        o = outputs or {}
+        anc = self.anc if self.pending_gather else None
+        _lib.check(self.lib.cdw_smc_propagate(
+            self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.pos[n]), _lib.ptr(self.vel[n]), self.P,
+            _lib.ptr(anc), _lib.ptr(self.aux[c]), _lib.ptr(self.cum), _lib.ptr(self.label[c]), _lib.ptr(lam_row), C.byref(prm),
+            C.c_uint64(seed), C.c_uint64(self.iteration * max(langevin.n_steps, 1)), C.c_int64(self.gid0), _lib.ptr(self.inc), _lib.ptr(self.W),
+            _lib.ptr(self.aux[n]), _lib.ptr(self.label[n]), _lib.ptr(o.get("u_first")), _lib.ptr(o.get("u_last")), _lib.ptr(o.get("shadow")),
+            _lib.ptr(o.get("proposal")), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), _lib.current_stream()), "cdw_smc_propagate")
+        self.cur = n
+        self.pending_gather = False
+
+    def weight_stats(self, stats_row, floor_threshold, w=None, wmin_key=None, n=None):
+        """Second half of K2: log-sum-exp, nESS, the resampling decision -> stats_row[8] (device)."""
+        w = self.W if w is None else w
+        _lib.check(self.lib.cdw_weight_stats(_lib.ptr(w), int(w.numel() if n is None else n), float(floor_threshold),
+                                            _lib.ptr(self.wmin_key if wmin_key is None else wmin_key), _lib.ptr(stats_row),
+                                            _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_weight_stats")
+
+    def draw_uniforms(self, seed, stream_id, n):
+        _lib.check(self.lib.cdw_philox_uniforms(C.c_uint64(seed), C.c_uint64(stream_id), int(n), _lib.ptr(self.uniforms), _lib.current_stream()),
+                   "cdw_philox_uniforms")
+
+    def resample(self, stats_row, kind, uniforms=None):
+        """K3a: ancestors from the integer cdf (identity + null update when the decision in stats_row says so)."""
+        u = self.uniforms if uniforms is None else uniforms
+        _lib.check(self.lib.cdw_resample_indices(int(kind), _lib.ptr(self.W), _lib.ptr(u), self.P, _lib.ptr(stats_row), _lib.ptr(self.cum),
+                                                _lib.ptr(self.cum), _lib.ptr(self.anc), _lib.ptr(self.cdf), _lib.ptr(self.workspace), self.ws_bytes,
+                                                _lib.current_stream()), "cdw_resample_indices")
+        self.pending_gather = True
+
+
+RESAMPLER_KINDS = {"multinomial": _lib.CDW_RESAMPLE_MULTINOMIAL, "systematic": _lib.CDW_RESAMPLE_SYSTEMATIC}
+
+
+class SMCEngine:
+    """The whole anneal on one GPU: T-1 iterations of (propagate+weigh, stats, uniforms, resample), no host sync.
+
+    Order of operations = the reference loop (openmm/coddiwomple.py:312-331), see oracle/smc.py for the array form.
+    """
+
+    def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5,
+                 always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None):
+        self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history)
+        self.system = self.ensemble.system
+        self.langevin = langevin or LangevinParameters()
+        self.parameter_sequence = list(parameter_sequence)
+        self.T = len(self.parameter_sequence)
+        self.lam = self.system.lambda_table(self.parameter_sequence, self.ensemble.device)
+        self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
+        self.threshold = -1.0 if always_resample else float(floor_threshold)
+        self.seed, self.resample_seed = int(seed), int(resample_seed)
+        self.stats = torch.zeros(max(self.T, 1), _lib.STATS_LEN, dtype=torch.float64, device=self.ensemble.device)
+        self.graph = None
+
+    @property
+    def beta(self):
+        return 1.0 / self.langevin.kT
+
+    def initialize(self, positions, velocities=None):
+        e = self.ensemble
+        e.set_positions(positions, velocities)
+        e.equip_initial(self.lam[0], self.beta)
+        self.stats.zero_()
+
+    def propagate(self, t):
+        """First kernel of iteration t (1-based): gather-on-load + E/F + incremental work + BAOAB + closing energy."""
+        self.ensemble.propagate_and_weigh(self.lam[t], self.langevin, self.seed, randomize_velocities=(t == 1))
+
+    def finish_iteration(self, t):
+        """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + search, cum update."""
+        e = self.ensemble
+        e.weight_stats(self.stats[t], self.threshold)
+        n_u = e.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
+        e.draw_uniforms(self.resample_seed, t, n_u)
+        e.resample(self.stats[t], self.kind)
+        if e.record_history:
+            e.history.append(dict(t=t, inc=e.inc.clone(), W=e.W.clone(), cum=e.cum.clone(), anc=e.anc.clone(), uniforms=e.uniforms[:n_u].clone()))
+
+    def step(self, t):
+        """Iteration t of the reference loop (openmm/coddiwomple.py:314-328)."""
+        self.propagate(t)
+        self.finish_iteration(t)
+
+    def run(self):
+        for t in range(1, self.T):
+            self.step(t)
+        self.ensemble.materialize()
+        return self
+
+    def anneal(self, positions, velocities=None):
+        self.initialize(positions, velocities)
+        return self.run()
+
+    # ------------------------------------------------------------------ results (host side; these synchronise)
+    def cumulative_works(self):
+        return self.ensemble.cum.cpu().numpy()
+
+    def free_energy(self):
+        """-log mean exp(-cum) in kT."""
+        c = self.ensemble.cum.cpu().numpy()
+        m = (-c).max()
+        return float(-(m + np.log(np.exp(-c - m).sum())) + np.log(c.size))
+
+    def resampled_iterations(self):
+        s = self.stats.cpu().numpy()
+        return [t for t in range(1, self.T) if s[t, _lib.STAT_RESAMPLE] != 0.0]
+
+    def ness_trace(self):
+        return self.stats[1:, _lib.STAT_NESS].cpu().numpy()

@@ -1,0 +1,100 @@
+"""OpenMM Propagator Adapter module — `OMMBIP` with the reference's `apply` signature
+(coddiwomple/openmm/propagators.py:21-261), executed by the fused BAOAB kernel (cdw_baoab)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..engine import positions_to_rows
+from ..propagators import Propagator
+from .states import OpenMMParticleState
+
+
+class OMMBIP(Propagator):
+    """Generalized OpenMM Base Integrator Propagator.
+
+    `apply` keeps the reference's semantics: the particle state is modified in place; `apply_pdf_to_context=True`
+    pushes the pdf_state's current parameters into the propagation "context" (here: a device lambda vector owned by
+    the propagator), False leaves the context's parameters as they were (tests/test_openmm.py:276-281);
+    `returnable_key` selects which accumulated work is returned (default: proposal_work = 0.).
+    Batched form: `apply_batch(pos_rows, vel_rows, ...)` on (P, A, 4) device tensors.
+    """
+
+    def __init__(self, openmm_pdf_state, integrator, context_cache=None, reassign_velocities=False, n_restart_attempts=0, seed=None):
+        super().__init__()
+        self.pdf_state = openmm_pdf_state
+        self.integrator = integrator
+        self.reassign_velocities = reassign_velocities
+        self.n_restart_attempts = n_restart_attempts
+        self.lib = openmm_pdf_state.lib
+        # the propagation context's own copy of the global parameters (openmmtools ContextCache in the reference)
+        self._context_lambda = openmm_pdf_state.lambda_device.clone()
+        self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._step_counter = 0
+        self._gid_counter = 0
+        self.integrator.reset()
+
+    def _get_context_parameters(self):
+        lam = self._context_lambda.cpu().numpy()
+        return {n: float(lam[i]) for i, n in enumerate(self.pdf_state.spec.lambda_names)}
+
+    def _get_global_integrator_variables(self):
+        i = self.integrator
+        return dict(a=i.a, b=i.b, shadow_work=i.shadow_work, proposal_work=i.proposal_work, kT=i.kT)
+
+    def context_reduced_potential(self, particle_state):
+        """beta*U in the propagation context (the reference reads it with context.getState(getEnergy=True))."""
+        rows = positions_to_rows(particle_state.positions[None])
+        u = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.check(self.lib.cdw_reduced_potential(self.pdf_state.device_system.handle, _lib.ptr(rows), 1, _lib.ptr(self._context_lambda),
+                                                 self.pdf_state.beta, _lib.ptr(u), _lib.current_stream()), "cdw_reduced_potential")
+        return float(u.item())
+
+    def apply_batch(self, pos_rows, vel_rows, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, randomize_velocities=False,
+                    track_works=True, gid0=None):
+        """In-place BAOAB on device rows.  Returns dict(u_first, u_last, shadow, proposal, nan) device tensors (kT)."""
+        if reset_integrator:
+            self.integrator.reset()
+        if apply_pdf_to_context:
+            self._context_lambda.copy_(self.pdf_state.lambda_device)
+        P = pos_rows.shape[0]
+        d = pos_rows.device
+        out = dict(u_first=torch.empty(P, dtype=torch.float64, device=d), u_last=torch.empty(P, dtype=torch.float64, device=d),
+                   shadow=torch.zeros(P, dtype=torch.float64, device=d), proposal=torch.zeros(P, dtype=torch.float64, device=d),
+                   nan=torch.zeros(P, dtype=torch.int32, device=d))
+        flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if (randomize_velocities or self.reassign_velocities) else 0) | \
+                (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
+        prm = self.integrator.as_struct(flags, n_steps=n_steps)
+        if gid0 is None:
+            gid0 = self._gid_counter
+        _lib.check(self.lib.cdw_baoab(self.pdf_state.device_system.handle, _lib.ptr(pos_rows), _lib.ptr(vel_rows), P, _lib.ptr(self._context_lambda),
+                                     C.byref(prm), C.c_uint64(self._seed), C.c_uint64(self._step_counter), C.c_int64(gid0), _lib.ptr(out["u_first"]),
+                                     _lib.ptr(out["u_last"]), _lib.ptr(out["shadow"]), _lib.ptr(out["proposal"]), _lib.ptr(out["nan"]),
+                                     _lib.current_stream()), "cdw_baoab")
+        self._step_counter += max(int(n_steps), 1)
+        return out
+
+    def apply(self, particle_state, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, returnable_key=None,
+              randomize_velocities=False, **kwargs):
+        assert isinstance(particle_state, OpenMMParticleState)
+        pos = positions_to_rows(particle_state.positions[None])
+        vel = positions_to_rows(particle_state.velocities[None]) if particle_state.velocities is not None else torch.zeros_like(pos)
+        out = self.apply_batch(pos, vel, n_steps=n_steps, reset_integrator=reset_integrator, apply_pdf_to_context=apply_pdf_to_context,
+                               randomize_velocities=randomize_velocities)
+        if int(out["nan"].item()):
+            import logging
+            logging.getLogger("openmm_propagators").warning("Potential energy is NaN after 0 attempts of integration with move OMMBIP")
+        else:
+            self.integrator.shadow_work += float(out["shadow"].item())
+            self.integrator.proposal_work += float(out["proposal"].item())
+        particle_state.positions = pos[0, :, :3].double().cpu().numpy()
+        particle_state.velocities = vel[0, :, :3].double().cpu().numpy()
+        if returnable_key is not None:
+            try:
+                proposal_work = getattr(self.integrator, f"get_{returnable_key}_work")(dimensionless=True)
+            except Exception as e:
+                raise Exception(f"{e}; the returnable key {returnable_key} is not a valid method in {self.integrator.__class__.__name__}")
+        else:
+            proposal_work = 0.
+        return particle_state, proposal_work

@@ -26,6 +26,12 @@ extern "C" {
 
 #define CDW_VERSION 1
 
+#if defined(__GNUC__)
+#define CDW_API __attribute__((visibility("default")))
+#else
+#define CDW_API
+#endif
+
 #define CDW_OK 0
 #define CDW_EINVAL (-1)   /* bad argument */
 #define CDW_ECUDA (-2)    /* CUDA runtime error (message in cdw_last_error) */
@@ -123,25 +129,25 @@ typedef struct cdw_langevin_params {
 #define CDW_STAT_NNAN 7      /* number of particles whose move was reverted (NaN guard) */
 #define CDW_STATS_LEN 8
 
-int cdw_version(void);
-const char* cdw_last_error(void);
+CDW_API int cdw_version(void);
+CDW_API const char* cdw_last_error(void);
 /* sm_count / compute capability of the current device; fails (CDW_ECUDA) when no CUDA device is usable */
-int cdw_device_info(int* sm_count, int* cc_major, int* cc_minor);
+CDW_API int cdw_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* replaces: OpenMMPDFState.__init__ building the ThermodynamicState + Context (openmm/states.py:50-86) */
-int cdw_system_create(const cdw_system_desc* desc, cdw_system** out);
-int cdw_system_destroy(cdw_system* sys);
-int cdw_system_n_atoms(const cdw_system* sys);
-int cdw_system_n_lambda(const cdw_system* sys);
+CDW_API int cdw_system_create(const cdw_system_desc* desc, cdw_system** out);
+CDW_API int cdw_system_destroy(cdw_system* sys);
+CDW_API int cdw_system_n_atoms(const cdw_system* sys);
+CDW_API int cdw_system_n_lambda(const cdw_system* sys);
 
 /* K1. replaces: OpenMMPDFState.reduced_potential (openmm/states.py:116-136), batched over P replicas.
  * u_out[p] = beta * U(pos[p]; lambda).  lambda: device pointer to n_lambda doubles. */
-int cdw_reduced_potential(const cdw_system* sys, const float* pos, int64_t n_particles, const double* lambda,
+CDW_API int cdw_reduced_potential(const cdw_system* sys, const float* pos, int64_t n_particles, const double* lambda,
                           double beta, double* u_out, cdw_stream stream);
 
 /* energy (kJ/mol) and forces (float4 rows, kJ/mol/nm) — what `f` / `energy` are inside the CustomIntegrator
  * (openmm/integrators.py:301,327); exposed for the Euler-Maruyama proposal and for tests. */
-int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_t n_particles, const double* lambda,
+CDW_API int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_t n_particles, const double* lambda,
                       double* energy_out, float* force_out, cdw_stream stream);
 
 /* K4 (+K3b on load, +K2 first half).  One SMC iteration's per-particle work, fused:
@@ -155,7 +161,7 @@ int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_t n_particl
  * shadow_out, proposal_out (reduced), nan_flags, wmin_key (one uint64, atomically min-ed with the order-preserving
  * key of W; initialise to ~0ull).  Optional inputs: anc, aux_in, cum_in, label_in.
  * Noise counters: particle gid = gid0 + p, step = step0 + s. */
-int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
+CDW_API int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
                       int64_t n_particles, const int32_t* anc, const double* aux_in, const double* cum_in,
                       const int32_t* label_in, const double* lambda, const cdw_langevin_params* params, uint64_t seed,
                       uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out, int32_t* label_out,
@@ -163,7 +169,7 @@ int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* v
                       int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream);
 
 /* replaces: OMMBIP.apply (openmm/propagators.py:89-219) for a batch, in place.  Thin wrapper over the kernel above. */
-int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_particles, const double* lambda,
+CDW_API int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_particles, const double* lambda,
               const cdw_langevin_params* params, uint64_t seed, uint64_t step0, int64_t gid0, double* u_first_out,
               double* u_last_out, double* shadow_out, double* proposal_out, int32_t* nan_flags, cdw_stream stream);
 
@@ -172,10 +178,10 @@ int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_particles
  * cdw_weight_update: inc[p] = u_new[p] + aux[p] (+ proposal[p] if not NULL); w_out[p] = cum[p] + inc[p]; min W -> wmin_key.
  * cdw_weight_stats : second pass over W: sum e, sum e^2, integer total; the last block finalises stats[] including
  *                    the resampling decision (threshold < 0: always resample, as observable=None does). */
-int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
+CDW_API int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
                       double* inc_out, double* w_out, uint64_t* wmin_key, cdw_stream stream);
-size_t cdw_weight_workspace_bytes(int64_t n);
-int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
+CDW_API size_t cdw_weight_workspace_bytes(int64_t n);
+CDW_API int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
                      void* workspace, size_t workspace_bytes, cdw_stream stream);
 
 /* K3a. replaces: MultinomialResampler._resample (resamplers.py:254-272); systematic is new.
@@ -183,34 +189,34 @@ int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const u
  * uniforms: n doubles in [0,1) (multinomial) or 1 double (systematic).  If stats[CDW_STAT_RESAMPLE] == 0 the kernels
  * write the identity ancestors and cum_out = W (the null update, resamplers.py:136-156); otherwise
  * cum_out[p] = cum_in[p] + (mean - cum_in[p]) (resamplers.py:196-197). */
-int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats,
+CDW_API int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats,
                          const double* cum_in, double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace,
                          size_t workspace_bytes, cdw_stream stream);
 
 /* K3b. replaces: the per-particle deepcopy loop of Resampler.resample (resamplers.py:123-129,193). */
-int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
+CDW_API int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
                          const double* aux_in, double* aux_out, const int32_t* label_in, int32_t* label_out,
                          int64_t n_particles, int32_t n_atoms, cdw_stream stream);
 
 /* multi-GPU variant of K3b: anc holds GLOBAL ancestor ids; rank r owns [r*n_per_rank, (r+1)*n_per_rank);
  * peer_pos/peer_vel/peer_aux/peer_label: device arrays of n_ranks base pointers (peer-mapped via CUDA IPC). */
-int cdw_gather_particles_peer(const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
+CDW_API int cdw_gather_particles_peer(const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
                               const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, const int32_t* anc,
                               float* pos_out, float* vel_out, double* aux_out, int32_t* label_out, int64_t n_local,
                               int32_t n_atoms, cdw_stream stream);
 
 /* utilities */
-int cdw_fill_u64(uint64_t* ptr, uint64_t value, int64_t n, cdw_stream stream);
+CDW_API int cdw_fill_u64(uint64_t* ptr, uint64_t value, int64_t n, cdw_stream stream);
 /* Philox uniforms with 53 random bits (same stream as oracle/rng.py:uniforms53) */
-int cdw_philox_uniforms(uint64_t seed, uint64_t stream_id, int64_t n, double* out, cdw_stream stream);
+CDW_API int cdw_philox_uniforms(uint64_t seed, uint64_t stream_id, int64_t n, double* out, cdw_stream stream);
 /* CUDA IPC plumbing for the peer gather (handles are 64 opaque bytes) */
-int cdw_ipc_get_handle(const void* dev_ptr, void* handle64_host);
-int cdw_ipc_open_handle(const void* handle64_host, void** dev_ptr_out);
-int cdw_ipc_close_handle(void* dev_ptr);
-int cdw_device_malloc(size_t bytes, void** out);
-int cdw_device_free(void* ptr);
+CDW_API int cdw_ipc_get_handle(const void* dev_ptr, void* handle64_host);
+CDW_API int cdw_ipc_open_handle(const void* handle64_host, void** dev_ptr_out);
+CDW_API int cdw_ipc_close_handle(void* dev_ptr);
+CDW_API int cdw_device_malloc(size_t bytes, void** out);
+CDW_API int cdw_device_free(void* ptr);
 /* FP64 / FP32 FMA-pipe micro-benchmark used for the roofline denominator: returns achieved TFLOP/s */
-int cdw_fma_peak(int fp64, int iters, double* tflops_out, double* ms_out);
+CDW_API int cdw_fma_peak(int fp64, int iters, double* tflops_out, double* ms_out);
 
 #ifdef __cplusplus
 }

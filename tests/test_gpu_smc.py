@@ -1,0 +1,229 @@
+"""The fused annealing loop and the reference-facing API on the GPU: bookkeeping exactness against the oracle,
+free-energy anchors of the reference, and the behavioural checks of coddiwomple/tests/test_openmm.py re-expressed."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from coddiwomple_b200 import _lib, testsystems as ts  # noqa: E402
+from oracle import smc as oracle_smc, weights  # noqa: E402
+from oracle.potential import XmlSystemOracle, kT_kj_per_mol  # noqa: E402
+from tests.helpers import GOLDEN, cache_frames, generic_layer, system_xml  # noqa: E402
+
+kT = kT_kj_per_mol()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("the -m gpu tests need a CUDA device: there is no CPU fallback to test")
+
+
+def _engine(xml, P, seq, **kw):
+    from coddiwomple_b200.engine import SMCEngine
+    return SMCEngine(xml, P, seq, **kw)
+
+
+def test_every_iteration_obeys_the_reference_bookkeeping():
+    """Record W, uniforms, ancestors and cum at every iteration of a GPU anneal and replay each iteration through the
+    oracle's restatement of Resampler.resample (resamplers.py:61-133): ancestors bit-exact, works to 1e-12."""
+    from coddiwomple_b200.engine import LangevinParameters
+    frames = cache_frames()
+    x0 = frames[np.random.RandomState(0).randint(0, len(frames), 512)]
+    seq = ts.relative_alchemical_sequence(12)
+    for kind in ("multinomial", "systematic"):
+        eng = _engine(system_xml("fluorobenzene"), 512, seq, langevin=LangevinParameters(timestep=0.002), resampler=kind, seed=3, resample_seed=4,
+                      record_history=True, floor_threshold=0.9)
+        eng.anneal(x0)
+        cum_prev = np.zeros(512)
+        stats = eng.stats.cpu().numpy()
+        n_resampled = 0
+        for h in eng.ensemble.history:
+            t = h["t"]
+            inc, W, cum, anc, u = (h[k].cpu().numpy() for k in ("inc", "W", "cum", "anc", "uniforms"))
+            np.testing.assert_array_equal(W, cum_prev + inc)
+            ref = weights.resample_step(cum_prev, inc, np.zeros(512), np.arange(512), uniforms=u, kind=kind, floor_threshold=0.9)
+            assert stats[t, _lib.STAT_NESS] == pytest.approx(ref["nESS"], rel=1e-12)
+            assert bool(stats[t, _lib.STAT_RESAMPLE]) == ref["resampled"]
+            np.testing.assert_array_equal(anc, ref["ancestors"])
+            np.testing.assert_allclose(cum, ref["cum"], rtol=1e-12, atol=1e-12)
+            n_resampled += ref["resampled"]
+            cum_prev = cum
+        assert n_resampled >= 1 and eng.resampled_iterations() == [h["t"] for h in eng.ensemble.history if stats[h["t"], _lib.STAT_RESAMPLE]]
+
+
+def test_first_iterations_track_the_oracle_anneal():
+    """Same inputs, same Philox counters: the GPU anneal and the oracle anneal agree on the incremental works of the
+    first iterations (later ones drift apart at the 1e-6 level of the fp32 coordinates, then through resampling)."""
+    frames = cache_frames()
+    x0 = frames[np.random.RandomState(1).randint(0, len(frames), 128)]
+    seq = ts.relative_alchemical_sequence(6)
+    eng = _engine(system_xml("fluorobenzene"), 128, seq, seed=5, resample_seed=6, record_history=True)
+    eng.anneal(x0)
+    trace = []
+    out = oracle_smc.anneal(XmlSystemOracle(system_xml("fluorobenzene")), x0, seq, seed=5, resample_seed=6, trace=trace)
+    h = eng.ensemble.history
+    np.testing.assert_allclose(h[0]["inc"].cpu().numpy(), trace[0]["inc"], rtol=1e-10)
+    np.testing.assert_array_equal(h[0]["anc"].cpu().numpy(), trace[0]["ancestors"])
+    if not trace[0]["resampled"]:
+        np.testing.assert_allclose(h[1]["inc"].cpu().numpy(), trace[1]["inc"], atol=1e-4)
+    assert abs(eng.free_energy() - out["free_energy"]) < 0.05
+
+
+def test_harmonic_oscillator_free_energy_is_one_kT():
+    """G6: x0 0 -> 2 sigma, U0 0 -> 1 kT gives Delta F = 1 kT exactly (coddiwomple/tests/utils.py:63-67); config 1."""
+    from coddiwomple_b200.engine import LangevinParameters
+    prm = ts.harmonic_oscillator_parameters()
+    x0 = np.random.RandomState(0).normal(0, prm["sigma"], (20000, 1, 3)).astype(np.float32)
+    for kind in ("multinomial", "systematic"):
+        eng = _engine(ts.harmonic_oscillator_xml(), 20000, ts.harmonic_parameter_sequence(21),
+                      langevin=LangevinParameters(timestep=prm["timestep"], collision_rate=prm["collision_rate"], n_steps=5), resampler=kind, seed=1, resample_seed=2)
+        eng.anneal(x0)
+        assert abs(eng.free_energy() - 1.0) < 0.03, eng.free_energy()
+        assert int(eng.ensemble.nan_flags.sum()) == 0
+
+
+def test_fluorobenzene_free_energy_band_of_the_reference():
+    """G5: 1.33 +- 0.2 kT for benzene -> fluorobenzene, 10 lambdas, 1 step per lambda (legacy_tests.py:90-94)."""
+    frames = cache_frames()
+    x0 = frames[np.random.RandomState(3).randint(0, len(frames), 4000)]
+    eng = _engine(system_xml("fluorobenzene"), 4000, ts.relative_alchemical_sequence(10), seed=11, resample_seed=12)
+    eng.anneal(x0)
+    assert abs(eng.free_energy() - 1.33) < 0.2, eng.free_energy()
+    x = eng.ensemble.positions.double().cpu().numpy()
+    o = XmlSystemOracle(system_xml("fluorobenzene"))
+    for (i, j, d) in o.constraints:   # particles stay on the constraint manifold through propagation and resampling
+        assert np.abs(np.linalg.norm(x[:, i] - x[:, j], axis=-1) / d - 1).max() < 5e-6
+    # aux carried with the resampled state is -u_T(x_T) (openmm/coddiwomple.py:326-327)
+    u = o.reduced_potential(x, ts.relative_alchemical_sequence(10)[-1])
+    np.testing.assert_allclose(eng.ensemble.auxiliary_work.cpu().numpy(), -u, rtol=1e-9)
+
+
+def test_mcmc_smc_resampler_signature_and_result():
+    """coddiwomple/tests/legacy_tests.py:52-95 re-expressed: same call, same assertions."""
+    from coddiwomple_b200.openmm.coddiwomple import mcmc_smc_resampler
+    import os
+    lambda_sequence = ts.relative_alchemical_sequence(10)
+    np.random.seed(0)
+    particles = mcmc_smc_resampler(system=system_xml("fluorobenzene"), endstate_cache_filename=os.path.join(GOLDEN, "fluorobenzene_cache.npy"),
+                                   directory_name=None, trajectory_prefix=None, md_topology=None, number_of_particles=10,
+                                   parameter_sequence=lambda_sequence)
+    assert len(particles) == 10
+    assert all(particle.iteration == 9 for particle in particles)
+    assert all(np.isfinite(particle.cumulative_work) for particle in particles)
+    np.random.seed(1)
+    particles = mcmc_smc_resampler(system_xml("fluorobenzene"), os.path.join(GOLDEN, "fluorobenzene_cache.npy"), None, None, None, 3000, lambda_sequence)
+    average_free_energy = np.mean([particle.cumulative_work for particle in particles[:50]])  # all equal after a final resample
+    fe = particles.engine.free_energy()
+    assert (1.33 - 0.2) / 1.33 < fe / 1.33 < (1.33 + 0.2) / 1.33
+    assert np.isfinite(average_free_energy)
+    p = particles[0]
+    assert p.state.positions.shape == (13, 3) and p.ancestry[0] == 0 and len(p.proposal_works) == 10
+
+
+def test_OpenMMPDFState_contract():
+    """coddiwomple/tests/test_openmm.py:24-59."""
+    from coddiwomple_b200.openmm.states import HarmonicAlchemicalState, OpenMMParticleState, OpenMMPDFState
+    pdf_state = OpenMMPDFState(system=ts.harmonic_oscillator_xml(), alchemical_composability=HarmonicAlchemicalState, temperature=300.0, pressure=None)
+    assert set(pdf_state.get_parameters()) == {f"{ts.HO_PREFIX}_x0", f"{ts.HO_PREFIX}_U0"}
+    pdf_state.set_parameters({f"{ts.HO_PREFIX}_x0": 1.0, f"{ts.HO_PREFIX}_U0": 1.0})
+    assert pdf_state.get_parameters() == {f"{ts.HO_PREFIX}_x0": 1.0, f"{ts.HO_PREFIX}_U0": 1.0}
+    with pytest.raises(AssertionError):
+        pdf_state.set_parameters({f"{ts.HO_PREFIX}_x0": 1.0})
+    state = OpenMMParticleState(positions=np.zeros((1, 3)))
+    K = ts.harmonic_oscillator_parameters()["K"]
+    assert pdf_state.reduced_potential(state) == pytest.approx((0.5 * K * 1.0 + 1.0) / kT, rel=1e-12)
+    with pytest.raises(NotImplementedError):
+        OpenMMPDFState(system=ts.harmonic_oscillator_xml(), pressure=1.0)
+
+
+def test_OMMLI_and_OMMBIP_contract():
+    """coddiwomple/tests/test_openmm.py:157-288 re-expressed on the harmonic test system."""
+    from coddiwomple_b200.openmm.integrators import OMMLI
+    from coddiwomple_b200.openmm.propagators import OMMBIP
+    from coddiwomple_b200.openmm.states import HarmonicAlchemicalState, OpenMMParticleState, OpenMMPDFState
+    prm = ts.harmonic_oscillator_parameters()
+    pdf_state = OpenMMPDFState(system=ts.harmonic_oscillator_xml(), alchemical_composability=HarmonicAlchemicalState, temperature=300.0, pressure=None)
+    integrator = OMMLI(temperature=300.0, collision_rate=prm["collision_rate"], timestep=prm["timestep"])
+    propagator = OMMBIP(openmm_pdf_state=pdf_state, integrator=integrator, seed=4)
+    assert propagator.pdf_state is pdf_state                       # :260 "VERY important for SMC"
+    particle_state = OpenMMParticleState(positions=np.zeros((1, 3)))
+    # null application (:264-268)
+    prior = pdf_state.reduced_potential(particle_state)
+    _, proposal_work = propagator.apply(particle_state, n_steps=0)
+    assert proposal_work == 0. and pdf_state.reduced_potential(particle_state) == prior
+    assert propagator.context_reduced_potential(particle_state) == pytest.approx(prior)
+    # context update internals (:271-281)
+    parameters = pdf_state.get_parameters()
+    parameters[f"{ts.HO_PREFIX}_U0"] = 1.
+    pdf_state.set_parameters(parameters)
+    propagator.apply(particle_state, n_steps=0, apply_pdf_to_context=False)
+    assert propagator._get_context_parameters()[f"{ts.HO_PREFIX}_U0"] == 0.
+    assert propagator.context_reduced_potential(particle_state) == pytest.approx(prior)
+    propagator.apply(particle_state, n_steps=0, apply_pdf_to_context=True)
+    assert propagator._get_context_parameters()[f"{ts.HO_PREFIX}_U0"] == 1.
+    assert propagator.context_reduced_potential(particle_state) == pytest.approx(prior + 1.0 / kT, rel=1e-12)
+    parameters[f"{ts.HO_PREFIX}_U0"] = 0.
+    pdf_state.set_parameters(parameters)
+    propagator.apply(particle_state, n_steps=0, apply_pdf_to_context=True)
+    # equilibrium sampling (:195-221): 100 x 20 steps with velocity re-randomisation
+    reduced_pe = []
+    for _ in range(100):
+        particle_state, proposal_work = propagator.apply(particle_state, n_steps=20, reset_integrator=False, apply_pdf_to_context=False, randomize_velocities=True)
+        assert proposal_work == 0.
+        assert integrator._get_energy_with_units('proposal_work', dimensionless=True) != 0.
+        assert integrator._get_energy_with_units('shadow_work', dimensionless=True) != 0.
+        reduced_pe.append(pdf_state.reduced_potential(particle_state))
+    tol = 6 * np.sqrt(1.5)
+    assert 1.5 - tol < np.mean(reduced_pe) < 1.5 + tol
+    assert propagator.apply(particle_state, n_steps=1, returnable_key="proposal")[1] == integrator.get_proposal_work()
+    with pytest.raises(Exception):
+        propagator.apply(particle_state, n_steps=1, returnable_key="nonexistent")
+    integrator.reset()
+    assert integrator._get_energy_with_units('proposal_work', dimensionless=True) == 0.
+    assert integrator._get_energy_with_units('shadow_work', dimensionless=True) == 0.
+    # stability (:288)
+    propagator.apply(particle_state, n_steps=1000, reset_integrator=True, apply_pdf_to_context=True, randomize_velocities=True)
+    assert np.isfinite(particle_state.positions).all()
+    with pytest.raises(NotImplementedError):
+        OMMLI(splitting="O V R V O")
+
+
+def test_batched_equilibrium_statistics_many_particles():
+    """The same G6 check on 20k replicas at once: <u> = 3/2 and std = sqrt(3/2) to ~1 %."""
+    from coddiwomple_b200.openmm.integrators import OMMLI
+    from coddiwomple_b200.openmm.propagators import OMMBIP
+    from coddiwomple_b200.openmm.states import HarmonicAlchemicalState, OpenMMPDFState
+    prm = ts.harmonic_oscillator_parameters()
+    pdf_state = OpenMMPDFState(system=ts.harmonic_oscillator_xml(), alchemical_composability=HarmonicAlchemicalState, pressure=None)
+    prop = OMMBIP(pdf_state, OMMLI(collision_rate=prm["collision_rate"], timestep=prm["timestep"]), seed=7)
+    pos = torch.zeros(20000, 1, 4, device="cuda")
+    vel = torch.zeros_like(pos)
+    prop.apply_batch(pos, vel, n_steps=400, randomize_velocities=True)
+    u = pdf_state.reduced_potential_batch(pos).cpu().numpy()
+    assert abs(u.mean() - 1.5) < 0.03 and abs(u.std() - np.sqrt(1.5)) < 0.04
+
+
+@pytest.mark.parametrize("case", [1, 2, 4])
+def test_Resampler_on_python_particles_matches_the_reference(case):
+    """`MultinomialResampler.resample` on a plain list of `Particle` objects (the reference's own calling convention),
+    under the same global numpy seed the reference consumed: ancestors, labels and aux identical, works to 1e-12."""
+    from coddiwomple_b200.particles import Particle
+    from coddiwomple_b200.resamplers import MultinomialResampler
+    from coddiwomple_b200.utils import nESS, vanilla_floor_threshold
+    c = generic_layer()["cases"][case]
+    P = c["P"]
+    particles = [Particle(index=i) for i in range(P)]
+    for p, cw, a in zip(particles, c["cumulative_works_in"], c["auxiliary_works_in"]):
+        p._cumulative_work, p._auxiliary_work = cw, a
+        p.update_state(("state", p.ancestry[0]))
+    assert nESS(particles, np.array(c["incremental_works"])) == pytest.approx(c["nESS"], rel=1e-12)
+    np.random.seed(1000 + c["seed"])
+    res = MultinomialResampler()
+    res.resample(particles, np.array(c["incremental_works"]), observable=nESS, threshold=vanilla_floor_threshold)
+    assert res.resampling_logger == c["resampling_logger"]
+    np.testing.assert_array_equal([p.state[1] for p in particles], c["after_thresholded"]["state_label"])
+    np.testing.assert_array_equal([p.ancestry[-1] for p in particles], c["after_thresholded"]["ancestry_last"])
+    np.testing.assert_array_equal([p.auxiliary_work for p in particles], c["after_thresholded"]["auxiliary_work"])
+    np.testing.assert_allclose([p.cumulative_work for p in particles], c["after_thresholded"]["cumulative_work"], rtol=1e-12, atol=1e-12)
