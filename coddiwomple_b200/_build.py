@@ -28,18 +28,20 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source into coddiwomple_b200/libcdw_b200.so (sm_100a, -lineinfo)."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA source into coddiwomple_b200/libcdw_b200.so (sm_100a, -lineinfo).
+    `defines`/`out` build tuning variants (e.g. -DCDW_KWARPS=4) next to the default library; CDW_LIB selects one at load."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    target = out or LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
         raise RuntimeError("nvcc failed building libcdw_b200.so")
     if verbose:
         sys.stderr.write(proc.stdout + proc.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcdw_b200.so")
+LIB_PATH = os.environ.get("CDW_LIB") or os.path.join(HERE, "libcdw_b200.so")  # CDW_LIB: a tuning variant built by _build.build(out=...)
 
 CDW_FLAG_RANDOMIZE_VELOCITIES = 1
 CDW_FLAG_TRACK_WORKS = 2

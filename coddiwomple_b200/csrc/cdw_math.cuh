@@ -17,6 +17,12 @@
 
 #define CDW_ONE_4PI_EPS0 138.935456
 
+#if defined(__CUDA_ARCH__)
+#define CDW_RSQRT(x) rsqrt(x)
+#else
+#define CDW_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
 namespace cdw {
 
 struct d3 {
@@ -90,9 +96,10 @@ CDW_HD void lower_softcore(EffPair& e, int cls, const double* par /*sigA,epsA,si
 template <bool F>
 CDW_HD double bond_term(d3 xi, d3 xj, double K, double L, d3& fi) {
     d3 d = xi - xj;
-    double r = sqrt(dot(d, d));
-    double dr = r - L;
-    if (F) fi = (-K * dr / r) * d;
+    double r2 = dot(d, d);
+    double ir = CDW_RSQRT(r2);
+    double dr = r2 * ir - L;
+    if (F) fi = (-K * dr * ir) * d;
     return 0.5 * K * dr * dr;
 }
 
@@ -100,17 +107,17 @@ template <bool F>
 CDW_HD double angle_term(d3 xi, d3 xj, d3 xk, double K, double T0, d3& fi, d3& fk) {
     d3 a = xi - xj, b = xk - xj;
     double a2 = dot(a, a), b2 = dot(b, b);
-    double c = dot(a, b) / sqrt(a2 * b2);
+    double c = dot(a, b) * CDW_RSQRT(a2 * b2);
     c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
     double th = acos(c);
     double dth = th - T0;
     if (F) {
         d3 cp = cross(a, b);
-        double rp = sqrt(dot(cp, cp));
-        rp = rp < 1e-12 ? 1e-12 : rp;
-        double de = K * dth;
-        fi = (de / (a2 * rp)) * cross(cp, a);
-        fk = (de / (b2 * rp)) * cross(b, cp);
+        double cp2 = dot(cp, cp);
+        cp2 = cp2 < 1e-24 ? 1e-24 : cp2;
+        double de = K * dth * CDW_RSQRT(cp2);
+        fi = (de / a2) * cross(cp, a);
+        fk = (de / b2) * cross(b, cp);
     }
     return 0.5 * K * dth * dth;
 }
@@ -122,8 +129,9 @@ CDW_HD double torsion_term(d3 xi, d3 xj, d3 xk, d3 xl, double kk, double c0, dou
     d3 b1 = xj - xi, b2 = xk - xj, b3 = xl - xk;
     d3 n1 = cross(b1, b2), n2 = cross(b2, b3);
     double n1sq = dot(n1, n1), n2sq = dot(n2, n2), b2sq = dot(b2, b2);
-    double rb2 = sqrt(b2sq);
-    double inv = 1.0 / sqrt(n1sq * n2sq);
+    double irb2 = CDW_RSQRT(b2sq);
+    double rb2 = b2sq * irb2;
+    double inv = CDW_RSQRT(n1sq * n2sq);
     double c = dot(n1, n2) * inv;
     double s = dot(b1, n2) * rb2 * inv;
     double cn = 1.0, sn = 0.0;
@@ -136,7 +144,8 @@ CDW_HD double torsion_term(d3 xi, d3 xj, d3 xk, d3 xl, double kk, double c0, dou
         double de = -kk * (double)n * (sn * c0 - cn * s0);  // dE/dphi
         fi = (de * rb2 / n1sq) * n1;
         fl = (-de * rb2 / n2sq) * n2;
-        double sa = dot(b1, b2) / b2sq, ta = dot(b3, b2) / b2sq;
+        double ib2 = irb2 * irb2;
+        double sa = dot(b1, b2) * ib2, ta = dot(b3, b2) * ib2;
         fj = (-1.0 - sa) * fi + ta * fl;
         fk = (-1.0 - ta) * fl + sa * fi;
     }
@@ -147,9 +156,9 @@ CDW_HD double torsion_term(d3 xi, d3 xj, d3 xk, d3 xl, double kk, double c0, dou
 template <bool F>
 CDW_HD double pair_term(const EffPair& p, d3 d, double& g) {
     double r2 = dot(d, d);
-    double ir2 = 1.0 / r2;
-    double r = sqrt(r2);
-    double ir = r * ir2;
+    double ir = CDW_RSQRT(r2);
+    double ir2 = ir * ir;
+    double r = r2 * ir;
     double e = 0.0;
     g = 0.0;
     if (p.flags & CDW_PAIR_NB) {
@@ -303,11 +312,13 @@ CDW_HD void normals3(uint64_t seed, uint64_t gid, uint32_t step, uint32_t atom, 
     z2 = (double)(r1 * cosf(a1));
 }
 
+#define CDW_MAX_DIRECT 3  // constraint clusters up to this size are projected by a direct k x k solve
+
 // Device-resident raw tables of one replica's force field (global memory) + layout of the per-launch shared memory.
 struct SysDev {
     int n_atoms, n_lambda;
     int n_bonds, n_angles, n_torsions, n_pairs, n_ext, n_exceptions, n_cons, n_clusters;
-    int n_atom_off, n_exc_off;
+    int n_atom_off, n_exc_off, n_coef;
     int slot_core, slot_insert, slot_delete, slot_alpha;
     int n_slots;       // force-scratch slots
     int a_pad;         // n_atoms rounded up to even (16 B alignment of double rows)
@@ -328,6 +339,8 @@ struct SysDev {
     const int* ext_atom; const int* ext_slot; const double* ext_par;
     // constraints grouped into clusters (connected components); one lane owns one cluster
     const int* cluster_start;   // [n_clusters+1]
+    const int* cluster_coef_start;  // [n_clusters+1]: offset of the k x k coupling coefficients (k <= CDW_MAX_DIRECT), else -1
+    const double* cluster_coef;     // c_qr = d(iq,ir)/m_ir - d(iq,jr)/m_jr - d(jq,ir)/m_ir + d(jq,jr)/m_jr
     const int* cons_atoms;      // [n_cons][2], sorted by cluster
     const double* cons_d2;      // [n_cons] d^2
     // force gather: atom -> scratch slots

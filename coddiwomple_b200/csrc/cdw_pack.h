@@ -136,6 +136,27 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     }
     const int n_clusters = (int)cluster_start.size();
     cluster_start.push_back((int)cons_d2.size());
+    // coupling coefficients of each small cluster: how a multiplier on constraint r changes the relative velocity /
+    // displacement along constraint q (direct k x k projection instead of Gauss-Seidel sweeps)
+    std::vector<int> cluster_coef_start(n_clusters + 1, 0);
+    std::vector<double> cluster_coef;
+    for (int c = 0; c < n_clusters; ++c) {
+        const int q0 = cluster_start[c], k = cluster_start[c + 1] - q0;
+        cluster_coef_start[c] = (int)cluster_coef.size();
+        if (k > CDW_MAX_DIRECT) continue;
+        for (int q = 0; q < k; ++q)
+            for (int r = 0; r < k; ++r) {
+                const int iq = cons_atoms[2 * (q0 + q)], jq = cons_atoms[2 * (q0 + q) + 1];
+                const int ir = cons_atoms[2 * (q0 + r)], jr = cons_atoms[2 * (q0 + r) + 1];
+                double cf = 0.0;
+                if (iq == ir) cf += 1.0 / d->masses[ir];
+                if (iq == jr) cf -= 1.0 / d->masses[jr];
+                if (jq == ir) cf -= 1.0 / d->masses[ir];
+                if (jq == jr) cf += 1.0 / d->masses[jr];
+                cluster_coef.push_back(cf);
+            }
+    }
+    cluster_coef_start[n_clusters] = (int)cluster_coef.size();
 
     // ---- force scratch slots: slot(type, pos, idx) = base(type) + pos * n_type + idx; CSR atom -> slots
     const int nb = d->n_bonds, na = d->n_angles, nt = d->n_torsions, np = d->n_pairs, ne = d->n_ext;
@@ -175,6 +196,7 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
            o_pp = pk.add(vec(d->pair_sc_par, 4 * np));
     size_t o_ea = pk.add(vec(d->ext_atom, ne)), o_es = pk.add(vec(d->ext_slot, 3 * ne)), o_epar = pk.add(vec(d->ext_par, 6 * ne));
     size_t o_cs = pk.add(cluster_start), o_ca = pk.add(cons_atoms), o_cd = pk.add(cons_d2);
+    size_t o_ccs = pk.add(cluster_coef_start), o_cc = pk.add(cluster_coef);
     size_t o_ss = pk.add(atom_slot_start), o_sl = pk.add(atom_slots);
 
 
@@ -182,7 +204,7 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     v.n_atoms = A; v.n_lambda = d->n_lambda;
     v.n_bonds = nb; v.n_angles = na; v.n_torsions = nt; v.n_pairs = np; v.n_ext = ne; v.n_exceptions = d->n_exceptions;
     v.n_cons = d->n_constraints; v.n_clusters = n_clusters;
-    v.n_atom_off = (int)atom_off_slot.size(); v.n_exc_off = (int)exc_off_slot.size();
+    v.n_atom_off = (int)atom_off_slot.size(); v.n_exc_off = (int)exc_off_slot.size(); v.n_coef = (int)cluster_coef.size();
     v.slot_core = d->slot_sterics_core; v.slot_insert = d->slot_sterics_insert; v.slot_delete = d->slot_sterics_delete; v.slot_alpha = d->slot_softcore_alpha;
     v.n_slots = n_slots;
     v.a_pad = (A + 1) & ~1;
@@ -194,6 +216,7 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     v.exc_par = (const double*)(B + o_ep); v.exc_off_start = (const int*)(B + o_eos); v.exc_off_slot = (const int*)(B + o_eosl); v.exc_off_par = (const double*)(B + o_eop);
     v.pair_atoms = (const int*)(B + o_pa); v.pair_nb = (const int*)(B + o_pn); v.pair_sc_class = (const int*)(B + o_pc); v.pair_sc_par = (const double*)(B + o_pp);
     v.ext_atom = (const int*)(B + o_ea); v.ext_slot = (const int*)(B + o_es); v.ext_par = (const double*)(B + o_epar);
+    v.cluster_coef_start = (const int*)(B + o_ccs); v.cluster_coef = (const double*)(B + o_cc);
     v.cluster_start = (const int*)(B + o_cs); v.cons_atoms = (const int*)(B + o_ca); v.cons_d2 = (const double*)(B + o_cd);
     v.atom_slot_start = (const int*)(B + o_ss); v.atom_slots = (const int*)(B + o_sl);
 
@@ -212,6 +235,7 @@ inline void rebase_system(SysDev& v, const unsigned char* base) {
     CDW_RB(exc_par); CDW_RB(exc_off_start); CDW_RB(exc_off_slot); CDW_RB(exc_off_par);
     CDW_RB(pair_atoms); CDW_RB(pair_nb); CDW_RB(pair_sc_class); CDW_RB(pair_sc_par);
     CDW_RB(ext_atom); CDW_RB(ext_slot); CDW_RB(ext_par);
+    CDW_RB(cluster_coef_start); CDW_RB(cluster_coef);
     CDW_RB(cluster_start); CDW_RB(cons_atoms); CDW_RB(cons_d2);
     CDW_RB(atom_slot_start); CDW_RB(atom_slots);
 #undef CDW_RB

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kThreads) reduced_potential_kernel(SysDev s, P
     for (long long p = (long long)blockIdx.x * kWarps + warp; p < a.n; p += (long long)gridDim.x * kWarps) replica_potential(s, T, W, a, p);
 }
 
-__global__ void __launch_bounds__(kThreads) smc_propagate_kernel(SysDev s, PropArgs a) {
+__global__ void __launch_bounds__(kThreads, CDW_MINBLOCKS) smc_propagate_kernel(SysDev s, PropArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long cta_min[kWarps];
     const Layout L = make_layout(s, true, kWarps);
@@ -81,7 +81,9 @@ using namespace cdw;
 
 extern "C" int cdw_reduced_potential(const cdw_system* sys, const float* pos, int64_t n, const double* lambda, double beta,
                                      double* u_out, cdw_stream stream) {
-    CDW_REQUIRE(sys && pos && u_out && n >= 0, "null argument");
+    CDW_REQUIRE(sys && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    CDW_REQUIRE(pos && u_out, "null argument");
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     PropArgs a = {};
     a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.beta = beta; a.energy_out = u_out;
@@ -90,7 +92,9 @@ extern "C" int cdw_reduced_potential(const cdw_system* sys, const float* pos, in
 
 extern "C" int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_t n, const double* lambda, double* energy_out,
                                  float* force_out, cdw_stream stream) {
-    CDW_REQUIRE(sys && pos && n >= 0, "null argument");
+    CDW_REQUIRE(sys && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    CDW_REQUIRE(pos, "null argument");
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     PropArgs a = {};
     a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.kT = 1.0; a.dt = 0.0; a.n_steps = 0; a.tol = 1e-6;
@@ -104,7 +108,9 @@ extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, con
                                  double* inc_out, double* w_out, double* aux_out, int32_t* label_out, double* u_first_out,
                                  double* u_last_out, double* shadow_out, double* proposal_out, int32_t* nan_flags, uint64_t* wmin_key,
                                  cdw_stream stream) {
-    CDW_REQUIRE(sys && pos_in && prm && n >= 0, "null argument");
+    CDW_REQUIRE(sys && prm && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    CDW_REQUIRE(pos_in, "null argument");
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     CDW_REQUIRE(!(anc && (pos_in == pos_out || (vel_in && vel_in == vel_out))), "gather-on-load needs distinct in/out buffers");

@@ -18,11 +18,13 @@
 #define CDW_CTA_THREADS(tid, nt) for (int tid = (int)threadIdx.x, nt = (int)blockDim.x, _cdw_once = 1; _cdw_once; _cdw_once = 0, __syncthreads())
 #define CDW_WARP_SUM(v) cdw::warp_sum_dev(v)
 #define CDW_LDG(p) __ldg(p)
+#define CDW_NOINLINE __device__ __noinline__
 #else
 #define CDW_LANES(lane) for (int lane = 0; lane < 32; ++lane)
 #define CDW_CTA_THREADS(tid, nt) for (int tid = 0, nt = 1; tid < 1; ++tid)
 #define CDW_WARP_SUM(v) (v)
 #define CDW_LDG(p) (*(p))
+#define CDW_NOINLINE inline
 #endif
 #if !defined(__CUDACC__)
 struct alignas(16) float4 {
@@ -41,13 +43,19 @@ __device__ __forceinline__ double warp_sum_dev(double v) {
 }
 #endif
 
-constexpr int kWarps = 4;  // replicas in flight per CTA
+#ifndef CDW_KWARPS
+#define CDW_KWARPS 8
+#endif
+#ifndef CDW_MINBLOCKS
+#define CDW_MINBLOCKS 2
+#endif
+constexpr int kWarps = CDW_KWARPS;  // replicas in flight per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxConstraintIters = 500;
 
 // ------------------------------------------------------------------------------------------------ shared-memory layout
 struct Layout {
-    size_t lam, nbeff, inv_m, sig_v, bonds, angles, torsions, pairs, exts, slot_start, slots, cl_start, cons_atoms, cons_d2;  // CTA-shared
+    size_t lam, nbeff, inv_m, sig_v, bonds, angles, torsions, pairs, exts, slot_start, slots, cl_start, cons_atoms, cons_d2, cl_coef_start, cl_coef;  // CTA-shared
     size_t warp0, warp_stride, x, v, f, xref, fs;                                                                                // per warp
     int ns_pad;
     size_t total;
@@ -73,6 +81,8 @@ CDW_HD Layout make_layout(const SysDev& s, bool forces, int warps) {
     L.cl_start = o; o = align16(o + sizeof(int) * (forces ? s.n_clusters + 1 : 0));
     L.cons_atoms = o; o = align16(o + sizeof(int) * (forces ? 2 * s.n_cons : 0));
     L.cons_d2 = o; o = align16(o + sizeof(double) * (forces ? s.n_cons : 0));
+    L.cl_coef_start = o; o = align16(o + sizeof(int) * (forces ? s.n_clusters + 1 : 0));
+    L.cl_coef = o; o = align16(o + sizeof(double) * (forces ? s.n_coef : 0));
     L.warp0 = o;
     size_t w = 0;
     const size_t row = sizeof(double) * 3 * s.a_pad;
@@ -93,7 +103,7 @@ CDW_HD Layout make_layout(const SysDev& s, bool forces, int warps) {
 struct Tables {  // pointers into the CTA-shared part
     double* lam; double* nbeff; double* inv_m; double* sig_v;
     EffBond* bonds; EffAngle* angles; EffTorsion* torsions; EffPair* pairs; EffExt* exts;
-    int* slot_start; int* slots; int* cl_start; int* cons_atoms; double* cons_d2;
+    int* slot_start; int* slots; int* cl_start; int* cons_atoms; double* cons_d2; int* cl_coef_start; double* cl_coef;
 };
 
 struct WarpMem {  // pointers into one warp's private part
@@ -107,6 +117,7 @@ CDW_HD Tables table_pointers(const Layout& L, unsigned char* smem) {
     T.pairs = (EffPair*)(smem + L.pairs); T.exts = (EffExt*)(smem + L.exts);
     T.slot_start = (int*)(smem + L.slot_start); T.slots = (int*)(smem + L.slots);
     T.cl_start = (int*)(smem + L.cl_start); T.cons_atoms = (int*)(smem + L.cons_atoms); T.cons_d2 = (double*)(smem + L.cons_d2);
+    T.cl_coef_start = (int*)(smem + L.cl_coef_start); T.cl_coef = (double*)(smem + L.cl_coef);
     return T;
 }
 
@@ -173,6 +184,8 @@ CDW_HD void build_tables(const SysDev& s, const Tables& T, const double* lam_g, 
             for (int q = tid; q < s.n_clusters + 1; q += nt) T.cl_start[q] = s.cluster_start[q];
             for (int q = tid; q < 2 * s.n_cons; q += nt) T.cons_atoms[q] = s.cons_atoms[q];
             for (int q = tid; q < s.n_cons; q += nt) T.cons_d2[q] = s.cons_d2[q];
+            for (int q = tid; q < s.n_clusters + 1; q += nt) T.cl_coef_start[q] = s.cluster_coef_start[q];
+            for (int q = tid; q < s.n_coef; q += nt) T.cl_coef[q] = s.cluster_coef[q];
         }
     }
     CDW_CTA_THREADS(tid, nt) {  // nbeff is complete: pair mixing rule / exceptions / soft-core
@@ -282,14 +295,25 @@ CDW_HD double energy_forces(const SysDev& s, const Tables& T, const WarpMem& W, 
 }
 
 // ------------------------------------------------------------------------------------------------ constraints
+struct ConsCtx {  // what the constraint routines need, passed BY VALUE so the noinline calls keep everything in registers
+    const int* cl_start; const int* cons_atoms; const int* cl_coef_start; const double* cl_coef; const double* cons_d2; const double* inv_m;
+    int n_clusters, Ap;
+};
+CDW_HD ConsCtx cons_ctx(const SysDev& s, const Tables& T) {
+    ConsCtx c;
+    c.cl_start = T.cl_start; c.cons_atoms = T.cons_atoms; c.cl_coef_start = T.cl_coef_start; c.cl_coef = T.cl_coef; c.cons_d2 = T.cons_d2; c.inv_m = T.inv_m;
+    c.n_clusters = s.n_cons ? s.n_clusters : 0; c.Ap = s.a_pad;
+    return c;
+}
+
 // One lane per constraint cluster (connected component of the constraint graph): Gauss-Seidel sweeps in constraint
 // order until every distance is inside OpenMM's (1 +- tol)^2 window.
-CDW_HD void shake(const SysDev& s, const Tables& T, double* x, const double* xref, double tol) {
-    if (s.n_cons == 0) return;
-    const int Ap = s.a_pad;
+CDW_NOINLINE void shake(const ConsCtx T, double* x, const double* xref, double tol) {
+    if (T.n_clusters == 0) return;
+    const int Ap = T.Ap;
     const double lower = 1.0 - 2.0 * tol + tol * tol, upper = 1.0 + 2.0 * tol + tol * tol;
     CDW_LANES(lane) {
-        for (int c = lane; c < s.n_clusters; c += 32) {
+        for (int c = lane; c < T.n_clusters; c += 32) {
             for (int it = 0; it < kMaxConstraintIters; ++it) {
                 bool updated = false;
                 for (int q = T.cl_start[c]; q < T.cl_start[c + 1]; ++q) {
@@ -312,28 +336,82 @@ CDW_HD void shake(const SysDev& s, const Tables& T, double* x, const double* xre
     }
 }
 
-CDW_HD void rattle_v(const SysDev& s, const Tables& T, const double* x, double* v, double tol) {
-    if (s.n_cons == 0) return;
-    const int Ap = s.a_pad;
+// Velocity constraints are linear: a cluster of k <= CDW_MAX_DIRECT coupled constraints is projected EXACTLY by one
+// k x k symmetric positive-definite solve, A_qr = (s_q . s_r) c_qr, A g = -(s_q . v_rel,q); no sweeps, no tolerance.
+template <int K>
+CDW_HD void rattle_cluster(const ConsCtx& T, const double* x, double* v, int Ap, int q0, const double* coef) {
+    d3 sv[K];
+    double b[K], A[K][K];
+    int ia[K], ja[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        const int i = T.cons_atoms[2 * (q0 + q)], j = T.cons_atoms[2 * (q0 + q) + 1];
+        ia[q] = i; ja[q] = j;
+        sv[q] = mk3(x[i] - x[j], x[Ap + i] - x[Ap + j], x[2 * Ap + i] - x[2 * Ap + j]);
+        b[q] = -dot(sv[q], mk3(v[i] - v[j], v[Ap + i] - v[Ap + j], v[2 * Ap + i] - v[2 * Ap + j]));
+    }
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int r = 0; r < K; ++r) A[q][r] = dot(sv[q], sv[r]) * coef[q * K + r];
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+        const double ip = 1.0 / A[p][p];
+#pragma unroll
+        for (int r = p + 1; r < K; ++r) {
+            const double fct = A[r][p] * ip;
+#pragma unroll
+            for (int c = p + 1; c < K; ++c) A[r][c] -= fct * A[p][c];
+            b[r] -= fct * b[p];
+        }
+        A[p][p] = ip;
+    }
+#pragma unroll
+    for (int p = K - 1; p >= 0; --p) {
+        double t = b[p];
+#pragma unroll
+        for (int c = p + 1; c < K; ++c) t -= A[p][c] * b[c];
+        b[p] = t * A[p][p];
+    }
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        const int i = ia[q], j = ja[q];
+        const double gi = b[q] * T.inv_m[i], gj = b[q] * T.inv_m[j];
+        v[i] += gi * sv[q].x; v[Ap + i] += gi * sv[q].y; v[2 * Ap + i] += gi * sv[q].z;
+        v[j] -= gj * sv[q].x; v[Ap + j] -= gj * sv[q].y; v[2 * Ap + j] -= gj * sv[q].z;
+    }
+}
+
+CDW_NOINLINE void rattle_v(const ConsCtx T, const double* x, double* v, double tol) {
+    if (T.n_clusters == 0) return;
+    const int Ap = T.Ap;
     CDW_LANES(lane) {
-        for (int c = lane; c < s.n_clusters; c += 32) {
-            for (int it = 0; it < kMaxConstraintIters; ++it) {
-                bool updated = false;
-                for (int q = T.cl_start[c]; q < T.cl_start[c + 1]; ++q) {
-                    int i = T.cons_atoms[2 * q], j = T.cons_atoms[2 * q + 1];
-                    double d2 = T.cons_d2[q];
-                    d3 sv = mk3(x[i] - x[j], x[Ap + i] - x[Ap + j], x[2 * Ap + i] - x[2 * Ap + j]);
-                    d3 vr = mk3(v[i] - v[j], v[Ap + i] - v[Ap + j], v[2 * Ap + i] - v[2 * Ap + j]);
-                    double sd = dot(sv, vr);
-                    if (fabs(sd) > tol * d2) {
-                        double imi = T.inv_m[i], imj = T.inv_m[j];
-                        double g = -sd / ((imi + imj) * dot(sv, sv));
-                        v[i] += g * imi * sv.x; v[Ap + i] += g * imi * sv.y; v[2 * Ap + i] += g * imi * sv.z;
-                        v[j] -= g * imj * sv.x; v[Ap + j] -= g * imj * sv.y; v[2 * Ap + j] -= g * imj * sv.z;
-                        updated = true;
+        for (int c = lane; c < T.n_clusters; c += 32) {
+            const int q0 = T.cl_start[c], k = T.cl_start[c + 1] - q0;
+            const double* coef = T.cl_coef + T.cl_coef_start[c];
+            if (k == 1) rattle_cluster<1>(T, x, v, Ap, q0, coef);
+            else if (k == 2) rattle_cluster<2>(T, x, v, Ap, q0, coef);
+            else if (k == 3) rattle_cluster<3>(T, x, v, Ap, q0, coef);
+            else {
+                // large clusters: Gauss-Seidel sweeps to |s . v_rel| <= tol d^2
+                for (int it = 0; it < kMaxConstraintIters; ++it) {
+                    bool updated = false;
+                    for (int q = q0; q < q0 + k; ++q) {
+                        int i = T.cons_atoms[2 * q], j = T.cons_atoms[2 * q + 1];
+                        double d2 = T.cons_d2[q];
+                        d3 sv = mk3(x[i] - x[j], x[Ap + i] - x[Ap + j], x[2 * Ap + i] - x[2 * Ap + j]);
+                        d3 vr = mk3(v[i] - v[j], v[Ap + i] - v[Ap + j], v[2 * Ap + i] - v[2 * Ap + j]);
+                        double sd = dot(sv, vr);
+                        if (fabs(sd) > tol * d2) {
+                            double imi = T.inv_m[i], imj = T.inv_m[j];
+                            double g = -sd / ((imi + imj) * dot(sv, sv));
+                            v[i] += g * imi * sv.x; v[Ap + i] += g * imi * sv.y; v[2 * Ap + i] += g * imi * sv.z;
+                            v[j] -= g * imj * sv.x; v[Ap + j] -= g * imj * sv.y; v[2 * Ap + j] -= g * imj * sv.z;
+                            updated = true;
+                        }
                     }
+                    if (!updated) break;
                 }
-                if (!updated) break;
             }
         }
     }
@@ -417,26 +495,40 @@ CDW_HD unsigned long long replica_step(const SysDev& s, const Tables& T, const W
             }
         }
     }
-    if (randomize) rattle_v(s, T, x, v, a.tol);
-    // ---- E1, F1 at (x_{t-1}, lambda_t): the incremental work (distribution_factories.py:120-129)
-    double U = energy_forces<true>(s, T, W, ns);
-    const double u_first = U;
-    if (a.force_out) {
-        CDW_LANES(lane) {
-            for (int at = lane; at < A; at += 32) a.force_out[p * A + at] = make_float4((float)f[at], (float)f[Ap + at], (float)f[2 * Ap + at], 0.f);
+    const ConsCtx cc = cons_ctx(s, T);
+    if (randomize) rattle_v(cc, x, v, a.tol);
+    double U = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, U_mid = 0.0;
+    // One force evaluation per pass (a single call site keeps the kernel inside the instruction cache):
+    //   pass 0     : E1, F1 at (x_{t-1}, lambda_t) -> the incremental work (distribution_factories.py:120-129)
+    //   pass st + 1: closes step st (second half-kick), i.e. "V R O R" of step st happen between pass st and st + 1.
+    for (int pass = 0;; ++pass) {
+        U = energy_forces<true>(s, T, W, ns);
+        if (pass == 0) {
+            u_first = U;
+            if (a.force_out) {
+                CDW_LANES(lane) {
+                    for (int at = lane; at < A; at += 32) a.force_out[p * A + at] = make_float4((float)f[at], (float)f[Ap + at], (float)f[2 * Ap + at], 0.f);
+                }
+            }
+        } else {
+            if (track) shadow += kinetic_energy(s, T, v) + U;  // closes the bookkeeping of the second R (its -(KE + U_mid) was added below)
+            // closing V (integrators.py:317-336)
+            double ke0 = track ? kinetic_energy(s, T, v) : 0.0;
+            kick(s, T, W, h);
+            rattle_v(cc, x, v, a.tol);
+            if (track) shadow += kinetic_energy(s, T, v) - ke0;
         }
-    }
-    double shadow = 0.0, proposal = 0.0, U_mid = 0.0;
-    for (int st = 0; st < a.n_steps; ++st) {
+        if (pass == a.n_steps) break;
+        const int st = pass;
         const bool last = st == a.n_steps - 1;
-        // V (integrators.py:317-336)
+        // V
         double ke0 = track ? kinetic_energy(s, T, v) : 0.0;
         kick(s, T, W, h);
-        rattle_v(s, T, x, v, a.tol);
+        rattle_v(cc, x, v, a.tol);
         if (track) shadow += kinetic_energy(s, T, v) - ke0;
         for (int half = 0; half < 2; ++half) {
             // R (integrators.py:297-315)
-            double e0 = track ? kinetic_energy(s, T, v) + (half == 0 ? U : U_mid) : 0.0;
+            if (track) shadow -= kinetic_energy(s, T, v) + (half == 0 ? U : U_mid);
             CDW_LANES(lane) {
                 for (int at = lane; at < A; at += 32) {
                     for (int c = 0; c < 3; ++c) {
@@ -447,14 +539,14 @@ CDW_HD unsigned long long replica_step(const SysDev& s, const Tables& T, const W
                 }
             }
             if (s.n_cons) {
-                shake(s, T, x, xref, a.tol);
+                shake(cc, x, xref, a.tol);
                 // v += (x - x1)/(dt/2) with x1 = xref + (dt/2) v   <=>   v = (x - xref)/(dt/2)
                 const double ih = 1.0 / h;
                 CDW_LANES(lane) {
                     for (int at = lane; at < A; at += 32)
                         for (int c = 0; c < 3; ++c) v[c * Ap + at] = (x[c * Ap + at] - xref[c * Ap + at]) * ih;
                 }
-                rattle_v(s, T, x, v, a.tol);
+                rattle_v(cc, x, v, a.tol);
             }
             if (half == 1 && last) {
                 // particles are stored as float4: evaluate the closing energy at exactly the stored coordinates
@@ -464,12 +556,10 @@ CDW_HD unsigned long long replica_step(const SysDev& s, const Tables& T, const W
                 }
             }
             if (half == 0) {
-                if (track) U_mid = energy_forces<false>(s, T, W, ns);
-            } else {
-                U = energy_forces<true>(s, T, W, ns);
-            }
-            if (track) shadow += kinetic_energy(s, T, v) + (half == 0 ? U_mid : U) - e0;
-            if (half == 0) {
+                if (track) {
+                    U_mid = energy_forces<false>(s, T, W, ns);
+                    shadow += kinetic_energy(s, T, v) + U_mid;
+                }
                 // O (integrators.py:338-350)
                 double k0 = track ? kinetic_energy(s, T, v) : 0.0;
                 CDW_LANES(lane) {
@@ -480,15 +570,11 @@ CDW_HD unsigned long long replica_step(const SysDev& s, const Tables& T, const W
                         v[at] = ca * v[at] + sg * z0; v[Ap + at] = ca * v[Ap + at] + sg * z1; v[2 * Ap + at] = ca * v[2 * Ap + at] + sg * z2;
                     }
                 }
-                rattle_v(s, T, x, v, a.tol);
+                rattle_v(cc, x, v, a.tol);
                 if (track) proposal -= kinetic_energy(s, T, v) - k0;
             }
         }
-        // closing V
-        ke0 = track ? kinetic_energy(s, T, v) : 0.0;
-        kick(s, T, W, h);
-        rattle_v(s, T, x, v, a.tol);
-        if (track) shadow += kinetic_energy(s, T, v) - ke0;
+        // the second R's  +(KE + U_new)  is added at the top of the next pass, once U_new is known
     }
     const double u_last = U;
     const bool bad = a.n_steps > 0 && !(u_last - u_last == 0.0);  // NaN or inf

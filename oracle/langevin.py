@@ -48,23 +48,46 @@ def _shake(x, xref, inv_m, constraints, tol):
     raise RuntimeError("oracle SHAKE did not converge")
 
 
+def constraint_clusters(constraints):
+    """Connected components of the constraint graph, each as a list of constraint indices (in input order)."""
+    parent = {}
+
+    def find(a):
+        parent.setdefault(a, a)
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    for (i, j, _) in constraints:
+        a, b = find(i), find(j)
+        if a != b:
+            parent[max(a, b)] = min(a, b)
+    groups = {}
+    for q, (i, _, _) in enumerate(constraints):
+        groups.setdefault(find(i), []).append(q)
+    return [groups[k] for k in sorted(groups)]
+
+
 def _rattle_v(x, v, inv_m, constraints, tol):
-    for _ in range(MAX_SHAKE_ITERS):
-        any_update = False
-        for (i, j, d) in constraints:
-            s = x[:, i] - x[:, j]
-            dot = (s * (v[:, i] - v[:, j])).sum(-1)
-            d2 = d * d
-            bad = np.abs(dot) > tol * d2
-            if not bad.any():
-                continue
-            any_update = True
-            g = np.where(bad, -dot / ((inv_m[i] + inv_m[j]) * (s * s).sum(-1)), 0.0)[:, None]
-            v[:, i] += g * inv_m[i] * s
-            v[:, j] -= g * inv_m[j] * s
-        if not any_update:
-            return
-    raise RuntimeError("oracle velocity constraints did not converge")
+    """Remove the velocity components along the constraints.  The condition is linear, so each cluster of coupled
+    constraints is projected exactly by one k x k solve (what `addConstrainVelocities` converges to):
+        A_qr = (s_q . s_r) c_qr,   c_qr = d(iq,ir)/m_ir - d(iq,jr)/m_jr - d(jq,ir)/m_ir + d(jq,jr)/m_jr,   A g = -(s_q . v_rel,q)
+    """
+    for cl in constraint_clusters(constraints):
+        k = len(cl)
+        idx = [(constraints[q][0], constraints[q][1]) for q in cl]
+        s = np.stack([x[:, i] - x[:, j] for (i, j) in idx], 1)            # (P, k, 3)
+        b = -np.stack([((x[:, i] - x[:, j]) * (v[:, i] - v[:, j])).sum(-1) for (i, j) in idx], 1)
+        coef = np.zeros((k, k))
+        for q, (iq, jq) in enumerate(idx):
+            for r, (ir, jr) in enumerate(idx):
+                coef[q, r] = (iq == ir) * inv_m[ir] - (iq == jr) * inv_m[jr] - (jq == ir) * inv_m[ir] + (jq == jr) * inv_m[jr]
+        A = np.einsum("pqc,prc->pqr", s, s) * coef[None]
+        g = np.linalg.solve(A, b[..., None])[..., 0]
+        for q, (i, j) in enumerate(idx):
+            v[:, i] += (g[:, q] * inv_m[i])[:, None] * s[:, q]
+            v[:, j] -= (g[:, q] * inv_m[j])[:, None] * s[:, q]
 
 
 def kinetic_energy(v, masses):

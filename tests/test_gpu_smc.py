@@ -32,9 +32,9 @@ def test_every_iteration_obeys_the_reference_bookkeeping():
     frames = cache_frames()
     x0 = frames[np.random.RandomState(0).randint(0, len(frames), 512)]
     seq = ts.relative_alchemical_sequence(12)
-    for kind in ("multinomial", "systematic"):
+    for kind, thr, always in (("multinomial", 0.9999, False), ("systematic", 0.5, True), ("multinomial", 0.5, False)):
         eng = _engine(system_xml("fluorobenzene"), 512, seq, langevin=LangevinParameters(timestep=0.002), resampler=kind, seed=3, resample_seed=4,
-                      record_history=True, floor_threshold=0.9)
+                      record_history=True, floor_threshold=thr, always_resample=always)
         eng.anneal(x0)
         cum_prev = np.zeros(512)
         stats = eng.stats.cpu().numpy()
@@ -43,14 +43,14 @@ def test_every_iteration_obeys_the_reference_bookkeeping():
             t = h["t"]
             inc, W, cum, anc, u = (h[k].cpu().numpy() for k in ("inc", "W", "cum", "anc", "uniforms"))
             np.testing.assert_array_equal(W, cum_prev + inc)
-            ref = weights.resample_step(cum_prev, inc, np.zeros(512), np.arange(512), uniforms=u, kind=kind, floor_threshold=0.9)
-            assert stats[t, _lib.STAT_NESS] == pytest.approx(ref["nESS"], rel=1e-12)
+            ref = weights.resample_step(cum_prev, inc, np.zeros(512), np.arange(512), uniforms=u, kind=kind, floor_threshold=thr, always=always)
+            assert stats[t, _lib.STAT_NESS] == pytest.approx(weights.nESS(cum_prev, inc), rel=1e-12)
             assert bool(stats[t, _lib.STAT_RESAMPLE]) == ref["resampled"]
             np.testing.assert_array_equal(anc, ref["ancestors"])
             np.testing.assert_allclose(cum, ref["cum"], rtol=1e-12, atol=1e-12)
             n_resampled += ref["resampled"]
             cum_prev = cum
-        assert n_resampled >= 1 and eng.resampled_iterations() == [h["t"] for h in eng.ensemble.history if stats[h["t"], _lib.STAT_RESAMPLE]]
+        assert (n_resampled >= 1 or thr == 0.5 and not always) and eng.resampled_iterations() == [h["t"] for h in eng.ensemble.history if stats[h["t"], _lib.STAT_RESAMPLE]]
 
 
 def test_first_iterations_track_the_oracle_anneal():
