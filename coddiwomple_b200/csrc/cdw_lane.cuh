@@ -1,0 +1,611 @@
+// cdw_lane.cuh — what a TEAM of T lanes (T = 1, 2, 4, ..., 32; same warp) does for ONE replica.
+//
+// Why this mapping (profiles/prof_propagate_r01_warp_per_replica_details.csv): with one warp per
+// replica the profiler showed 3-29 active lanes per instruction (constraints 3.2, force gather 10.5, angles 18,
+// torsions 23.5, pairs 29) and ~15 000 warp-instructions per replica-iteration, two thirds of them bookkeeping
+// (scratch-slot stores, CSR gather, warp syncs, lane loops).  With one thread per replica every lane of a warp
+// executes the SAME term of 32 different replicas: 32/32 lanes active in every phase, term parameters are
+// warp-uniform broadcast loads from shared memory, forces are accumulated by plain read-modify-write on the
+// thread's own column (no atomics, no scratch, no gather, no __syncwarp), and constraint clusters are solved
+// sequentially by the thread that owns the replica.
+//
+// One thread per replica needs ~12 B of shared memory per degree of freedom per thread, which caps residency at a
+// few warps per SM for 20-atom systems, and a batch of 10^4 replicas is only 313 warps.  So the code is written for
+// a TEAM of T lanes per replica: the T lanes split the term lists, atoms and constraint clusters of their replica
+// round-robin, each accumulates forces into its own fp32 copy (summed after the evaluation; still no atomics), and
+// energies are combined with log2(T) shuffles.  T = 1 is the pure lane-per-replica case (and the host harness);
+// the launcher picks T from the batch size and the shared-memory footprint so that the SMs stay full.
+//
+// Layout: the CTA stages the lambda-resolved term tables once (shared by all its threads); every per-replica
+// array (x, v, f, r0) is stored [element][thread] in shared memory, so a warp touching element k of its 32 replicas
+// hits 32 consecutive banks.  Global rows (float4 per atom) are moved by the whole CTA with coalesced loads and
+// transposed into that layout; the resampling gather is that load (row index = ancestor).
+//
+// Numerical contract: particle state (x, v) is fp32 wherever it is stored, on chip and off; all
+// arithmetic on it (energies, forces, constraints, integrator) is fp64; forces are accumulated in fp32.
+//
+// Reference semantics: OMMLI "V R O R V" (coddiwomple/openmm/integrators.py:297-350) driven by OMMBIP.apply
+// (coddiwomple/openmm/propagators.py:127-219); reduced potential (coddiwomple/openmm/states.py:116-136);
+// incremental work (coddiwomple/distribution_factories.py:124-129).
+#pragma once
+#include "cdw_math.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define CDW_CTA_THREADS(tid, nt) for (int tid = (int)threadIdx.x, nt = (int)blockDim.x, _cdw_once = 1; _cdw_once; _cdw_once = 0, __syncthreads())
+#define CDW_LDG(p) __ldg(p)
+#define CDW_TEAM_SYNC(M) __syncwarp((M).mask)
+#define CDW_SHFL_XOR(M, v, o) __shfl_xor_sync((M).mask, (v), (o))
+#else
+#define CDW_CTA_THREADS(tid, nt) for (int tid = 0, nt = 1; tid < 1; ++tid)
+#define CDW_LDG(p) (*(p))
+#define CDW_TEAM_SYNC(M) ((void)0)
+#define CDW_SHFL_XOR(M, v, o) (v)
+#endif
+#if !defined(__CUDACC__)
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#endif
+
+namespace cdw {
+
+constexpr int kMaxConstraintIters = 500;
+
+// ------------------------------------------------------------------------------------------------ shared-memory layout
+// kR = replicas staged per CTA (blockDim = kR * T).  Component c of atom a of replica column r lives at
+// arr[(3 a + c) * kR + ((r + a * sw) & (kR - 1))], sw = 32 / T: the per-atom rotation makes the T lanes of a team,
+// which touch T different atoms of the SAME column, hit T different banks, without padding; the three components
+// of an atom are kR words apart (immediate offsets).  r0 and the force copies use the same rule with the
+// constraint / atom index.
+#if defined(__CUDA_ARCH__)
+constexpr int kR = 32;
+#else
+constexpr int kR = 1;  // host harness: one replica at a time
+#endif
+struct Layout {
+    size_t lam, nbeff, inv_m, sig_v, bonds, angles, torsions, pairs, exts, cl_start, cons_atoms, cons_d2, cl_coef_start, cl_coef;  // CTA-shared tables
+    size_t x, v, f, r0, src, bad;                                                                                                  // [element][replica]
+    size_t total;
+};
+
+CDW_HD size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+CDW_HD Layout make_layout(const SysDev& s, bool forces, int R, int T) {  // R: kR on the device, 1 on the host
+    Layout L;
+    size_t o = 0;
+    const int A = s.n_atoms;
+    L.lam = o; o = align16(o + sizeof(double) * (s.n_lambda > 0 ? s.n_lambda : 1));
+    L.nbeff = o; o = align16(o + sizeof(double) * 3 * A);
+    L.inv_m = o; o = align16(o + sizeof(double) * A);
+    L.sig_v = o; o = align16(o + sizeof(double) * A);
+    L.bonds = o; o = align16(o + sizeof(EffBond) * s.n_bonds);
+    L.angles = o; o = align16(o + sizeof(EffAngle) * s.n_angles);
+    L.torsions = o; o = align16(o + sizeof(EffTorsion) * s.n_torsions);
+    L.pairs = o; o = align16(o + sizeof(EffPair) * s.n_pairs);
+    L.exts = o; o = align16(o + sizeof(EffExt) * s.n_ext);
+    L.cl_start = o; o = align16(o + sizeof(int) * (forces ? s.n_clusters + 1 : 0));
+    L.cons_atoms = o; o = align16(o + sizeof(int) * (forces ? 2 * s.n_cons : 0));
+    L.cons_d2 = o; o = align16(o + sizeof(double) * (forces ? s.n_cons : 0));
+    L.cl_coef_start = o; o = align16(o + sizeof(int) * (forces ? s.n_clusters + 1 : 0));
+    L.cl_coef = o; o = align16(o + sizeof(double) * (forces ? s.n_coef : 0));
+    const size_t col = sizeof(float) * R;
+    L.x = o; o = align16(o + col * 3 * A);
+    L.v = L.f = L.r0 = L.src = L.bad = o;
+    if (forces) {
+        L.v = o; o = align16(o + col * 3 * A);
+        L.f = o; o = align16(o + col * 3 * A * T);  // one force copy per team lane
+        L.r0 = o; o = align16(o + col * 3 * (s.n_cons > 0 ? s.n_cons : 0));
+        L.src = o; o = align16(o + sizeof(long long) * R);
+        L.bad = o; o = align16(o + sizeof(int) * R);
+    }
+    L.total = o;
+    return L;
+}
+
+struct Tables {  // pointers into the CTA-shared tables
+    double* lam; double* nbeff; double* inv_m; double* sig_v;
+    EffBond* bonds; EffAngle* angles; EffTorsion* torsions; EffPair* pairs; EffExt* exts;
+    int* cl_start; int* cons_atoms; double* cons_d2; int* cl_coef_start; double* cl_coef;
+};
+
+struct LaneMem {  // this thread's view of its replica's columns
+    float* x; float* v; float* f; float* r0;
+    long long* src; int* bad;
+    int rid;           // this replica's column (0 .. kR-1)
+    int T, tl, sw;     // team size, lane within the team, bank rotation (32 / T, 0 on the host)
+    unsigned mask;     // lanes of this warp whose replica is valid
+};
+
+CDW_HD Tables table_pointers(const Layout& L, unsigned char* smem) {
+    Tables T;
+    T.lam = (double*)(smem + L.lam); T.nbeff = (double*)(smem + L.nbeff); T.inv_m = (double*)(smem + L.inv_m); T.sig_v = (double*)(smem + L.sig_v);
+    T.bonds = (EffBond*)(smem + L.bonds); T.angles = (EffAngle*)(smem + L.angles); T.torsions = (EffTorsion*)(smem + L.torsions);
+    T.pairs = (EffPair*)(smem + L.pairs); T.exts = (EffExt*)(smem + L.exts);
+    T.cl_start = (int*)(smem + L.cl_start); T.cons_atoms = (int*)(smem + L.cons_atoms); T.cons_d2 = (double*)(smem + L.cons_d2);
+    T.cl_coef_start = (int*)(smem + L.cl_coef_start); T.cl_coef = (double*)(smem + L.cl_coef);
+    return T;
+}
+
+CDW_HD LaneMem lane_pointers(const Layout& L, unsigned char* smem, int T, int tid) {
+    LaneMem M;
+    M.x = (float*)(smem + L.x); M.v = (float*)(smem + L.v); M.f = (float*)(smem + L.f); M.r0 = (float*)(smem + L.r0);
+    M.src = (long long*)(smem + L.src); M.bad = (int*)(smem + L.bad);
+    M.T = T; M.rid = tid / T; M.tl = tid - M.rid * T; M.sw = kR > 1 ? 32 / T : 0;
+    M.mask = 0xffffffffu;
+    return M;
+}
+
+// word offset of group g (an atom or a constraint: three consecutive components) in column r (see Layout)
+#define CDW_BASE_R(g, r) ((g) * (3 * kR) + (((r) + (g) * sw) & (kR - 1)))
+#define CDW_BASE(g) CDW_BASE_R(g, rid)
+#define CDW_UNPACK(M) const int rid = (M).rid, T_ = (M).T, tl = (M).tl, sw = (M).sw; (void)T_; (void)tl; (void)rid; (void)sw
+
+CDW_HD double team_sum(const LaneMem& M, double v) {
+    for (int o = M.T >> 1; o > 0; o >>= 1) v += CDW_SHFL_XOR(M, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ prologue (once per CTA)
+// Resolve the lambda vector into effective term records: the per-replica code never touches lambda again.
+CDW_HD void build_tables(const SysDev& s, const Tables& T, const double* lam_g, double kT, bool forces) {
+    CDW_CTA_THREADS(tid, nt) {
+        for (int q = tid; q < s.n_lambda; q += nt) T.lam[q] = lam_g[q];
+    }
+    const double* lam = T.lam;
+    CDW_CTA_THREADS(tid, nt) {
+        // per-atom effective NonbondedForce parameters (ParticleOffsets)
+        for (int a = tid; a < s.n_atoms; a += nt) {
+            double q = s.nb_atom_par[3 * a], sg = s.nb_atom_par[3 * a + 1], ep = s.nb_atom_par[3 * a + 2];
+            for (int o = s.atom_off_start[a]; o < s.atom_off_start[a + 1]; ++o) {
+                double l = lam[s.atom_off_slot[o]];
+                q += l * s.atom_off_par[3 * o]; sg += l * s.atom_off_par[3 * o + 1]; ep += l * s.atom_off_par[3 * o + 2];
+            }
+            T.nbeff[3 * a] = q; T.nbeff[3 * a + 1] = sg; T.nbeff[3 * a + 2] = ep;
+            T.inv_m[a] = s.inv_mass[a];
+            T.sig_v[a] = sqrt(kT * s.inv_mass[a]);
+        }
+        for (int q = tid; q < s.n_bonds; q += nt) {
+            EffBond b;
+            b.i = s.bond_atoms[2 * q]; b.j = s.bond_atoms[2 * q + 1];
+            b.K = affine(s.bond_par[4 * q], s.bond_par[4 * q + 1], s.bond_slot[q], lam);
+            b.L = affine(s.bond_par[4 * q + 2], s.bond_par[4 * q + 3], s.bond_slot[q], lam);
+            T.bonds[q] = b;
+        }
+        for (int q = tid; q < s.n_angles; q += nt) {
+            EffAngle a;
+            a.i = s.angle_atoms[3 * q]; a.j = s.angle_atoms[3 * q + 1]; a.k = s.angle_atoms[3 * q + 2]; a.pad = 0;
+            a.K = affine(s.angle_par[4 * q], s.angle_par[4 * q + 1], s.angle_slot[q], lam);
+            a.T0 = affine(s.angle_par[4 * q + 2], s.angle_par[4 * q + 3], s.angle_slot[q], lam);
+            T.angles[q] = a;
+        }
+        for (int q = tid; q < s.n_torsions; q += nt) {
+            EffTorsion t;
+            t.i = s.torsion_atoms[4 * q]; t.j = s.torsion_atoms[4 * q + 1]; t.k = s.torsion_atoms[4 * q + 2]; t.l = s.torsion_atoms[4 * q + 3];
+            t.kk = affine(s.torsion_par[3 * q], s.torsion_par[3 * q + 1], s.torsion_slot[q], lam);
+            double ph = s.torsion_par[3 * q + 2];
+            t.c0 = cos(ph); t.s0 = sin(ph);
+            t.n = s.torsion_n[q]; t.pad = 0;
+            T.torsions[q] = t;
+        }
+        for (int q = tid; q < s.n_ext; q += nt) {
+            EffExt e;
+            e.atom = s.ext_atom[q]; e.pad = 0;
+            e.K = affine(s.ext_par[6 * q], s.ext_par[6 * q + 1], s.ext_slot[3 * q], lam);
+            e.x0 = affine(s.ext_par[6 * q + 2], s.ext_par[6 * q + 3], s.ext_slot[3 * q + 1], lam);
+            e.U0 = affine(s.ext_par[6 * q + 4], s.ext_par[6 * q + 5], s.ext_slot[3 * q + 2], lam);
+            T.exts[q] = e;
+        }
+        if (forces) {
+            for (int q = tid; q < s.n_clusters + 1; q += nt) T.cl_start[q] = s.cluster_start[q];
+            for (int q = tid; q < 2 * s.n_cons; q += nt) T.cons_atoms[q] = s.cons_atoms[q];
+            for (int q = tid; q < s.n_cons; q += nt) T.cons_d2[q] = s.cons_d2[q];
+            for (int q = tid; q < s.n_clusters + 1; q += nt) T.cl_coef_start[q] = s.cluster_coef_start[q];
+            for (int q = tid; q < s.n_coef; q += nt) T.cl_coef[q] = s.cluster_coef[q];
+        }
+    }
+    CDW_CTA_THREADS(tid, nt) {  // nbeff is complete: pair mixing rule / exceptions / soft-core
+        for (int q = tid; q < s.n_pairs; q += nt) {
+            EffPair p;
+            p.i = s.pair_atoms[2 * q]; p.j = s.pair_atoms[2 * q + 1]; p.flags = 0; p.pad = 0;
+            p.qqC = p.sig = p.eps = 0.0;
+            p.sc_sig = p.sc_eps = p.sc_rlj = p.sc_F = p.sc_U = 0.0;
+            int nbk = s.pair_nb[q];
+            if (nbk == -2) {
+                p.qqC = CDW_ONE_4PI_EPS0 * (T.nbeff[3 * p.i] * T.nbeff[3 * p.j]);
+                p.sig = 0.5 * (T.nbeff[3 * p.i + 1] + T.nbeff[3 * p.j + 1]);
+                p.eps = sqrt(T.nbeff[3 * p.i + 2] * T.nbeff[3 * p.j + 2]);
+                p.flags |= CDW_PAIR_NB;
+            } else if (nbk >= 0) {
+                double qq = s.exc_par[3 * nbk], sg = s.exc_par[3 * nbk + 1], ep = s.exc_par[3 * nbk + 2];
+                for (int o = s.exc_off_start[nbk]; o < s.exc_off_start[nbk + 1]; ++o) {
+                    double l = lam[s.exc_off_slot[o]];
+                    qq += l * s.exc_off_par[3 * o]; sg += l * s.exc_off_par[3 * o + 1]; ep += l * s.exc_off_par[3 * o + 2];
+                }
+                p.qqC = CDW_ONE_4PI_EPS0 * qq; p.sig = sg; p.eps = ep;
+                p.flags |= CDW_PAIR_NB;
+            }
+            if (p.eps != 0.0) p.flags |= CDW_PAIR_LJ;
+            int cls = s.pair_sc_class[q];
+            if (cls >= 0)
+                lower_softcore(p, cls, s.pair_sc_par + 4 * q, lam[s.slot_core], lam[s.slot_insert], lam[s.slot_delete], lam[s.slot_alpha]);
+            T.pairs[q] = p;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ energy / forces
+CDW_HD d3 ld3(const float* arr, int base) { return mk3((double)arr[base], (double)arr[base + kR], (double)arr[base + 2 * kR]); }
+CDW_HD void st3(float* arr, int base, d3 v) { arr[base] = (float)v.x; arr[base + kR] = (float)v.y; arr[base + 2 * kR] = (float)v.z; }
+CDW_HD void add3f(float* arr, int base, d3 v) { arr[base] += (float)v.x; arr[base + kR] += (float)v.y; arr[base + 2 * kR] += (float)v.z; }
+
+// Potential energy (kJ/mol) of the team's replica (same value in every lane of the team).  With F the forces end up
+// in force copy 0: each lane accumulates the terms it evaluates into its own copy, then the copies are summed.
+// Entered and left with the team synchronised.
+template <bool F>
+CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms;
+    const float* x = M.x;
+    float* f = M.f + tl * (3 * kR) * A;  // this lane's force copy
+    CDW_TEAM_SYNC(M);
+    if (F) {
+        for (int a = 0; a < A; ++a) {
+            const int b = CDW_BASE(a);
+            f[b] = 0.f; f[b + kR] = 0.f; f[b + 2 * kR] = 0.f;
+        }
+    }
+    double e = 0.0;
+    for (int q = tl; q < s.n_bonds; q += T_) {
+        const EffBond b = T.bonds[q];
+        const int bi = CDW_BASE(b.i), bj = CDW_BASE(b.j);
+        d3 fi;
+        e += bond_term<F>(ld3(x, bi), ld3(x, bj), b.K, b.L, fi);
+        if (F) { add3f(f, bi, fi); add3f(f, bj, -1.0 * fi); }
+    }
+    for (int q = tl; q < s.n_angles; q += T_) {
+        const EffAngle a = T.angles[q];
+        const int bi = CDW_BASE(a.i), bj = CDW_BASE(a.j), bk = CDW_BASE(a.k);
+        d3 fi, fk;
+        e += angle_term<F>(ld3(x, bi), ld3(x, bj), ld3(x, bk), a.K, a.T0, fi, fk);
+        if (F) { add3f(f, bi, fi); add3f(f, bj, -1.0 * (fi + fk)); add3f(f, bk, fk); }
+    }
+    for (int q = tl; q < s.n_torsions; q += T_) {
+        const EffTorsion t = T.torsions[q];
+        const int bi = CDW_BASE(t.i), bj = CDW_BASE(t.j), bk = CDW_BASE(t.k), bl = CDW_BASE(t.l);
+        d3 fi, fj, fk, fl;
+        e += torsion_term<F>(ld3(x, bi), ld3(x, bj), ld3(x, bk), ld3(x, bl), t.kk, t.c0, t.s0, t.n, fi, fj, fk, fl);
+        if (F) { add3f(f, bi, fi); add3f(f, bj, fj); add3f(f, bk, fk); add3f(f, bl, fl); }
+    }
+    for (int q = tl; q < s.n_pairs; q += T_) {
+        const EffPair& p = T.pairs[q];
+        const int bi = CDW_BASE(p.i), bj = CDW_BASE(p.j);
+        const d3 d = ld3(x, bi) - ld3(x, bj);
+        double g;
+        e += pair_term<F>(p, d, g);
+        if (F) { const d3 fj = g * d; add3f(f, bi, -1.0 * fj); add3f(f, bj, fj); }
+    }
+    for (int q = tl; q < s.n_ext; q += T_) {
+        const EffExt w = T.exts[q];
+        const int bw = CDW_BASE(w.atom);
+        d3 fw;
+        e += ext_term<F>(ld3(x, bw), w.K, w.x0, w.U0, fw);
+        if (F) add3f(f, bw, fw);
+    }
+    e = team_sum(M, e);
+    if (F && T_ > 1) {
+        CDW_TEAM_SYNC(M);
+        const int copy = (3 * kR) * A;
+        for (int a = tl; a < A; a += T_) {
+            const int b = CDW_BASE(a);
+            float ax = M.f[b], ay = M.f[b + kR], az = M.f[b + 2 * kR];
+            for (int c = 1; c < T_; ++c) { ax += M.f[c * copy + b]; ay += M.f[c * copy + b + kR]; az += M.f[c * copy + b + 2 * kR]; }
+            M.f[b] = ax; M.f[b + kR] = ay; M.f[b + 2 * kR] = az;
+        }
+    }
+    CDW_TEAM_SYNC(M);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------ constraints
+// SHAKE: Gauss-Seidel sweeps per cluster until every distance is inside OpenMM's (1 +- tol)^2 window.  The
+// displacement is applied to x and, divided by the drift time, to v ("v += (x - x1)/(dt/2)", integrators.py:310).
+// r0 = constraint vectors before the drift (saved by the caller).  Clusters are dealt round-robin to the team lanes.
+CDW_HD void lane_shake(const SysDev& s, const Tables& T, const LaneMem& M, double tol, double inv_h) {
+    CDW_UNPACK(M);
+    const double lower = 1.0 - 2.0 * tol + tol * tol, upper = 1.0 + 2.0 * tol + tol * tol;
+    for (int c = tl; c < s.n_clusters; c += T_) {
+        const int q0 = T.cl_start[c], q1 = T.cl_start[c + 1];
+        for (int it = 0; it < kMaxConstraintIters; ++it) {
+            bool updated = false;
+            for (int q = q0; q < q1; ++q) {
+                const int i = T.cons_atoms[2 * q], j = T.cons_atoms[2 * q + 1];
+                const int bi = CDW_BASE(i), bj = CDW_BASE(j);
+                const double d2 = T.cons_d2[q];
+                const d3 xi = ld3(M.x, bi), xj = ld3(M.x, bj);
+                const d3 sv = xi - xj;
+                const double r2 = dot(sv, sv);
+                if (r2 < lower * d2 || r2 > upper * d2) {
+                    const d3 r0 = ld3(M.r0, CDW_BASE(q));
+                    const double imi = T.inv_m[i], imj = T.inv_m[j];
+                    const double g = (d2 - r2) / (2.0 * (imi + imj) * dot(sv, r0));
+                    const double gi = g * imi, gj = g * imj;
+                    st3(M.x, bi, xi + gi * r0);
+                    st3(M.x, bj, xj - gj * r0);
+                    st3(M.v, bi, ld3(M.v, bi) + (gi * inv_h) * r0);
+                    st3(M.v, bj, ld3(M.v, bj) - (gj * inv_h) * r0);
+                    updated = true;
+                }
+            }
+            if (!updated) break;
+        }
+    }
+    CDW_TEAM_SYNC(M);
+}
+
+// Velocity constraints are linear: a cluster of k <= CDW_MAX_DIRECT coupled constraints is projected EXACTLY by one
+// k x k symmetric positive-definite solve, A_qr = (s_q . s_r) c_qr, A g = -(s_q . v_rel,q); no sweeps, no tolerance.
+template <int K>
+CDW_HD void lane_rattle_cluster(const Tables& T, const LaneMem& M, int q0, const double* coef) {
+    CDW_UNPACK(M);
+    d3 sv[K];
+    double b[K], A[K][K];
+    int bi[K], bj[K];
+    double mi[K], mj[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        const int i = T.cons_atoms[2 * (q0 + q)], j = T.cons_atoms[2 * (q0 + q) + 1];
+        bi[q] = CDW_BASE(i); bj[q] = CDW_BASE(j);
+        mi[q] = T.inv_m[i]; mj[q] = T.inv_m[j];
+        sv[q] = ld3(M.x, bi[q]) - ld3(M.x, bj[q]);
+        b[q] = -dot(sv[q], ld3(M.v, bi[q]) - ld3(M.v, bj[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int r = 0; r < K; ++r) A[q][r] = dot(sv[q], sv[r]) * coef[q * K + r];
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+        const double ip = 1.0 / A[p][p];
+#pragma unroll
+        for (int r = p + 1; r < K; ++r) {
+            const double fct = A[r][p] * ip;
+#pragma unroll
+            for (int c = p + 1; c < K; ++c) A[r][c] -= fct * A[p][c];
+            b[r] -= fct * b[p];
+        }
+        A[p][p] = ip;
+    }
+#pragma unroll
+    for (int p = K - 1; p >= 0; --p) {
+        double t = b[p];
+#pragma unroll
+        for (int c = p + 1; c < K; ++c) t -= A[p][c] * b[c];
+        b[p] = t * A[p][p];
+    }
+#pragma unroll
+    for (int q = 0; q < K; ++q) {  // sequential: constraints of a cluster share atoms
+        st3(M.v, bi[q], ld3(M.v, bi[q]) + (b[q] * mi[q]) * sv[q]);
+        st3(M.v, bj[q], ld3(M.v, bj[q]) - (b[q] * mj[q]) * sv[q]);
+    }
+}
+
+CDW_HD void lane_rattle(const SysDev& s, const Tables& T, const LaneMem& M, double tol) {
+    CDW_UNPACK(M);
+    for (int c = tl; c < s.n_clusters; c += T_) {
+        const int q0 = T.cl_start[c], k = T.cl_start[c + 1] - q0;
+        const double* coef = T.cl_coef + T.cl_coef_start[c];
+        if (k == 1) lane_rattle_cluster<1>(T, M, q0, coef);
+        else if (k == 2) lane_rattle_cluster<2>(T, M, q0, coef);
+        else if (k == 3) lane_rattle_cluster<3>(T, M, q0, coef);
+        else {
+            // large clusters: Gauss-Seidel sweeps to |s . v_rel| <= tol d^2
+            for (int it = 0; it < kMaxConstraintIters; ++it) {
+                bool updated = false;
+                for (int q = q0; q < q0 + k; ++q) {
+                    const int i = T.cons_atoms[2 * q], j = T.cons_atoms[2 * q + 1];
+                    const int bi = CDW_BASE(i), bj = CDW_BASE(j);
+                    const double d2 = T.cons_d2[q];
+                    const d3 sv = ld3(M.x, bi) - ld3(M.x, bj);
+                    const d3 vi = ld3(M.v, bi), vj = ld3(M.v, bj);
+                    const double sd = dot(sv, vi - vj);
+                    if (fabs(sd) > tol * d2) {
+                        const double imi = T.inv_m[i], imj = T.inv_m[j];
+                        const double g = -sd / ((imi + imj) * dot(sv, sv));
+                        st3(M.v, bi, vi + (g * imi) * sv);
+                        st3(M.v, bj, vj - (g * imj) * sv);
+                        updated = true;
+                    }
+                }
+                if (!updated) break;
+            }
+        }
+    }
+    CDW_TEAM_SYNC(M);
+}
+
+CDW_HD double lane_kinetic(const SysDev& s, const Tables& T, const LaneMem& M) {
+    CDW_UNPACK(M);
+    double k = 0.0;
+    for (int a = tl; a < s.n_atoms; a += T_) {
+        const d3 v = ld3(M.v, CDW_BASE(a));
+        k += dot(v, v) / T.inv_m[a];
+    }
+    return 0.5 * team_sum(M, k);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel arguments
+struct PropArgs {
+    const float4* pos_in; const float4* vel_in; float4* pos_out; float4* vel_out;
+    long long n;
+    const int* anc; const double* aux_in; const double* cum_in; const int* label_in;
+    const double* lambda;
+    double dt, gamma, kT, tol;
+    int n_steps; unsigned flags;
+    unsigned long long seed, step0; long long gid0;
+    double* inc_out; double* w_out; double* aux_out; int* label_out;
+    double* u_first_out; double* u_last_out; double* shadow_out; double* proposal_out;
+    int* nan_flags; unsigned long long* wmin_key;
+    double* energy_out; float4* force_out;  // cdw_energy_forces
+    double beta;                             // cdw_reduced_potential
+};
+
+// CTA-cooperative, coalesced load of `count` rows starting at particle p0 into the [element][replica] layout.
+// Row r comes from particle anc[p0 + r] when anc != NULL: this load IS the resampling gather (resamplers.py:123-129).
+CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* smem, const Layout& L, int sw, long long p0, int count, bool with_v) {
+    const int A = s.n_atoms;
+    float* X = (float*)(smem + L.x);
+    float* V = (float*)(smem + L.v);
+    long long* SRC = (long long*)(smem + L.src);
+    CDW_CTA_THREADS(tid, nt) {
+        if (with_v) {
+            for (int r = tid; r < count; r += nt) SRC[r] = a.anc ? (long long)a.anc[p0 + r] : p0 + r;
+        }
+    }
+    CDW_CTA_THREADS(tid, nt) {
+        for (int idx = tid; idx < count * A; idx += nt) {
+            const int r = idx / A, at = idx - r * A;
+            const long long src = with_v ? SRC[r] : p0 + r;
+            const int b = CDW_BASE_R(at, r);
+            const float4 q = CDW_LDG(a.pos_in + src * A + at);
+            X[b] = q.x; X[b + kR] = q.y; X[b + 2 * kR] = q.z;
+            if (with_v) {
+                const float4 w = a.vel_in ? CDW_LDG(a.vel_in + src * A + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+                V[b] = w.x; V[b + kR] = w.y; V[b + 2 * kR] = w.z;
+            }
+        }
+    }
+}
+
+// CTA-cooperative, coalesced store; a replica whose move produced a non-finite energy keeps the caller's state
+// (propagators.py:166-186).
+CDW_HD void cta_store_rows(const SysDev& s, const PropArgs& a, unsigned char* smem, const Layout& L, int sw, long long p0, int count) {
+    const int A = s.n_atoms;
+    const float* X = (const float*)(smem + L.x);
+    const float* V = (const float*)(smem + L.v);
+    const float* Fv = (const float*)(smem + L.f);
+    const long long* SRC = (const long long*)(smem + L.src);
+    const int* BAD = (const int*)(smem + L.bad);
+    CDW_CTA_THREADS(tid, nt) {
+        for (int idx = tid; idx < count * A; idx += nt) {
+            const int r = idx / A, at = idx - r * A;
+            const int b = CDW_BASE_R(at, r);
+            if (a.force_out) a.force_out[(p0 + r) * A + at] = make_float4(Fv[b], Fv[b + kR], Fv[b + 2 * kR], 0.f);
+            if (a.pos_out) {
+                float4 q, w;
+                if (!BAD[r]) {
+                    q = make_float4(X[b], X[b + kR], X[b + 2 * kR], 0.f);
+                    w = make_float4(V[b], V[b + kR], V[b + 2 * kR], 0.f);
+                } else {
+                    q = CDW_LDG(a.pos_in + SRC[r] * A + at);
+                    w = a.vel_in ? CDW_LDG(a.vel_in + SRC[r] * A + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                a.pos_out[(p0 + r) * A + at] = q;
+                if (a.vel_out) a.vel_out[(p0 + r) * A + at] = w;
+            }
+        }
+    }
+}
+
+// K4 body (+ first half of K2) for the replica already staged in this team's column.
+// Returns the order-preserving key of W[p] (for the running min).
+//
+// The integrator is a tiny op-code loop  E (V R O R E V)^n  with ONE call site per routine (force evaluation, SHAKE,
+// velocity projection, kinetic energy): the fully inlined body stays inside the instruction cache.
+//   E : energy + forces at the current x.   First E: E1, F1 at (x_{t-1}, lambda_t) -> the incremental work
+//       (distribution_factories.py:120-129); later E's close a step.
+//   V : v += (dt/2) f / m                                            (integrators.py:317-336)
+//   R : x += (dt/2) v ; SHAKE ; v += (x - x1)/(dt/2)                 (integrators.py:297-315)
+//   O : v = a v + b sqrt(kT/m) xi                                    (integrators.py:338-350)
+//   every V, R, O is followed by the velocity-constraint projection, as every step of the reference program is.
+CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const LaneMem& M, const PropArgs& a, long long p) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms;
+    const long long src = M.src[rid];
+    const unsigned long long gid = (unsigned long long)(a.gid0 + p);
+    const double h = 0.5 * a.dt;
+    const double ca = exp(-a.gamma * a.dt), cb = sqrt(1.0 - exp(-2.0 * a.gamma * a.dt));
+    const bool track = (a.flags & CDW_FLAG_TRACK_WORKS) != 0;
+    const double inv_kT = 1.0 / a.kT;
+    enum { OP_E = 0, OP_V = 1, OP_R = 2, OP_O = 3, OP_MB = 4 };
+    double U = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0;
+    const int n_ops = 1 + 6 * a.n_steps;
+    // op -1 (only with RANDOMIZE): Context.setVelocitiesToTemperature (propagators.py:137-138)
+    for (int op = (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES) ? -1 : 0; op < n_ops; ++op) {
+        int kind, slot = 0, st = 0;
+        if (op < 0) kind = OP_MB;
+        else if (op == 0) kind = OP_E;
+        else {
+            slot = (op - 1) % 6; st = (op - 1) / 6;  // V R O R E V
+            kind = slot == 0 || slot == 5 ? OP_V : (slot == 1 || slot == 3 ? OP_R : (slot == 2 ? OP_O : OP_E));
+        }
+        if (kind == OP_E) {
+            U = lane_energy<true>(s, T, M);
+            if (op == 0) u_first = U;
+            else if (track) shadow += pending + U;  // closes the second R of the step: (KE + U_new) - (KE_old + U_mid)
+            continue;
+        }
+        const double ke_before = track ? lane_kinetic(s, T, M) : 0.0;
+        if (kind == OP_V) {
+            for (int at = tl; at < A; at += T_) {
+                const int b = CDW_BASE(at);
+                st3(M.v, b, ld3(M.v, b) + (h * T.inv_m[at]) * ld3(M.f, b));
+            }
+        } else if (kind == OP_R) {
+            for (int q = tl; q < s.n_cons; q += T_) {  // constraint vectors before the drift (fp32 differences)
+                const int bi = CDW_BASE(T.cons_atoms[2 * q]), bj = CDW_BASE(T.cons_atoms[2 * q + 1]), bq = CDW_BASE(q);
+                M.r0[bq] = M.x[bi] - M.x[bj]; M.r0[bq + kR] = M.x[bi + kR] - M.x[bj + kR]; M.r0[bq + 2 * kR] = M.x[bi + 2 * kR] - M.x[bj + 2 * kR];
+            }
+            CDW_TEAM_SYNC(M);
+            for (int at = tl; at < A; at += T_) {
+                const int b = CDW_BASE(at);
+                st3(M.x, b, ld3(M.x, b) + h * ld3(M.v, b));
+            }
+            CDW_TEAM_SYNC(M);
+            if (s.n_cons) lane_shake(s, T, M, a.tol, 1.0 / h);
+        } else {  // OP_O / OP_MB: fresh Gaussian noise, counter = (seed; gid, step, atom, kind)
+            const bool mb = kind == OP_MB;
+            const double cv = mb ? 0.0 : ca, cn = mb ? 1.0 : cb;
+            for (int at = tl; at < A; at += T_) {
+                double z0, z1, z2;
+                normals3(a.seed, gid, (uint32_t)(a.step0 + st), (uint32_t)at, mb ? CDW_KIND_MAXWELL_BOLTZMANN : CDW_KIND_O_STEP, z0, z1, z2);
+                const int b = CDW_BASE(at);
+                const double sg = cn * T.sig_v[at];
+                st3(M.v, b, cv * ld3(M.v, b) + sg * mk3(z0, z1, z2));
+            }
+        }
+        CDW_TEAM_SYNC(M);
+        if (s.n_cons) lane_rattle(s, T, M, a.tol);
+        if (track && kind != OP_MB) {
+            const double ke_after = lane_kinetic(s, T, M);
+            if (kind == OP_V) shadow += ke_after - ke_before;                    // integrators.py:336
+            else if (kind == OP_O) proposal -= ke_after - ke_before;             // integrators.py:350
+            else if (slot == 1) {                                                // first R: needs the energy at the new x (integrators.py:313-315)
+                const double U_mid = lane_energy<true>(s, T, M);
+                shadow += (ke_after + U_mid) - (ke_before + U);
+                U = U_mid;
+            } else pending = ke_after - (ke_before + U);                         // second R: U here is U_mid; closed by the next E
+        }
+    }
+    const double u_last = U;
+    const bool bad = a.n_steps > 0 && !(u_last - u_last == 0.0);  // NaN or inf
+    const double aux = a.aux_in ? a.aux_in[src] : 0.0;
+    const double inc = u_first * inv_kT + aux;
+    const double w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
+    if (tl == 0) {
+        M.bad[rid] = bad ? 1 : 0;
+        if (a.inc_out) a.inc_out[p] = inc;
+        if (a.w_out) a.w_out[p] = w;
+        if (a.aux_out) a.aux_out[p] = -(bad ? u_first : u_last) * inv_kT;
+        if (a.label_out) a.label_out[p] = a.label_in ? a.label_in[src] : (int)src;
+        if (a.u_first_out) a.u_first_out[p] = u_first * inv_kT;
+        if (a.u_last_out) a.u_last_out[p] = u_last * inv_kT;
+        if (a.shadow_out) a.shadow_out[p] = shadow * inv_kT;
+        if (a.proposal_out) a.proposal_out[p] = proposal * inv_kT;
+        if (a.nan_flags) a.nan_flags[p] = bad ? 1 : 0;
+        if (a.energy_out) a.energy_out[p] = u_first;
+    }
+    return ordered_key(w);
+}
+
+}  // namespace cdw

@@ -1,64 +1,115 @@
 // cdw_propagate.cu — K1 (batched reduced potential) and K4 (fused SMC propagate: gather-on-load, energy+force,
 // incremental work, BAOAB + SHAKE/RATTLE + Philox, closing energy) for sm_100a.
 //
-// Mapping: one warp per replica, kWarps replicas in flight per CTA, persistent CTAs looping over
-// replicas.  The per-replica algorithm lives in cdw_replica.cuh (shared with the host test harness); this file is
-// the kernel shells and the C ABI.
+// Mapping: one THREAD per replica, persistent CTAs looping over batches of blockDim replicas.  The
+// per-replica algorithm lives in cdw_lane.cuh (shared with the host test harness); this file is the kernel shells and
+// the C ABI.
 //   * prologue (once per CTA): the lambda vector is resolved into "effective" term records in shared memory;
-//   * a replica's positions are loaded as coalesced float4 (one lane per atom) into fp64 shared arrays and stay on
-//     chip for all substeps; forces are evaluated in fp64, written per term to an fp32 scratch slot (no atomics:
-//     shared-memory float/double atomicAdd is a CAS loop on sm_100) and summed per atom through a CSR list;
-//   * constraints: one lane per constraint cluster, Gauss-Seidel SHAKE / velocity RATTLE.
+//   * a batch of rows is loaded by the whole CTA as coalesced float4 and transposed into [element][thread] shared
+//     arrays, where the state stays on chip for all substeps; every lane of a warp then evaluates the same term of 32
+//     different replicas (warp-uniform parameter broadcasts, no atomics, no inter-lane traffic);
+//   * constraints: exact k x k velocity projection and Gauss-Seidel SHAKE per cluster, per thread.
+#include <stdlib.h>
+
 #include "cdw_common.h"
-#include "cdw_replica.cuh"
+#include "cdw_lane.cuh"
 
 namespace cdw {
 
-__global__ void __launch_bounds__(kThreads) reduced_potential_kernel(SysDev s, PropArgs a) {
+constexpr int kMaxThreads = 256;
+
+struct Shape {
+    int R, T;  // replicas staged per CTA, lanes per replica; blockDim = R * T
+};
+
+__global__ void __launch_bounds__(kMaxThreads) reduced_potential_kernel(SysDev s, PropArgs a, Shape sh) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Layout L = make_layout(s, false, kWarps);
+    const int T_ = sh.T, sw = 32 / T_;
+    const Layout L = make_layout(s, false, kR, T_);
     const Tables T = table_pointers(L, smem);
     build_tables(s, T, a.lambda, 1.0, false);
-    const int warp = threadIdx.x >> 5;
-    const WarpMem W = warp_pointers(L, smem, warp);
-    for (long long p = (long long)blockIdx.x * kWarps + warp; p < a.n; p += (long long)gridDim.x * kWarps) replica_potential(s, T, W, a, p);
+    LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
+    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
+        const long long left = a.n - p0;
+        const int count = left < kR ? (int)left : kR;
+        cta_load_rows(s, a, smem, L, sw, p0, count, false);
+        const bool valid = M.rid < count;
+        M.mask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const double e = lane_energy<false>(s, T, M);
+            if (M.tl == 0) a.energy_out[p0 + M.rid] = a.beta * e;
+        }
+        __syncthreads();
+    }
 }
 
-__global__ void __launch_bounds__(kThreads, CDW_MINBLOCKS) smc_propagate_kernel(SysDev s, PropArgs a) {
+#ifndef CDW_MINBLOCKS
+#define CDW_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kMaxThreads, CDW_MINBLOCKS) smc_propagate_kernel(SysDev s, PropArgs a, Shape sh) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ unsigned long long cta_min[kWarps];
-    const Layout L = make_layout(s, true, kWarps);
+    __shared__ unsigned long long cta_min[kMaxThreads / 32];
+    const int T_ = sh.T, sw = 32 / T_;
+    const Layout L = make_layout(s, true, kR, T_);
     const Tables T = table_pointers(L, smem);
     build_tables(s, T, a.lambda, a.kT, true);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const WarpMem W = warp_pointers(L, smem, warp);
+    LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
     unsigned long long my_min = ~0ull;
-    for (long long p = (long long)blockIdx.x * kWarps + warp; p < a.n; p += (long long)gridDim.x * kWarps) {
-        unsigned long long key = replica_step(s, T, W, L.ns_pad, a, p);
-        my_min = key < my_min ? key : my_min;
+    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
+        const long long left = a.n - p0;
+        const int count = left < kR ? (int)left : kR;
+        cta_load_rows(s, a, smem, L, sw, p0, count, true);
+        const bool valid = M.rid < count;
+        M.mask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned long long key = lane_step(s, T, M, a, p0 + M.rid);
+            my_min = key < my_min ? key : my_min;
+        }
+        __syncthreads();
+        cta_store_rows(s, a, smem, L, sw, p0, count);
     }
     // one atomic per CTA for the running min of W (the log-sum-exp shift of K2)
-    if (lane == 0) cta_min[warp] = my_min;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, my_min, o);
+        my_min = other < my_min ? other : my_min;
+    }
+    if ((threadIdx.x & 31) == 0) cta_min[threadIdx.x >> 5] = my_min;
     __syncthreads();
     if (a.wmin_key && threadIdx.x == 0) {
         unsigned long long m = cta_min[0];
-        for (int w = 1; w < kWarps; ++w) m = cta_min[w] < m ? cta_min[w] : m;
+        for (int w = 1; w < ((int)blockDim.x + 31) / 32; ++w) m = cta_min[w] < m ? cta_min[w] : m;
         if (m != ~0ull) atomicMin(a.wmin_key, m);
     }
 }
 
-static int grid_for(const void* kernel, size_t smem, long long n) {
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    long long need = (n + kWarps - 1) / kWarps;
-    long long cap = (long long)sms * per_sm;
-    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+// Launch shape.  T lanes per replica (power of two), kR = 32 replica columns per CTA (blockDim = 32 T <= 256, so T <= 8).
+// CDW_TEAM overrides the choice (tuning).
+static Shape pick_shape(const SysDev& dev, bool forces, long long n, int sms) {
+    static const char* env = getenv("CDW_TEAM");
+    Shape sh;
+    sh.R = 32;
+    if (env && atoi(env) > 0) {
+        sh.T = atoi(env);
+    } else {
+        // measured on B200 (tools/tune_step.py): T = 4 is the sweet spot for 13-22 atom systems at every
+        // batch size (fewer lanes starve the SM of resident warps, more lanes pay for force copies and idle tails);
+        // tiny systems have nothing to split, and tiny batches need wider teams just to occupy the SM sub-partitions.
+        sh.T = dev.n_atoms >= 8 ? 4 : (dev.n_atoms >= 4 ? 2 : 1);
+        while (sh.T < 8 && dev.n_atoms >= 2 * sh.T && (n * sh.T + 31) / 32 < (long long)sms * 4) sh.T *= 2;
+    }
+    if (sh.T > 8) sh.T = 8;
+    while (sh.T > 1 && make_layout(dev, forces, sh.R, sh.T).total > 227 * 1024) sh.T /= 2;
+    return sh;
 }
 
 static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t st) {
-    const Layout L = make_layout(sys->dev, forces, kWarps);
+    int devid = 0, sms = 148;
+    cudaGetDevice(&devid);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
+    const Shape sh = pick_shape(sys->dev, forces, a.n, sms);
+    const int nthr = sh.R * sh.T;
+    const Layout L = make_layout(sys->dev, forces, sh.R, sh.T);
     const void* k = forces ? (const void*)smc_propagate_kernel : (const void*)reduced_potential_kernel;
     if (L.total > 227 * 1024) {
         set_error("system needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
@@ -66,11 +117,14 @@ static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t 
     }
     CDW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     if (a.n == 0) return CDW_OK;
-    int grid = grid_for(k, L.total, a.n);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, nthr, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long need = (a.n + sh.R - 1) / sh.R, cap = (long long)sms * per_sm;
+    const int grid = (int)(need < cap ? need : cap);
     if (forces)
-        smc_propagate_kernel<<<grid, kThreads, L.total, st>>>(sys->dev, a);
+        smc_propagate_kernel<<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
     else
-        reduced_potential_kernel<<<grid, kThreads, L.total, st>>>(sys->dev, a);
+        reduced_potential_kernel<<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }

@@ -15,9 +15,8 @@ constraint order, relative distance tolerance as OpenMM's (1 +- tol)^2 window) a
 Philox (oracle/rng.py) because OpenMM's generator is not reproducible outside OpenMM: parity with the reference's
 trajectories is statistical only; parity with the CUDA kernel is numerical (same counters -> same normals).
 
-Arithmetic mirrors the kernel contract: fp64 everywhere inside a call; positions are rounded to fp32
-after the last drift of the call (before the closing force evaluation) and velocities on return, because particles
-are stored as float4 between calls.
+Arithmetic mirrors the kernel contract: particle state (x, v) lives on the fp32 grid wherever it is
+stored (float4 rows in HBM, fp32 columns in shared memory); every update is computed in fp64 and rounded back.
 """
 import numpy as np
 
@@ -26,11 +25,18 @@ from . import rng
 MAX_SHAKE_ITERS = 500
 
 
-def _shake(x, xref, inv_m, constraints, tol):
+def r32(a):
+    """Round to the fp32 grid (the stored precision of particle state) and continue in fp64."""
+    return np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
+def _shake(x, v, r0, inv_m, constraints, tol, inv_h):
+    """Gauss-Seidel SHAKE in constraint order; every update moves x and, divided by the drift time, v
+    ("v += (x - x1)/(dt/2)", integrators.py:310).  State is re-rounded to fp32 after each update."""
     lower, upper = 1.0 - 2.0 * tol + tol * tol, 1.0 + 2.0 * tol + tol * tol
     for _ in range(MAX_SHAKE_ITERS):
         any_update = False
-        for (i, j, d) in constraints:
+        for q, (i, j, d) in enumerate(constraints):
             s = x[:, i] - x[:, j]
             r2 = (s * s).sum(-1)
             d2 = d * d
@@ -38,11 +44,12 @@ def _shake(x, xref, inv_m, constraints, tol):
             if not bad.any():
                 continue
             any_update = True
-            r0 = xref[:, i] - xref[:, j]
-            g = (d2 - r2) / (2.0 * (inv_m[i] + inv_m[j]) * (s * r0).sum(-1))
+            g = (d2 - r2) / (2.0 * (inv_m[i] + inv_m[j]) * (s * r0[q]).sum(-1))
             g = np.where(bad, g, 0.0)[:, None]
-            x[:, i] += g * inv_m[i] * r0
-            x[:, j] -= g * inv_m[j] * r0
+            x[:, i] = r32(x[:, i] + g * inv_m[i] * r0[q])
+            x[:, j] = r32(x[:, j] - g * inv_m[j] * r0[q])
+            v[:, i] = r32(v[:, i] + g * inv_m[i] * inv_h * r0[q])
+            v[:, j] = r32(v[:, j] - g * inv_m[j] * inv_h * r0[q])
         if not any_update:
             return
     raise RuntimeError("oracle SHAKE did not converge")
@@ -86,8 +93,8 @@ def _rattle_v(x, v, inv_m, constraints, tol):
         A = np.einsum("pqc,prc->pqr", s, s) * coef[None]
         g = np.linalg.solve(A, b[..., None])[..., 0]
         for q, (i, j) in enumerate(idx):
-            v[:, i] += (g[:, q] * inv_m[i])[:, None] * s[:, q]
-            v[:, j] -= (g[:, q] * inv_m[j])[:, None] * s[:, q]
+            v[:, i] = r32(v[:, i] + (g[:, q] * inv_m[i])[:, None] * s[:, q])
+            v[:, j] = r32(v[:, j] - (g[:, q] * inv_m[j])[:, None] * s[:, q])
 
 
 def kinetic_energy(v, masses):
@@ -97,29 +104,31 @@ def kinetic_energy(v, masses):
 def maxwell_boltzmann(x, masses, constraints, kT, seed, gids, step, tol=1e-6):
     """Context.setVelocitiesToTemperature as used by propagators.py:137-138: v ~ N(0, kT/m), then velocity constraints."""
     xi = rng.normals(seed, gids, step, len(masses), rng.KIND_MAXWELL_BOLTZMANN)
-    v = np.sqrt(kT / masses)[None, :, None] * xi
+    v = r32(np.sqrt(kT / masses)[None, :, None] * xi)
     if constraints:
         _rattle_v(np.asarray(x, dtype=np.float64), v, 1.0 / masses, constraints, tol)
     return v
 
 
 def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed, gids, step0, tol=1e-6,
-          randomize_velocities=False, track_works=False, round_fp32=True):
+          randomize_velocities=False, track_works=False):
     """n_steps of "V R O R V".  energy_forces(x) -> (U[P] kJ/mol, F[P,A,3]).
 
     Returns dict(x, v, u_first, u_last, shadow_work, proposal_work, nan) with energies in kJ/mol; `nan[p]` marks
     particles whose closing energy was not finite — their (x, v) are reverted to the input, which is what
     propagators.py:166-186 does with the default n_restart_attempts = 0.
+    Precision contract shared with the CUDA kernel: x and v live on the fp32 grid (they are float4 rows in HBM and
+    fp32 columns in shared memory); every update is computed in fp64 and rounded back.
     """
-    x0 = np.array(x, dtype=np.float64)
+    x0 = r32(x)
     x = x0.copy()
     masses = np.asarray(masses, dtype=np.float64)
     inv_m = 1.0 / masses
     P, A = x.shape[0], x.shape[1]
-    v0 = np.array(v, dtype=np.float64)  # a reverted move returns the caller's state (propagators.py:184)
+    v0 = r32(v)  # a reverted move returns the caller's state (propagators.py:184)
     if randomize_velocities:
         v = maxwell_boltzmann(x, masses, constraints, kT, seed, gids, step0, tol)
-    v = np.array(v, dtype=np.float64)
+    v = r32(v)
     a = np.exp(-gamma * dt)
     b = np.sqrt(1.0 - np.exp(-2.0 * gamma * dt))
     sig = np.sqrt(kT / masses)[None, :, None]
@@ -131,7 +140,7 @@ def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed
     for s in range(n_steps):
         # V
         ke0 = kinetic_energy(v, masses) if track_works else None
-        v = v + h * F * inv_m[None, :, None]
+        v = r32(v + h * F * inv_m[None, :, None])
         if constraints:
             _rattle_v(x, v, inv_m, constraints, tol)
         if track_works:
@@ -140,15 +149,11 @@ def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed
             # R
             if track_works:
                 e0 = kinetic_energy(v, masses) + (U if half == 0 else U_mid)
-            xref = x.copy()
-            x = x + h * v
-            x1 = x.copy()
+            r0 = [(x[:, i].astype(np.float32) - x[:, j].astype(np.float32)).astype(np.float64) for (i, j, _) in constraints]
+            x = r32(x + h * v)
             if constraints:
-                _shake(x, xref, inv_m, constraints, tol)
-                v = v + (x - x1) / h
+                _shake(x, v, r0, inv_m, constraints, tol, 1.0 / h)
                 _rattle_v(x, v, inv_m, constraints, tol)
-            if half == 1 and s == n_steps - 1 and round_fp32:
-                x = x.astype(np.float32).astype(np.float64)
             if track_works or half == 1:
                 if half == 0:
                     U_mid = energy_forces(x)[0]
@@ -160,14 +165,14 @@ def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed
                 # O
                 ke0 = kinetic_energy(v, masses) if track_works else None
                 xi = rng.normals(seed, gids, step0 + s, A, rng.KIND_O_STEP)
-                v = a * v + b * sig * xi
+                v = r32(a * v + b * sig * xi)
                 if constraints:
                     _rattle_v(x, v, inv_m, constraints, tol)
                 if track_works:
                     proposal -= kinetic_energy(v, masses) - ke0
         # closing V
         ke0 = kinetic_energy(v, masses) if track_works else None
-        v = v + h * F * inv_m[None, :, None]
+        v = r32(v + h * F * inv_m[None, :, None])
         if constraints:
             _rattle_v(x, v, inv_m, constraints, tol)
         if track_works:
@@ -177,6 +182,4 @@ def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed
     if nan.any():
         x[nan] = x0[nan]
         v[nan] = v0[nan]
-    if round_fp32:
-        v = v.astype(np.float32).astype(np.float64)
     return dict(x=x, v=v, u_first=u_first, u_last=u_last, shadow_work=shadow, proposal_work=proposal, nan=nan)

@@ -1,5 +1,5 @@
-// harness.cpp — TEST-ONLY host build of the per-replica device algorithm (cdw_replica.cuh compiled by g++ with the
-// lane loops run sequentially).  It lets the CPU test-suite check lambda lowering, term energies/forces, the
+// harness.cpp — TEST-ONLY host build of the per-replica device algorithm (cdw_lane.cuh compiled by g++; one host
+// "thread" per replica).  It lets the CPU test-suite check lambda lowering, term energies/forces, the
 // scratch-slot force gather, SHAKE/RATTLE, BAOAB and the Philox/det_exp/fixed-point helpers against the fp64 oracle
 // on the build host, where there is no GPU.  It is NOT part of the product: coddiwomple_b200 never loads it and has
 // no CPU fallback.
@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../coddiwomple_b200/csrc/cdw_pack.h"
-#include "../../coddiwomple_b200/csrc/cdw_replica.cuh"
+#include "../../coddiwomple_b200/csrc/cdw_lane.cuh"
 
 using namespace cdw;
 
@@ -42,25 +42,27 @@ extern "C" int hh_system_destroy(hh_system* s) {
 extern "C" int hh_system_info(const hh_system* s, int* n_slots, int* n_clusters, size_t* smem_energy, size_t* smem_step) {
     *n_slots = s->dev.n_slots;
     *n_clusters = s->dev.n_clusters;
-    *smem_energy = make_layout(s->dev, false, kWarps).total;
-    *smem_step = make_layout(s->dev, true, kWarps).total;
+    *smem_energy = make_layout(s->dev, false, 32, 8).total;
+    *smem_step = make_layout(s->dev, true, 32, 8).total;
     return 0;
 }
 
 static int run(const hh_system* s, PropArgs& a, bool forces) {
-    const Layout L = make_layout(s->dev, forces, 1);
+    const Layout L = make_layout(s->dev, forces, 1, 1);
     std::vector<unsigned char> smem(L.total + 64, 0);
     unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));
     const Tables T = table_pointers(L, base);
     build_tables(s->dev, T, a.lambda, forces ? a.kT : 1.0, forces);
-    const WarpMem W = warp_pointers(L, base, 0);
+    const LaneMem M = lane_pointers(L, base, 1, 0);
     unsigned long long mn = ~0ull;
     for (long long p = 0; p < a.n; ++p) {
+        cta_load_rows(s->dev, a, base, L, 0, p, 1, forces);
         if (forces) {
-            unsigned long long k = replica_step(s->dev, T, W, L.ns_pad, a, p);
+            unsigned long long k = lane_step(s->dev, T, M, a, p);
             mn = k < mn ? k : mn;
+            cta_store_rows(s->dev, a, base, L, 0, p, 1);
         } else {
-            replica_potential(s->dev, T, W, a, p);
+            a.energy_out[p] = a.beta * lane_energy<false>(s->dev, T, M);
         }
     }
     if (forces && a.wmin_key && mn < *a.wmin_key) *a.wmin_key = mn;
