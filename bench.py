@@ -160,7 +160,8 @@ def run_gpu(args):
     x0_pinned = positions_to_rows(x0_host, device=None, pinned=True)
     x0_dev = x0_pinned.cuda()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
-    cum_host = torch.empty(P, dtype=torch.float64, pin_memory=True)
+    cum_dev = eng.cum if world > 1 else eng.ensemble.cum          # sharded runs keep the (8-byte) weights replicated
+    cum_host = torch.empty(cum_dev.numel(), dtype=torch.float64, pin_memory=True)
 
     def barrier():
         if world > 1:
@@ -176,7 +177,7 @@ def run_gpu(args):
         dev = x0_pinned.to("cuda", non_blocking=True)
         eng.initialize(dev)
         eng.run()
-        cum_host.copy_(eng.ensemble.cum, non_blocking=True)
+        cum_host.copy_(cum_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps):
@@ -206,33 +207,33 @@ def run_gpu(args):
     e2e_value = units_per_step / (np.mean(ms_e2e) * 1e-3)
     fe = eng.free_energy()
 
+    # ---- roofline of the dominant kernel: the fused propagate kernel, timed with CUDA events on its stream
+    flops = algorithmic_flops(spec, langevin.n_steps)
+    eng.initialize(x0_dev)
+    evs = []
+    for t in range(1, eng.T):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.propagate(t)
+        e1.record()
+        eng.finish_iteration(t)
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel: the fused propagate kernel, timed with CUDA events on its stream
-        flops = algorithmic_flops(spec, langevin.n_steps)
-        eng.initialize(x0_dev)
-        evs = []
-        for t in range(1, eng.T):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            eng.propagate(t)
-            e1.record()
-            eng.finish_iteration(t)
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
         fp64_peak, _ = kernels.fma_peak(True, 8192)
         fp32_peak, _ = kernels.fma_peak(False, 8192)
         achieved = flops["per_iteration"] * P / (k_ms * 1e-3) / 1e12
         peaks, peaks_src = measured_peaks()
         share = k_ms * (eng.T - 1) / float(np.mean(ms))
         # ---- HBM-bound resampling kernels at sweep size (config 5), for the record
-        sweep = resampling_sweep(torch, kernels, _lib, 1 << 24, spec.n_atoms if spec.n_atoms < 14 else 13)
-        cpu_rate, cpu_dt, _ = cpu_port_rate(48, N_LAMBDA)
+        sweep = resampling_sweep(torch, kernels, _lib, 1 << 24, spec.n_atoms if spec.n_atoms < 14 else 13) if world == 1 else None
+        cpu_rate, cpu_dt, _ = cpu_port_rate(48, N_LAMBDA) if world == 1 else (None, 0.0, None)
         line = {"metric": "particle-Langevin-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "particles_per_gpu": P, "n_lambda": N_LAMBDA, "atoms": spec.n_atoms, "resampler": "multinomial@nESS<=0.5",
+                "config": {"workload": WORKLOAD, "particles_per_gpu": P, "parallelism": (f"particles sharded over {world} GPUs; all-gather of W + peer-mapped gather-on-load" if world > 1 else "single GPU"), "n_lambda": N_LAMBDA, "atoms": spec.n_atoms, "resampler": "multinomial@nESS<=0.5",
                            "step": "one full anneal = 99 SMC iterations", "l2": "flushed between anneals by a 256 MiB write", "terms": spec.counts()},
                 "anneals_per_s": 1e3 / float(np.mean(ms)), "free_energy_kT": fe, "resampled_iterations": len(eng.resampled_iterations()),
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": float(np.mean(ms_e2e)), "h2d_bytes_per_step": int(x0_pinned.numel() * 4),
@@ -244,12 +245,12 @@ def run_gpu(args):
                              "peak_source": "cdw_fma_peak(fp64) micro-benchmark run in this process (MEASURED_PEAKS.json has no FP pipe figure)",
                              "fp32_fma_peak_tflops": fp32_peak, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
                 "resampling_sweep": sweep,
-                "cpu_baseline": {"value": cpu_rate, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-                                 "sample": f"oracle/ numpy port, 48 particles x {N_LAMBDA} lambda ({cpu_dt:.1f} s)"},
+                "cpu_baseline": ({"value": cpu_rate, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+                                  "sample": f"oracle/ numpy port, 48 particles x {N_LAMBDA} lambda ({cpu_dt:.1f} s)"} if world == 1 else None),
                 "clocks": clocks.summary()}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        eng.close()
         dist.destroy_process_group()
 
 

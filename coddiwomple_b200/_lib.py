@@ -87,6 +87,8 @@ _SIGNATURES = {
     "cdw_energy_forces": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "cdw_smc_propagate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64,
                                     C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cdw_smc_propagate_sharded": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64,
+                                            C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "cdw_baoab": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "cdw_weight_update": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "cdw_weight_workspace_bytes": (C.c_size_t, [C.c_int64]),

@@ -448,7 +448,18 @@ struct PropArgs {
     int* nan_flags; unsigned long long* wmin_key;
     double* energy_out; float4* force_out;  // cdw_energy_forces
     double beta;                             // cdw_reduced_potential
+    // sharded runs: ancestors are GLOBAL ids; rank g owns [g * n_per_rank, (g + 1) * n_per_rank) and its rows are
+    // reachable through peer-mapped pointers (CUDA IPC over NVLink).  NULL peer_pos = single-GPU addressing.
+    const float4* const* peer_pos; const float4* const* peer_vel; const double* const* peer_aux; const int* const* peer_label;
+    long long n_per_rank;
 };
+
+// where row `src` (a global particle id when the run is sharded) lives
+CDW_HD const float4* row_ptr(const PropArgs& a, const float4* local, const float4* const* peers, long long src, int A) {
+    if (!a.peer_pos) return local + src * A;
+    const long long r = src / a.n_per_rank;
+    return peers[r] + (src - r * a.n_per_rank) * A;
+}
 
 // CTA-cooperative, coalesced load of `count` rows starting at particle p0 into the [element][replica] layout.
 // Row r comes from particle anc[p0 + r] when anc != NULL: this load IS the resampling gather (resamplers.py:123-129).
@@ -467,10 +478,10 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
             const int r = idx / A, at = idx - r * A;
             const long long src = with_v ? SRC[r] : p0 + r;
             const int b = CDW_BASE_R(at, r);
-            const float4 q = CDW_LDG(a.pos_in + src * A + at);
+            const float4 q = row_ptr(a, a.pos_in, a.peer_pos, src, A)[at];  // NVLink load when the ancestor lives on a peer
             X[b] = q.x; X[b + kR] = q.y; X[b + 2 * kR] = q.z;
             if (with_v) {
-                const float4 w = a.vel_in ? CDW_LDG(a.vel_in + src * A + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 w = a.vel_in ? row_ptr(a, a.vel_in, a.peer_vel, src, A)[at] : make_float4(0.f, 0.f, 0.f, 0.f);
                 V[b] = w.x; V[b + kR] = w.y; V[b + 2 * kR] = w.z;
             }
         }
@@ -497,8 +508,8 @@ CDW_HD void cta_store_rows(const SysDev& s, const PropArgs& a, unsigned char* sm
                     q = make_float4(X[b], X[b + kR], X[b + 2 * kR], 0.f);
                     w = make_float4(V[b], V[b + kR], V[b + 2 * kR], 0.f);
                 } else {
-                    q = CDW_LDG(a.pos_in + SRC[r] * A + at);
-                    w = a.vel_in ? CDW_LDG(a.vel_in + SRC[r] * A + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    q = row_ptr(a, a.pos_in, a.peer_pos, SRC[r], A)[at];
+                    w = a.vel_in ? row_ptr(a, a.vel_in, a.peer_vel, SRC[r], A)[at] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 a.pos_out[(p0 + r) * A + at] = q;
                 if (a.vel_out) a.vel_out[(p0 + r) * A + at] = w;
@@ -589,7 +600,16 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
     }
     const double u_last = U;
     const bool bad = a.n_steps > 0 && !(u_last - u_last == 0.0);  // NaN or inf
-    const double aux = a.aux_in ? a.aux_in[src] : 0.0;
+    double aux = 0.0;
+    int label = (int)src;
+    if (a.peer_pos) {
+        const long long r = src / a.n_per_rank, l = src - r * a.n_per_rank;
+        if (a.peer_aux) aux = a.peer_aux[r][l];
+        if (a.peer_label) label = a.peer_label[r][l];
+    } else {
+        if (a.aux_in) aux = a.aux_in[src];
+        if (a.label_in) label = a.label_in[src];
+    }
     const double inc = u_first * inv_kT + aux;
     const double w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
     if (tl == 0) {
@@ -597,7 +617,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         if (a.inc_out) a.inc_out[p] = inc;
         if (a.w_out) a.w_out[p] = w;
         if (a.aux_out) a.aux_out[p] = -(bad ? u_first : u_last) * inv_kT;
-        if (a.label_out) a.label_out[p] = a.label_in ? a.label_in[src] : (int)src;
+        if (a.label_out) a.label_out[p] = label;
         if (a.u_first_out) a.u_first_out[p] = u_first * inv_kT;
         if (a.u_last_out) a.u_last_out[p] = u_last * inv_kT;
         if (a.shadow_out) a.shadow_out[p] = shadow * inv_kT;

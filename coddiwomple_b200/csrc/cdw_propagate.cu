@@ -180,6 +180,27 @@ extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, con
     return launch(sys, a, true, (cudaStream_t)stream);
 }
 
+extern "C" int cdw_smc_propagate_sharded(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
+                                         const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, float* pos_out, float* vel_out, int64_t n,
+                                         const int32_t* anc, const double* cum_in, const double* lambda, const cdw_langevin_params* prm, uint64_t seed,
+                                         uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out, int32_t* label_out,
+                                         int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream) {
+    CDW_REQUIRE(sys && prm && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    CDW_REQUIRE(peer_pos && peer_vel && pos_out && vel_out && anc && n_ranks > 0 && n_per_rank > 0, "null argument");
+    CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
+    CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
+    PropArgs a = {};
+    a.peer_pos = (const float4* const*)peer_pos; a.peer_vel = (const float4* const*)peer_vel; a.peer_aux = peer_aux; a.peer_label = peer_label;
+    a.n_per_rank = n_per_rank;
+    a.vel_in = (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
+    a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
+    a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
+    a.seed = seed; a.step0 = step0; a.gid0 = gid0;
+    a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
+    return launch(sys, a, true, (cudaStream_t)stream);
+}
+
 extern "C" int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n, const double* lambda, const cdw_langevin_params* prm,
                          uint64_t seed, uint64_t step0, int64_t gid0, double* u_first_out, double* u_last_out, double* shadow_out,
                          double* proposal_out, int32_t* nan_flags, cdw_stream stream) {

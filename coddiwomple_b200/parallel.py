@@ -1,0 +1,258 @@
+"""Multi-GPU SMC annealing: particles sharded over the GPUs of one box, one process per GPU.
+
+The reference has no parallelism of any kind; this is new.  Design ("replicated weights, sharded
+state"):
+
+  * rank g owns the contiguous block of global particle ids [g * P/G, (g + 1) * P/G): positions, velocities, aux and
+    labels of those slots live in ITS HBM only (double-buffered rows, exported to the other ranks with CUDA IPC so
+    that every rank can read every rank's rows over NVLink);
+  * the per-particle weights are tiny (8 B) and every rank needs the global normaliser, nESS, the resampling decision
+    and the global cdf: after the fused propagate kernel each rank contributes its slice W_loc to ONE NCCL all-gather
+    (the (max, sum-exp) all-reduce of the north star is subsumed: every rank reduces the gathered vector itself, in the
+    same order, so the statistics are bit-identical on all ranks and identical to a single-GPU run);
+  * ancestors are global ids; the next propagate kernel loads each slot's ancestor row straight from the owning
+    rank's buffer through a peer-mapped pointer: the resampling gather, the NVLink all-to-all migration and the
+    propagation are one kernel (cdw_smc_propagate_sharded);
+  * the all-gather is also the cross-rank ordering point: a rank's buffers are only read by peers after that rank's
+    own all-gather contribution, i.e. after its propagate kernel has written them.
+
+Noise is keyed by the global particle id and the weights are reduced identically everywhere, so an anneal on G GPUs
+is bit-identical to the same anneal on one GPU (tests/multi_gpu_check.py asserts exactly that).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import RESAMPLER_KINDS, DeviceSystem, LangevinParameters, positions_to_rows
+
+
+def shard_bounds(n_particles, world_size, rank):
+    """[first, last) global ids of `rank`'s block; the particle count must divide evenly."""
+    if n_particles % world_size:
+        raise ValueError(f"{n_particles} particles do not divide over {world_size} ranks")
+    per = n_particles // world_size
+    return rank * per, (rank + 1) * per
+
+
+def owner_of(global_ids, n_per_rank):
+    """(owning rank, local slot) of global particle ids."""
+    g = np.asarray(global_ids)
+    return g // n_per_rank, g % n_per_rank
+
+
+def migration_matrix(ancestors, world_size):
+    """M[dst, src] = number of particle rows rank dst pulls from rank src for the global ancestor vector."""
+    anc = np.asarray(ancestors)
+    per = len(anc) // world_size
+    dst = np.arange(len(anc)) // per
+    src = anc // per
+    m = np.zeros((world_size, world_size), dtype=np.int64)
+    np.add.at(m, (dst, src), 1)
+    return m
+
+
+class _IpcBuffer:
+    """A cudaMalloc'ed buffer owned by this rank, viewable as a torch tensor and exportable to peers."""
+
+    def __init__(self, lib, shape, dtype):
+        self.lib = lib
+        self.shape, self.dtype = tuple(shape), dtype
+        self.nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        self.ptr = C.c_void_p()
+        _lib.check(lib.cdw_device_malloc(max(self.nbytes, 16), C.byref(self.ptr)), "cdw_device_malloc")
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.ptr.value, False), "version": 2}
+        self.tensor = torch.as_tensor(self, device=f"cuda:{torch.cuda.current_device()}")
+        self.tensor.zero_()
+
+    def handle(self):
+        h = (C.c_ubyte * 64)()
+        _lib.check(self.lib.cdw_ipc_get_handle(self.ptr, h), "cdw_ipc_get_handle")
+        return bytes(h)
+
+    def free(self):
+        if self.ptr:
+            self.lib.cdw_device_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+class ShardedSMCEngine:
+    """Same loop as SMCEngine over `n_particles` GLOBAL particles, sharded over the ranks of `group` (NCCL)."""
+
+    def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5, always_resample=False,
+                 seed=0, resample_seed=1, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (backend nccl, one process per GPU)")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.P = int(n_particles)
+        self.first, self.last = shard_bounds(self.P, self.world, self.rank)
+        self.P_loc = self.last - self.first
+        self.system = system if isinstance(system, DeviceSystem) else DeviceSystem(system)
+        self.lib = self.system.lib
+        self.A = self.system.n_atoms
+        self.langevin = langevin or LangevinParameters()
+        self.parameter_sequence = list(parameter_sequence)
+        self.T = len(self.parameter_sequence)
+        self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
+        self.lam = self.system.lambda_table(self.parameter_sequence, self.device)
+        self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
+        self.threshold = -1.0 if always_resample else float(floor_threshold)
+        self.seed, self.resample_seed = int(seed), int(resample_seed)
+        d, P, Pl, A = self.device, self.P, self.P_loc, self.A
+        # ---- sharded state, double-buffered, IPC-exported
+        self._opened = []
+        self._bufs = {name: [_IpcBuffer(self.lib, shape, dt) for _ in range(2)]
+                      for name, shape, dt in (("pos", (Pl, A, 4), torch.float32), ("vel", (Pl, A, 4), torch.float32), ("aux", (Pl,), torch.float64),
+                                              ("label", (Pl,), torch.int32))}
+        self.peer = {name: [self._exchange(name, b) for b in range(2)] for name in self._bufs}
+        # ---- replicated weights (global length on every rank)
+        self.W = torch.zeros(P, dtype=torch.float64, device=d)
+        self.W_loc = torch.zeros(Pl, dtype=torch.float64, device=d)
+        self.inc_loc = torch.zeros(Pl, dtype=torch.float64, device=d)
+        self.cum = torch.zeros(P, dtype=torch.float64, device=d)
+        self.anc = torch.arange(P, dtype=torch.int32, device=d)
+        self.nan_flags = torch.zeros(Pl, dtype=torch.int32, device=d)
+        self.wmin_key = torch.zeros(1, dtype=torch.int64, device=d)
+        self.scratch_key = torch.zeros(1, dtype=torch.int64, device=d)
+        self.uniforms = torch.zeros(P, dtype=torch.float64, device=d)
+        self.cdf = torch.zeros(P, dtype=torch.int64, device=d)
+        self.W_copy = torch.zeros(P, dtype=torch.float64, device=d)
+        self.ws_bytes = int(self.lib.cdw_weight_workspace_bytes(P))
+        self.workspace = torch.zeros((self.ws_bytes + 7) // 8, dtype=torch.int64, device=d)
+        self.stats = torch.zeros(max(self.T, 1), _lib.STATS_LEN, dtype=torch.float64, device=d)
+        self.cur = 0
+        self.iteration = 0
+        self.pending_gather = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _exchange(self, name, b):
+        """All-gather the IPC handles of buffer (name, b); returns a device array of world-size base pointers."""
+        mine = self._bufs[name][b]
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine.handle(), group=self.group)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(mine.ptr.value)
+            else:
+                out = C.c_void_p()
+                _lib.check(self.lib.cdw_ipc_open_handle((C.c_ubyte * 64).from_buffer_copy(h), C.byref(out)), "cdw_ipc_open_handle")
+                self._opened.append(out.value)
+                ptrs.append(out.value)
+        return torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+
+    def local(self, name, b=None):
+        return self._bufs[name][self.cur if b is None else b].tensor
+
+    @property
+    def beta(self):
+        return 1.0 / self.langevin.kT
+
+    # ------------------------------------------------------------------ the loop
+    def initialize(self, positions_local, velocities_local=None):
+        """positions_local: this rank's block, (P/G, A, 3) host array or (P/G, A, 4) device rows."""
+        rows = positions_local if torch.is_tensor(positions_local) else positions_to_rows(positions_local, self.device)
+        self.cur = 0
+        self.local("pos").copy_(rows, non_blocking=True)
+        if velocities_local is None:
+            self.local("vel").zero_()
+        else:
+            self.local("vel").copy_(velocities_local if torch.is_tensor(velocities_local) else positions_to_rows(velocities_local, self.device))
+        u0 = torch.empty(self.P_loc, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.cdw_reduced_potential(self.system.handle, _lib.ptr(self.local("pos")), self.P_loc, _lib.ptr(self.lam[0]), self.beta, _lib.ptr(u0),
+                                                 _lib.current_stream()), "cdw_reduced_potential")
+        self.local("aux").copy_(-u0)
+        self.local("label").copy_(torch.arange(self.first, self.last, dtype=torch.int32, device=self.device))
+        self.cum.zero_()
+        self.anc.copy_(torch.arange(self.P, dtype=torch.int32, device=self.device))
+        self.stats.zero_()
+        self.iteration = 0
+        self.pending_gather = False
+        dist.barrier(group=self.group)  # every rank's initial rows are in place before any peer read
+
+    def propagate(self, t):
+        self.iteration = t
+        c, n = self.cur, 1 - self.cur
+        flags = _lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0
+        prm = self.langevin.as_struct(flags)
+        self.wmin_key.fill_(-1)
+        _lib.check(self.lib.cdw_smc_propagate_sharded(
+            self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]),
+            self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), self.P_loc, _lib.ptr(self.anc[self.first:self.last]),
+            _lib.ptr(self.cum[self.first:self.last]), _lib.ptr(self.lam[t]), C.byref(prm), C.c_uint64(self.seed),
+            C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc), _lib.ptr(self.W_loc), _lib.ptr(self.local("aux", n)),
+            _lib.ptr(self.local("label", n)), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), _lib.current_stream()), "cdw_smc_propagate_sharded")
+        self.cur = n
+
+    def finish_iteration(self, t):
+        # C1: one all-gather of the 8-byte weights; also the ordering point for the peer reads of the next iteration
+        dist.all_gather_into_tensor(self.W, self.W_loc, group=self.group)
+        # every rank reduces the SAME vector in the SAME order: global min, log-sum-exp, nESS, decision
+        self.scratch_key.fill_(-1)
+        _lib.check(self.lib.cdw_weight_update(_lib.ptr(self.W), None, None, None, self.P, None, _lib.ptr(self.W_copy), _lib.ptr(self.scratch_key),
+                                             _lib.current_stream()), "cdw_weight_update")
+        _lib.check(self.lib.cdw_weight_stats(_lib.ptr(self.W), self.P, self.threshold, _lib.ptr(self.scratch_key), _lib.ptr(self.stats[t]),
+                                            _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_weight_stats")
+        n_u = self.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
+        _lib.check(self.lib.cdw_philox_uniforms(C.c_uint64(self.resample_seed), C.c_uint64(t), n_u, _lib.ptr(self.uniforms), _lib.current_stream()),
+                   "cdw_philox_uniforms")
+        _lib.check(self.lib.cdw_resample_indices(self.kind, _lib.ptr(self.W), _lib.ptr(self.uniforms), self.P, _lib.ptr(self.stats[t]), _lib.ptr(self.cum),
+                                                _lib.ptr(self.cum), _lib.ptr(self.anc), _lib.ptr(self.cdf), _lib.ptr(self.workspace), self.ws_bytes,
+                                                _lib.current_stream()), "cdw_resample_indices")
+        self.pending_gather = True
+
+    def step(self, t):
+        self.propagate(t)
+        self.finish_iteration(t)
+
+    def materialize(self):
+        """Apply the last resampling to this rank's block (peer gather over NVLink)."""
+        if self.pending_gather:
+            c, n = self.cur, 1 - self.cur
+            _lib.check(self.lib.cdw_gather_particles_peer(
+                _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]), self.world,
+                self.P_loc, _lib.ptr(self.anc[self.first:self.last]), _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)),
+                _lib.ptr(self.local("aux", n)), _lib.ptr(self.local("label", n)), self.P_loc, self.A, _lib.current_stream()), "cdw_gather_particles_peer")
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)  # nobody reuses the source buffers before every rank has pulled its rows
+            self.cur = n
+            self.pending_gather = False
+
+    def run(self):
+        for t in range(1, self.T):
+            self.step(t)
+        self.materialize()
+        return self
+
+    def anneal(self, positions_local, velocities_local=None):
+        self.initialize(positions_local, velocities_local)
+        return self.run()
+
+    # ------------------------------------------------------------------ results
+    def cumulative_works(self):
+        return self.cum.cpu().numpy()
+
+    def free_energy(self):
+        c = self.cum.cpu().numpy()
+        m = (-c).max()
+        return float(-(m + np.log(np.exp(-c - m).sum())) + np.log(c.size))
+
+    def resampled_iterations(self):
+        s = self.stats.cpu().numpy()
+        return [t for t in range(1, self.T) if s[t, _lib.STAT_RESAMPLE] != 0.0]
+
+    def close(self):
+        """Unmap the peers' buffers, then (after every rank has done so) free this rank's own."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for ptr in self._opened:
+            self.lib.cdw_ipc_close_handle(C.c_void_p(ptr))
+        self._opened = []
+        dist.barrier(group=self.group)
+        for bufs in self._bufs.values():
+            for b in bufs:
+                b.free()

@@ -168,6 +168,18 @@ CDW_API int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const 
                       double* u_first_out, double* u_last_out, double* shadow_out, double* proposal_out,
                       int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream);
 
+/* Sharded form of cdw_smc_propagate for one rank of a multi-GPU run (particles are partitioned in contiguous blocks
+ * of n_per_rank by global id; this rank propagates its n local slots, whose global ids start at gid0).
+ * `anc[p]` is the GLOBAL ancestor of local slot p; its row, aux and label are read straight from the owning rank's
+ * buffers through peer-mapped pointers (peer_*[rank], CUDA IPC over NVLink): the resampling gather, the particle
+ * migration and the propagation are ONE kernel.  cum_in points at this rank's slice of the cumulative works. */
+CDW_API int cdw_smc_propagate_sharded(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel,
+                                      const double* const* peer_aux, const int32_t* const* peer_label, int32_t n_ranks,
+                                      int64_t n_per_rank, float* pos_out, float* vel_out, int64_t n_particles, const int32_t* anc,
+                                      const double* cum_in, const double* lambda, const cdw_langevin_params* params, uint64_t seed,
+                                      uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out,
+                                      int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream);
+
 /* replaces: OMMBIP.apply (openmm/propagators.py:89-219) for a batch, in place.  Thin wrapper over the kernel above. */
 CDW_API int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_particles, const double* lambda,
               const cdw_langevin_params* params, uint64_t seed, uint64_t step0, int64_t gid0, double* u_first_out,
