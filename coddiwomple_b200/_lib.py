@@ -94,6 +94,7 @@ _SIGNATURES = {
     "cdw_weight_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "cdw_weight_stats": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, _P, C.c_size_t, _P]),
     "cdw_resample_indices": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "cdw_smc_resample": (C.c_int, [C.c_int, _P, C.c_int64, C.c_double, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "cdw_gather_particles": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "cdw_gather_particles_peer": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "cdw_fill_u64": (C.c_int, [_P, C.c_uint64, C.c_int64, _P]),

@@ -8,6 +8,8 @@
 // Exactness: ancestors come from an INTEGER cdf (weights quantised with det_exp + rint, uint64 prefix sum, integer
 // search), so they are independent of summation order, block schedule and GPU count, and equal oracle/resampling.py
 // bit for bit.
+#include <stdlib.h>
+
 #include "cdw_common.h"
 
 namespace cdw {
@@ -278,6 +280,126 @@ __global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K2 + K3a fused (small n)
+// One CTA does everything after the propagate kernel for n <= kFusedMax particles: log-sum-exp / nESS / decision,
+// Philox uniforms, integer cdf (kept in shared memory), search, cum update, and re-arming of the running-min key.
+// Same integer algorithm as the multi-kernel path => same ancestors bit for bit; for batches this small the
+// multi-kernel path is pure launch latency (7 launches for ~30 us of work at n = 1e4).
+constexpr int kFusedThreads = 1024;
+constexpr int kFusedMax = 16384;
+
+__device__ __forceinline__ double philox_uniform53(unsigned long long seed, unsigned long long stream_id, long long i) {
+    u4 c;
+    const long long pair = i >> 1;
+    c.x = (uint32_t)pair; c.y = (uint32_t)((unsigned long long)pair >> 32); c.z = (uint32_t)stream_id; c.w = 0x5EEDu;
+    const u4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const unsigned long long bits = (i & 1) ? ((((unsigned long long)r.z << 32) | r.w) >> 11) : ((((unsigned long long)r.x << 32) | r.y) >> 11);
+    return (double)bits * 1.1102230246251565e-16;
+}
+
+__global__ void __launch_bounds__(kFusedThreads) fused_resample_kernel(int kind, const double* __restrict__ w, int n, double threshold,
+                                                                      unsigned long long* wmin_key, unsigned long long seed, unsigned long long stream_id,
+                                                                      double* stats, const double* cum_in, double* cum_out, int* __restrict__ anc,
+                                                                      double* __restrict__ uniforms_out, int s1) {
+    extern __shared__ __align__(16) unsigned long long cdf[];  // [n]
+    __shared__ double shd[kFusedThreads / 32];
+    __shared__ unsigned long long shu[kFusedThreads / 32];
+    __shared__ unsigned long long carry_sh;
+    __shared__ double bc[4];
+    __shared__ int shift_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double wmin = ordered_key_inverse(*wmin_key);
+    const double scale1 = pow2(s1);
+    double se = 0.0, se2 = 0.0;
+    unsigned long long t1 = 0;
+    for (int i = tid; i < n; i += kFusedThreads) {
+        const double e = det_exp(CDW_ADD(wmin, -w[i]));
+        se += e;
+        se2 += e * e;
+        t1 += __double2ull_rn(CDW_MUL(e, scale1));
+    }
+    se = block_reduce(se, [](double a, double b) { return a + b; }, shd);
+    se2 = block_reduce(se2, [](double a, double b) { return a + b; }, shd);
+    t1 = block_reduce(t1, [](unsigned long long a, unsigned long long b) { return a + b; }, shu);
+    if (tid == 0) {
+        const int bitlen = 64 - __clzll((long long)t1);
+        int shift = 60 - bitlen;
+        shift = shift < 0 ? 0 : shift;
+        shift_sh = s1 + shift;
+        const double ness = (se * se) / ((double)n * se2);
+        const double mean = wmin - log(se) + log((double)n);
+        const double res = (threshold < 0.0 || ness <= threshold) ? 1.0 : 0.0;
+        stats[CDW_STAT_WMIN] = wmin; stats[CDW_STAT_SUM_E] = se; stats[CDW_STAT_SUM_E2] = se2; stats[CDW_STAT_NESS] = ness;
+        stats[CDW_STAT_MEAN] = mean; stats[CDW_STAT_RESAMPLE] = res; stats[CDW_STAT_TOTAL] = 0.0; stats[CDW_STAT_NNAN] = 0.0;
+        bc[0] = res; bc[1] = mean;
+        carry_sh = 0;
+        *wmin_key = ~0ull;  // re-arm the running min for the next propagate launch
+    }
+    __syncthreads();
+    const bool resample = bc[0] != 0.0;
+    const double mean = bc[1];
+    if (!resample) {
+        for (int i = tid; i < n; i += kFusedThreads) {
+            anc[i] = i;
+            if (cum_out) cum_out[i] = w[i];  // null update (resamplers.py:136-156)
+        }
+        return;
+    }
+    const double scale = pow2(shift_sh);
+    // integer cdf in shared memory: chunks of 1024 consecutive elements, block-wide inclusive scan + running carry
+    for (int base = 0; base < n; base += kFusedThreads) {
+        const int i = base + tid;
+        const unsigned long long v = i < n ? quantise(w[i], wmin, scale) : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) shu[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long t = shu[lane];
+            unsigned long long sc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, sc, o);
+                if (lane >= o) sc += u;
+            }
+            shu[lane] = sc - t;
+        }
+        __syncthreads();
+        const unsigned long long mine = carry_sh + shu[warp] + incl;
+        if (i < n) cdf[i] = mine;
+        __syncthreads();
+        if (tid == kFusedThreads - 1) carry_sh = mine;
+        __syncthreads();
+    }
+    const unsigned long long total = carry_sh;
+    if (tid == 0) stats[CDW_STAT_TOTAL] = (double)total;
+    const double u0 = kind == CDW_RESAMPLE_SYSTEMATIC ? philox_uniform53(seed, stream_id, 0) : 0.0;
+    if (tid == 0 && uniforms_out && kind == CDW_RESAMPLE_SYSTEMATIC) uniforms_out[0] = u0;
+    for (int i = tid; i < n; i += kFusedThreads) {
+        double u;
+        if (kind == CDW_RESAMPLE_SYSTEMATIC) u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
+        else {
+            u = philox_uniform53(seed, stream_id, i);
+            if (uniforms_out) uniforms_out[i] = u;
+        }
+        const unsigned long long target = fixed_target(u, total);
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf[mid] > target) hi = mid; else lo = mid + 1;
+        }
+        anc[i] = lo;
+        if (cum_out) {
+            const double c = cum_in ? cum_in[i] : 0.0;
+            cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K3b: gather
 __global__ void __launch_bounds__(kBlock) gather_kernel(const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
                                                         const int* __restrict__ anc, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
@@ -416,6 +538,36 @@ extern "C" int cdw_resample_indices(int kind, const double* w, const double* uni
     search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
+}
+
+extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double floor_threshold, uint64_t* wmin_key, uint64_t seed, uint64_t stream_id,
+                                double* stats, const double* cum_in, double* cum_out, int32_t* anc_out, uint64_t* cdf_out, double* uniforms,
+                                void* workspace, size_t workspace_bytes, cdw_stream stream) {
+    CDW_REQUIRE(w && wmin_key && stats && anc_out && cdf_out && uniforms && workspace && n > 0, "null argument or n == 0");
+    CDW_REQUIRE(kind == CDW_RESAMPLE_MULTINOMIAL || kind == CDW_RESAMPLE_SYSTEMATIC, "unknown resampler kind");
+    CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
+    cudaStream_t st = (cudaStream_t)stream;
+    static const char* no_fuse = getenv("CDW_NO_FUSED_RESAMPLE");
+    if (n <= kFusedMax && !no_fuse) {
+        int b = 0;
+        while ((1ll << b) < n) ++b;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CDW_CUDA(cudaFuncSetAttribute((const void*)fused_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kFusedMax)));
+            attr_set = true;
+        }
+        fused_resample_kernel<<<1, kFusedThreads, sizeof(unsigned long long) * (size_t)n, st>>>(kind, w, (int)n, floor_threshold, (unsigned long long*)wmin_key, seed,
+                                                                                                  stream_id, stats, cum_in, cum_out, anc_out, uniforms, 61 - b);
+        CDW_CUDA(cudaGetLastError());
+        return CDW_OK;
+    }
+    int rc = cdw_weight_stats(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    rc = cdw_philox_uniforms(seed, stream_id, kind == CDW_RESAMPLE_MULTINOMIAL ? n : 1, uniforms, stream);
+    if (rc) return rc;
+    rc = cdw_resample_indices(kind, w, uniforms, n, stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return cdw_fill_u64(wmin_key, ~0ull, 1, stream);
 }
 
 extern "C" int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,

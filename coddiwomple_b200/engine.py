@@ -194,6 +194,7 @@ class ParticleEnsemble:
         self.aux[self.cur].copy_(-u0)
         self.cum.zero_()
         self.iteration = 0
+        self.wmin_key.fill_(-1)  # ~0ull: arm the running min; cdw_smc_resample re-arms it after every iteration
         return u0
 
     def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None):
@@ -202,7 +203,6 @@ class ParticleEnsemble:
         c, n = self.cur, 1 - self.cur
         flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0) | (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
         prm = langevin.as_struct(flags)
-        self.wmin_key.fill_(-1)  # ~0ull
         o = outputs or {}
         anc = self.anc if self.pending_gather else None
         _lib.check(self.lib.cdw_smc_propagate(
@@ -213,6 +213,14 @@ class ParticleEnsemble:
             _lib.ptr(o.get("proposal")), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), _lib.current_stream()), "cdw_smc_propagate")
         self.cur = n
         self.pending_gather = False
+
+    def resample_fused(self, stats_row, kind, floor_threshold, seed, stream_id):
+        """K2 second half + K3a (+ uniforms, + re-arming the running min) in one call: cdw_smc_resample."""
+        _lib.check(self.lib.cdw_smc_resample(int(kind), _lib.ptr(self.W), self.P, float(floor_threshold), _lib.ptr(self.wmin_key), C.c_uint64(seed),
+                                            C.c_uint64(stream_id), _lib.ptr(stats_row), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(self.anc),
+                                            _lib.ptr(self.cdf), _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()),
+                   "cdw_smc_resample")
+        self.pending_gather = True
 
     def weight_stats(self, stats_row, floor_threshold, w=None, wmin_key=None, n=None):
         """Second half of K2: log-sum-exp, nESS, the resampling decision -> stats_row[8] (device)."""
@@ -261,10 +269,15 @@ class SMCEngine:
     def beta(self):
         return 1.0 / self.langevin.kT
 
-    def initialize(self, positions, velocities=None):
+    def load(self, positions, velocities=None):
+        """Stage the initial particles (samples of the first target) into buffer 0."""
         e = self.ensemble
+        e.cur, e.pending_gather, e.iteration = 0, False, 0
         e.set_positions(positions, velocities)
-        e.equip_initial(self.lam[0], self.beta)
+
+    def initialize(self, positions, velocities=None):
+        self.load(positions, velocities)
+        self.ensemble.equip_initial(self.lam[0], self.beta)
         self.stats.zero_()
 
     def propagate(self, t):
@@ -274,10 +287,8 @@ class SMCEngine:
     def finish_iteration(self, t):
         """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + search, cum update."""
         e = self.ensemble
-        e.weight_stats(self.stats[t], self.threshold)
+        e.resample_fused(self.stats[t], self.kind, self.threshold, self.resample_seed, t)
         n_u = e.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
-        e.draw_uniforms(self.resample_seed, t, n_u)
-        e.resample(self.stats[t], self.kind)
         if e.record_history:
             e.history.append(dict(t=t, inc=e.inc.clone(), W=e.W.clone(), cum=e.cum.clone(), anc=e.anc.clone(), uniforms=e.uniforms[:n_u].clone()))
 
@@ -293,8 +304,45 @@ class SMCEngine:
         return self
 
     def anneal(self, positions, velocities=None):
+        if self.graph is not None:
+            return self.anneal_graph(positions, velocities)
         self.initialize(positions, velocities)
         return self.run()
+
+    # ------------------------------------------------------------------ CUDA graph of the whole anneal
+    def _body(self):
+        self.ensemble.equip_initial(self.lam[0], self.beta)
+        self.stats.zero_()
+        self.run()
+
+    def capture(self):
+        """Capture `equip initial sample + T-1 iterations + final gather` (2 T launches) into one CUDA graph.
+        The loop has no host decision (the resampling test runs on the device), so the whole anneal replays as a
+        single graph launch; positions are (re)staged with load() before each replay."""
+        e = self.ensemble
+        if e.record_history:
+            raise ValueError("record_history needs the eager loop")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
+            e.cur, e.pending_gather, e.iteration = 0, False, 0
+            self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        e.cur, e.pending_gather, e.iteration = 0, False, 0
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self._graph_final = (e.cur, e.pending_gather, e.iteration)
+        self.graph = g
+        return self
+
+    def anneal_graph(self, positions, velocities=None):
+        self.load(positions, velocities)
+        self.graph.replay()
+        e = self.ensemble
+        e.cur, e.pending_gather, e.iteration = self._graph_final
+        return self
 
     # ------------------------------------------------------------------ results (host side; these synchronise)
     def cumulative_works(self):

@@ -195,14 +195,9 @@ class ShardedSMCEngine:
         self.scratch_key.fill_(-1)
         _lib.check(self.lib.cdw_weight_update(_lib.ptr(self.W), None, None, None, self.P, None, _lib.ptr(self.W_copy), _lib.ptr(self.scratch_key),
                                              _lib.current_stream()), "cdw_weight_update")
-        _lib.check(self.lib.cdw_weight_stats(_lib.ptr(self.W), self.P, self.threshold, _lib.ptr(self.scratch_key), _lib.ptr(self.stats[t]),
-                                            _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_weight_stats")
-        n_u = self.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
-        _lib.check(self.lib.cdw_philox_uniforms(C.c_uint64(self.resample_seed), C.c_uint64(t), n_u, _lib.ptr(self.uniforms), _lib.current_stream()),
-                   "cdw_philox_uniforms")
-        _lib.check(self.lib.cdw_resample_indices(self.kind, _lib.ptr(self.W), _lib.ptr(self.uniforms), self.P, _lib.ptr(self.stats[t]), _lib.ptr(self.cum),
-                                                _lib.ptr(self.cum), _lib.ptr(self.anc), _lib.ptr(self.cdf), _lib.ptr(self.workspace), self.ws_bytes,
-                                                _lib.current_stream()), "cdw_resample_indices")
+        _lib.check(self.lib.cdw_smc_resample(self.kind, _lib.ptr(self.W), self.P, self.threshold, _lib.ptr(self.scratch_key), C.c_uint64(self.resample_seed),
+                                            C.c_uint64(t), _lib.ptr(self.stats[t]), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(self.anc), _lib.ptr(self.cdf),
+                                            _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_smc_resample")
         self.pending_gather = True
 
     def step(self, t):
@@ -227,6 +222,8 @@ class ShardedSMCEngine:
             self.step(t)
         self.materialize()
         return self
+
+    graph = None
 
     def anneal(self, positions_local, velocities_local=None):
         self.initialize(positions_local, velocities_local)

@@ -205,6 +205,15 @@ CDW_API int cdw_resample_indices(int kind, const double* w, const double* unifor
                          const double* cum_in, double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace,
                          size_t workspace_bytes, cdw_stream stream);
 
+/* K2 (second half) + K3a in one call: everything between two propagate launches of the SMC loop
+ * (openmm/coddiwomple.py:318).  Uniforms come from Philox (seed, stream_id): n draws for multinomial, one for systematic
+ * (written to `uniforms` for inspection).  *wmin_key (the running min left by cdw_smc_propagate) is consumed and re-armed
+ * to ~0.  For n <= 16384 this is a single one-CTA kernel with the integer cdf in shared memory; larger batches run
+ * cdw_weight_stats + cdw_philox_uniforms + cdw_resample_indices.  Same ancestors either way. */
+CDW_API int cdw_smc_resample(int kind, const double* w, int64_t n, double floor_threshold, uint64_t* wmin_key, uint64_t seed,
+                             uint64_t stream_id, double* stats, const double* cum_in, double* cum_out, int32_t* anc_out,
+                             uint64_t* cdf_out, double* uniforms, void* workspace, size_t workspace_bytes, cdw_stream stream);
+
 /* K3b. replaces: the per-particle deepcopy loop of Resampler.resample (resamplers.py:123-129,193). */
 CDW_API int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
                          const double* aux_in, double* aux_out, const int32_t* label_in, int32_t* label_out,
