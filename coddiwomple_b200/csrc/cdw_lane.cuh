@@ -246,8 +246,8 @@ template <bool F>
 CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
     CDW_UNPACK(M);
     const int A = s.n_atoms;
-    const float* x = M.x;
-    float* f = M.f + tl * (3 * kR) * A;  // this lane's force copy
+    const float* __restrict__ x = M.x;
+    float* __restrict__ f = M.f + tl * (3 * kR) * A;  // this lane's force copy
     CDW_TEAM_SYNC(M);
     if (F) {
         for (int a = 0; a < A; ++a) {
@@ -277,13 +277,26 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
         e += torsion_term<F>(ld3(x, bi), ld3(x, bj), ld3(x, bk), ld3(x, bl), t.kk, t.c0, t.s0, t.n, fi, fj, fk, fl);
         if (F) { add3f(f, bi, fi); add3f(f, bj, fj); add3f(f, bk, fk); add3f(f, bl, fl); }
     }
-    for (int q = tl; q < s.n_pairs; q += T_) {
-        const EffPair& p = T.pairs[q];
-        const int bi = CDW_BASE(p.i), bj = CDW_BASE(p.j);
-        const d3 d = ld3(x, bi) - ld3(x, bj);
-        double g;
-        e += pair_term<F>(p, d, g);
-        if (F) { const d3 fj = g * d; add3f(f, bi, -1.0 * fj); add3f(f, bj, fj); }
+    {
+        // pairs are sorted by (i, j); each lane takes a contiguous block, so runs of pairs share atom i: its position is
+        // loaded once and its force is accumulated in registers (fp64) and flushed when the run ends
+        const int per = (s.n_pairs + T_ - 1) / T_;
+        const int q0 = tl * per, q1 = q0 + per < s.n_pairs ? q0 + per : s.n_pairs;
+        int cur = -1, bi = 0;
+        d3 xi = mk3(0.0, 0.0, 0.0), fi = mk3(0.0, 0.0, 0.0);
+        for (int q = q0; q < q1; ++q) {
+            const EffPair& p = T.pairs[q];
+            if (p.i != cur) {
+                if (F && cur >= 0) add3f(f, bi, fi);
+                cur = p.i; bi = CDW_BASE(cur); xi = ld3(x, bi); fi = mk3(0.0, 0.0, 0.0);
+            }
+            const int bj = CDW_BASE(p.j);
+            const d3 d = xi - ld3(x, bj);
+            double g;
+            e += pair_term<F>(p, d, g);
+            if (F) { const d3 fj = g * d; fi = fi - fj; add3f(f, bj, fj); }
+        }
+        if (F && cur >= 0) add3f(f, bi, fi);
     }
     for (int q = tl; q < s.n_ext; q += T_) {
         const EffExt w = T.exts[q];

@@ -107,7 +107,8 @@ template <bool F>
 CDW_HD double angle_term(d3 xi, d3 xj, d3 xk, double K, double T0, d3& fi, d3& fk) {
     d3 a = xi - xj, b = xk - xj;
     double a2 = dot(a, a), b2 = dot(b, b);
-    double c = dot(a, b) * CDW_RSQRT(a2 * b2);
+    const double iab = CDW_RSQRT(a2 * b2);  // 1 / (|a| |b|)
+    double c = dot(a, b) * iab;
     c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
     double th = acos(c);
     double dth = th - T0;
@@ -115,9 +116,9 @@ CDW_HD double angle_term(d3 xi, d3 xj, d3 xk, double K, double T0, d3& fi, d3& f
         d3 cp = cross(a, b);
         double cp2 = dot(cp, cp);
         cp2 = cp2 < 1e-24 ? 1e-24 : cp2;
-        double de = K * dth * CDW_RSQRT(cp2);
-        fi = (de / a2) * cross(cp, a);
-        fk = (de / b2) * cross(b, cp);
+        const double de = K * dth * CDW_RSQRT(cp2) * (iab * iab);  // 1/a2 = iab^2 b2, 1/b2 = iab^2 a2: no divisions
+        fi = (de * b2) * cross(cp, a);
+        fk = (de * a2) * cross(b, cp);
     }
     return 0.5 * K * dth * dth;
 }
@@ -141,9 +142,9 @@ CDW_HD double torsion_term(d3 xi, d3 xj, d3 xk, d3 xl, double kk, double c0, dou
         cn = t;
     }
     if (F) {
-        double de = -kk * (double)n * (sn * c0 - cn * s0);  // dE/dphi
-        fi = (de * rb2 / n1sq) * n1;
-        fl = (-de * rb2 / n2sq) * n2;
+        const double de = -kk * (double)n * (sn * c0 - cn * s0) * rb2 * (inv * inv);  // dE/dphi |b2| / (n1sq n2sq)
+        fi = (de * n2sq) * n1;    // 1/n1sq = inv^2 n2sq: no divisions
+        fl = (-de * n1sq) * n2;
         double ib2 = irb2 * irb2;
         double sa = dot(b1, b2) * ib2, ta = dot(b3, b2) * ib2;
         fj = (-1.0 - sa) * fi + ta * fl;
@@ -152,37 +153,32 @@ CDW_HD double torsion_term(d3 xi, d3 xj, d3 xk, d3 xl, double kk, double c0, dou
     return kk * (1.0 + cn * c0 + sn * s0);
 }
 
-// nonbonded pair: returns energy; g = (dE/dr)/r so that force on i is -g * (xi - xj)
+// nonbonded pair: returns energy; g = (dE/dr)/r so that force on i is -g * (xi - xj).
+// Branch-free over the three parts (Coulomb, plain LJ, soft-core LJ): an absent part has zero coefficients, so all
+// lanes of a warp run the same instruction stream whatever pair they hold; only the quadratic cap (r < r_LJ, which
+// exists for lambda-softened pairs only) is a branch.
 template <bool F>
 CDW_HD double pair_term(const EffPair& p, d3 d, double& g) {
-    double r2 = dot(d, d);
-    double ir = CDW_RSQRT(r2);
-    double ir2 = ir * ir;
-    double r = r2 * ir;
-    double e = 0.0;
-    g = 0.0;
-    if (p.flags & CDW_PAIR_NB) {
-        double ec = p.qqC * ir;
-        e += ec;
-        if (F) g -= ec * ir2;
-        if (p.flags & CDW_PAIR_LJ) {
-            double s2 = p.sig * p.sig * ir2, s6 = s2 * s2 * s2;
-            e += 4.0 * p.eps * s6 * (s6 - 1.0);
-            if (F) g += 4.0 * p.eps * (-12.0 * s6 * s6 + 6.0 * s6) * ir2;
+    const double r2 = dot(d, d);
+    const double ir = CDW_RSQRT(r2);
+    const double ir2 = ir * ir;
+    const double ec = p.qqC * ir;                                   // 138.935456 qq / r
+    const double s2 = p.sig * p.sig * ir2, s6 = s2 * s2 * s2;       // plain LJ (NonbondedForce)
+    const double t2 = p.sc_sig * p.sc_sig * ir2, x6 = t2 * t2 * t2; // soft-core LJ outside r_LJ
+    double e = ec + 4.0 * p.eps * s6 * (s6 - 1.0);
+    double esc = 4.0 * p.sc_eps * x6 * (x6 - 1.0);
+    if (F) g = (-ec + 4.0 * p.eps * (6.0 * s6 - 12.0 * s6 * s6)) * ir2;
+    double gsc = F ? 4.0 * p.sc_eps * (6.0 * x6 - 12.0 * x6 * x6) * ir2 : 0.0;
+    if (p.sc_rlj > 0.0) {
+        const double r = r2 * ir;
+        if (r < p.sc_rlj) {
+            const double dr = r - p.sc_rlj;
+            esc = p.sc_F * (0.5 * dr * dr - dr) + p.sc_U;
+            gsc = p.sc_F * (dr - 1.0) * ir;
         }
     }
-    if (p.flags & CDW_PAIR_SC) {
-        if ((p.flags & CDW_PAIR_CAP) && r < p.sc_rlj) {
-            double dr = r - p.sc_rlj;
-            e += p.sc_F * (0.5 * dr * dr - dr) + p.sc_U;
-            if (F) g += p.sc_F * (dr - 1.0) * ir;
-        } else {
-            double s2 = p.sc_sig * p.sc_sig * ir2, x = s2 * s2 * s2;
-            e += 4.0 * p.sc_eps * x * (x - 1.0);
-            if (F) g += 4.0 * p.sc_eps * (-12.0 * x * x + 6.0 * x) * ir2;
-        }
-    }
-    return e;
+    if (F) g += gsc;
+    return e + esc;
 }
 
 template <bool F>

@@ -249,7 +249,7 @@ def spec_from_xml(xml_text):
                     if exc[k][0] == 0 and exc[k][2] == 0 and k not in off_by_exc:
                         continue  # a plain exclusion
                     pairs[(i, j)] = k
-    keys = sorted(set(pairs) | set(sc_pairs))
+    keys = sorted(set(pairs) | set(sc_pairs))  # sorted by (i, j): the kernel keeps atom i in registers over a run of pairs
     pair_atoms = [k for k in keys]
     pair_nb = [pairs.get(k, -1) for k in keys]
     pair_sc_class = [sc_pairs[k][0] if k in sc_pairs else -1 for k in keys]
