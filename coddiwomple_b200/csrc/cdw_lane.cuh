@@ -284,7 +284,32 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
         const int q0 = tl * per, q1 = q0 + per < s.n_pairs ? q0 + per : s.n_pairs;
         int cur = -1, bi = 0;
         d3 xi = mk3(0.0, 0.0, 0.0), fi = mk3(0.0, 0.0, 0.0);
-        for (int q = q0; q < q1; ++q) {
+        int q = q0;
+        for (; q + 1 < q1; q += 2) {  // two pairs per trip: their arithmetic is independent and interleaves
+            const EffPair& pa = T.pairs[q];
+            const EffPair& pb = T.pairs[q + 1];
+            if (pa.i != cur) {
+                if (F && cur >= 0) add3f(f, bi, fi);
+                cur = pa.i; bi = CDW_BASE(cur); xi = ld3(x, bi); fi = mk3(0.0, 0.0, 0.0);
+            }
+            const bool same = pb.i == cur;
+            const int bib = same ? bi : CDW_BASE(pb.i);
+            const d3 xib = same ? xi : ld3(x, bib);
+            const int bja = CDW_BASE(pa.j), bjb = CDW_BASE(pb.j);
+            const d3 da = xi - ld3(x, bja), db = xib - ld3(x, bjb);
+            double ga, gb;
+            e += pair_term<F>(pa, da, ga);
+            e += pair_term<F>(pb, db, gb);
+            if (F) {
+                const d3 fja = ga * da, fjb = gb * db;
+                fi = fi - fja;
+                add3f(f, bja, fja);
+                if (!same) { add3f(f, bi, fi); cur = pb.i; bi = bib; xi = xib; fi = mk3(0.0, 0.0, 0.0); }
+                fi = fi - fjb;
+                add3f(f, bjb, fjb);
+            } else if (!same) { cur = pb.i; bi = bib; xi = xib; }
+        }
+        for (; q < q1; ++q) {
             const EffPair& p = T.pairs[q];
             if (p.i != cur) {
                 if (F && cur >= 0) add3f(f, bi, fi);

@@ -156,7 +156,7 @@ CDW_HD double torsion_term(d3 xi, d3 xj, d3 xk, d3 xl, double kk, double c0, dou
 // nonbonded pair: returns energy; g = (dE/dr)/r so that force on i is -g * (xi - xj).
 // Branch-free over the three parts (Coulomb, plain LJ, soft-core LJ): an absent part has zero coefficients, so all
 // lanes of a warp run the same instruction stream whatever pair they hold; only the quadratic cap (r < r_LJ, which
-// exists for lambda-softened pairs only) is a branch.
+// exists for lambda-softened pairs only) is a select.
 template <bool F>
 CDW_HD double pair_term(const EffPair& p, d3 d, double& g) {
     const double r2 = dot(d, d);
@@ -169,14 +169,12 @@ CDW_HD double pair_term(const EffPair& p, d3 d, double& g) {
     double esc = 4.0 * p.sc_eps * x6 * (x6 - 1.0);
     if (F) g = (-ec + 4.0 * p.eps * (6.0 * s6 - 12.0 * s6 * s6)) * ir2;
     double gsc = F ? 4.0 * p.sc_eps * (6.0 * x6 - 12.0 * x6 * x6) * ir2 : 0.0;
-    if (p.sc_rlj > 0.0) {
-        const double r = r2 * ir;
-        if (r < p.sc_rlj) {
-            const double dr = r - p.sc_rlj;
-            esc = p.sc_F * (0.5 * dr * dr - dr) + p.sc_U;
-            gsc = p.sc_F * (dr - 1.0) * ir;
-        }
-    }
+    // quadratic cap inside r_LJ (r_LJ = 0 when the pair is not softened: never taken); selects, not branches, so that
+    // two pairs can be evaluated in one basic block (instruction-level parallelism)
+    const double dr = r2 * ir - p.sc_rlj;
+    const bool cap = dr < 0.0;
+    esc = cap ? p.sc_F * (0.5 * dr * dr - dr) + p.sc_U : esc;
+    gsc = cap ? p.sc_F * (dr - 1.0) * ir : gsc;
     if (F) g += gsc;
     return e + esc;
 }
