@@ -238,6 +238,12 @@ CDW_HD void build_tables(const SysDev& s, const Tables& T, const double* lam_g, 
 CDW_HD d3 ld3(const float* arr, int base) { return mk3((double)arr[base], (double)arr[base + kR], (double)arr[base + 2 * kR]); }
 CDW_HD void st3(float* arr, int base, d3 v) { arr[base] = (float)v.x; arr[base + kR] = (float)v.y; arr[base + 2 * kR] = (float)v.z; }
 CDW_HD void add3f(float* arr, int base, d3 v) { arr[base] += (float)v.x; arr[base + kR] += (float)v.y; arr[base + 2 * kR] += (float)v.z; }
+struct f3 {
+    float x, y, z;
+};
+CDW_HD f3 ldf3(const float* arr, int base) { f3 r; r.x = arr[base]; r.y = arr[base + kR]; r.z = arr[base + 2 * kR]; return r; }
+CDW_HD d3 widen(f3 a) { return mk3((double)a.x, (double)a.y, (double)a.z); }
+CDW_HD void add3ff(float* arr, int base, f3 v) { arr[base] += v.x; arr[base + kR] += v.y; arr[base + 2 * kR] += v.z; }
 
 // Potential energy (kJ/mol) of the team's replica (same value in every lane of the team).  With F the forces end up
 // in force copy 0: each lane accumulates the terms it evaluates into its own copy, then the copies are summed.
@@ -282,46 +288,59 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
         // loaded once and its force is accumulated in registers (fp64) and flushed when the run ends
         const int per = (s.n_pairs + T_ - 1) / T_;
         const int q0 = tl * per, q1 = q0 + per < s.n_pairs ? q0 + per : s.n_pairs;
+        // Geometry and energy in fp64 from the fp32 coordinates; the FORCE vector is formed in fp32 (g rounded once, fp32
+        // coordinate differences) because it is accumulated in fp32 anyway: one fp64->fp32 conversion per pair instead of
+        // three (conversions run on the quarter-rate XU pipe, the busiest pipe of this kernel).
         int cur = -1, bi = 0;
-        d3 xi = mk3(0.0, 0.0, 0.0), fi = mk3(0.0, 0.0, 0.0);
+        f3 xi32 = {0.f, 0.f, 0.f}, fi = {0.f, 0.f, 0.f};
+        d3 xi = mk3(0.0, 0.0, 0.0);
         int q = q0;
+#define CDW_PAIR_RUN(P)                                                              \
+        if ((P).i != cur) {                                                          \
+            if (F && cur >= 0) add3ff(f, bi, fi);                                    \
+            cur = (P).i; bi = CDW_BASE(cur); xi32 = ldf3(x, bi); xi = widen(xi32);   \
+            fi.x = fi.y = fi.z = 0.f;                                                \
+        }
+#define CDW_PAIR_APPLY(G, XJ32, BJ)                                                  \
+        {                                                                            \
+            const float g32 = (float)(G);                                            \
+            f3 fj;                                                                   \
+            fj.x = g32 * (xi32.x - (XJ32).x); fj.y = g32 * (xi32.y - (XJ32).y); fj.z = g32 * (xi32.z - (XJ32).z); \
+            fi.x -= fj.x; fi.y -= fj.y; fi.z -= fj.z;                                \
+            add3ff(f, (BJ), fj);                                                     \
+        }
         for (; q + 1 < q1; q += 2) {  // two pairs per trip: their arithmetic is independent and interleaves
             const EffPair& pa = T.pairs[q];
             const EffPair& pb = T.pairs[q + 1];
-            if (pa.i != cur) {
-                if (F && cur >= 0) add3f(f, bi, fi);
-                cur = pa.i; bi = CDW_BASE(cur); xi = ld3(x, bi); fi = mk3(0.0, 0.0, 0.0);
-            }
-            const bool same = pb.i == cur;
-            const int bib = same ? bi : CDW_BASE(pb.i);
-            const d3 xib = same ? xi : ld3(x, bib);
+            CDW_PAIR_RUN(pa)
             const int bja = CDW_BASE(pa.j), bjb = CDW_BASE(pb.j);
-            const d3 da = xi - ld3(x, bja), db = xib - ld3(x, bjb);
-            double ga, gb;
-            e += pair_term<F>(pa, da, ga);
-            e += pair_term<F>(pb, db, gb);
-            if (F) {
-                const d3 fja = ga * da, fjb = gb * db;
-                fi = fi - fja;
-                add3f(f, bja, fja);
-                if (!same) { add3f(f, bi, fi); cur = pb.i; bi = bib; xi = xib; fi = mk3(0.0, 0.0, 0.0); }
-                fi = fi - fjb;
-                add3f(f, bjb, fjb);
-            } else if (!same) { cur = pb.i; bi = bib; xi = xib; }
+            const f3 xja = ldf3(x, bja), xjb = ldf3(x, bjb);
+            if (pb.i == cur) {
+                double ga, gb;
+                e += pair_term<F>(pa, xi - widen(xja), ga);
+                e += pair_term<F>(pb, xi - widen(xjb), gb);
+                if (F) { CDW_PAIR_APPLY(ga, xja, bja) CDW_PAIR_APPLY(gb, xjb, bjb) }
+            } else {
+                double ga, gb;
+                e += pair_term<F>(pa, xi - widen(xja), ga);
+                if (F) CDW_PAIR_APPLY(ga, xja, bja)
+                CDW_PAIR_RUN(pb)
+                e += pair_term<F>(pb, xi - widen(xjb), gb);
+                if (F) CDW_PAIR_APPLY(gb, xjb, bjb)
+            }
         }
         for (; q < q1; ++q) {
             const EffPair& p = T.pairs[q];
-            if (p.i != cur) {
-                if (F && cur >= 0) add3f(f, bi, fi);
-                cur = p.i; bi = CDW_BASE(cur); xi = ld3(x, bi); fi = mk3(0.0, 0.0, 0.0);
-            }
+            CDW_PAIR_RUN(p)
             const int bj = CDW_BASE(p.j);
-            const d3 d = xi - ld3(x, bj);
+            const f3 xj = ldf3(x, bj);
             double g;
-            e += pair_term<F>(p, d, g);
-            if (F) { const d3 fj = g * d; fi = fi - fj; add3f(f, bj, fj); }
+            e += pair_term<F>(p, xi - widen(xj), g);
+            if (F) CDW_PAIR_APPLY(g, xj, bj)
         }
-        if (F && cur >= 0) add3f(f, bi, fi);
+        if (F && cur >= 0) add3ff(f, bi, fi);
+#undef CDW_PAIR_RUN
+#undef CDW_PAIR_APPLY
     }
     for (int q = tl; q < s.n_ext; q += T_) {
         const EffExt w = T.exts[q];
