@@ -252,7 +252,7 @@ class SMCEngine:
     """
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5,
-                 always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None):
+                 always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None, record_works_every=None):
         self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history)
         self.system = self.ensemble.system
         self.langevin = langevin or LangevinParameters()
@@ -264,6 +264,12 @@ class SMCEngine:
         self.seed, self.resample_seed = int(seed), int(resample_seed)
         self.stats = torch.zeros(max(self.T, 1), _lib.STATS_LEN, dtype=torch.float64, device=self.ensemble.device)
         self.graph = None
+        # optional cumulative-work trajectory (the AIS state-work record, openmm/propagators.py:311-337)
+        self.record_works_every = int(record_works_every) if record_works_every else None
+        if self.record_works_every:
+            k = self.record_works_every
+            self._work_rows = [t for t in range(1, self.T) if t % k == 0 or t == self.T - 1]
+            self._works = torch.zeros(len(self._work_rows) + 1, self.ensemble.P, dtype=torch.float64, device=self.ensemble.device)
 
     @property
     def beta(self):
@@ -288,6 +294,8 @@ class SMCEngine:
         """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + search, cum update."""
         e = self.ensemble
         e.resample_fused(self.stats[t], self.kind, self.threshold, self.resample_seed, t)
+        if self.record_works_every and t in self._work_rows:
+            self._works[self._work_rows.index(t) + 1].copy_(e.cum)
         n_u = e.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
         if e.record_history:
             e.history.append(dict(t=t, inc=e.inc.clone(), W=e.W.clone(), cum=e.cum.clone(), anc=e.anc.clone(), uniforms=e.uniforms[:n_u].clone()))
@@ -357,6 +365,10 @@ class SMCEngine:
     def resampled_iterations(self):
         s = self.stats.cpu().numpy()
         return [t for t in range(1, self.T) if s[t, _lib.STAT_RESAMPLE] != 0.0]
+
+    def work_history(self):
+        """(n_records + 1, P) cumulative works in kT; row 0 is the zero every AIS record starts with."""
+        return self._works.cpu().numpy()
 
     def ness_trace(self):
         return self.stats[1:, _lib.STAT_NESS].cpu().numpy()

@@ -48,3 +48,52 @@ class OMMLI(LangevinParameters):
 
     def get_shadow_work(self, dimensionless=True):
         return self._get_energy_with_units("shadow_work", dimensionless)
+
+
+class OMMLIAIS(OMMLI):
+    """Annealed-importance-sampling Langevin integrator — coddiwomple/openmm/integrators.py:468-665.
+
+    Splitting "P I H N S V R O R V": before every BAOAB step the protocol advances (I: iteration += 1,
+    fractional_iteration = iteration / n_steps; H: lambda <- f(fractional_iteration)) and the state work accumulates
+    new_pe - old_pe at fixed coordinates (P, N, S).  That is exactly the incremental work the fused propagate kernel
+    computes (inc = u_k(x_{k-1}) - u_{k-1}(x_{k-1})), so AIS is the SMC loop with resampling switched off; the Lepton
+    update functions are lowered on the host to a [n_steps + 1][n_lambda] table (openmm/lepton.py).
+    """
+
+    def __init__(self, openmm_pdf_update_functions, n_steps, temperature=300.0, collision_rate=1.0, timestep=0.001, splitting="P I H N S V R O R V",
+                 constraint_tolerance=1e-6, **kwargs):
+        if openmm_pdf_update_functions is None:
+            raise Exception(f"the {self.__class__.__name__} class requires update functions")
+        if (n_steps < 0) or (n_steps != int(n_steps)):
+            raise Exception('n_steps must be an integer >= 0')
+        if " ".join(splitting.upper().split()) != "P I H N S V R O R V":
+            raise NotImplementedError(f"splitting {splitting!r}: only 'P I H N S V R O R V' is implemented")
+        self._openmm_pdf_update_functions = dict(openmm_pdf_update_functions)
+        self._n_steps = int(n_steps)
+        self._function_parameters = list(self._openmm_pdf_update_functions.keys())
+        super().__init__(temperature=temperature, collision_rate=collision_rate, timestep=timestep, splitting="V R O R V", constraint_tolerance=constraint_tolerance)
+        self._splitting = splitting
+
+    def parameter_sequence(self, start_parameters):
+        """lambda_0 = the pdf_state's current parameters (the driver resets them to the end state), then f(k / n_steps)."""
+        from .lepton import protocol_table
+        seq = [dict(start_parameters)]
+        for row in protocol_table(self._openmm_pdf_update_functions, self._n_steps):
+            full = dict(start_parameters)
+            full.update(row)
+            seq.append(full)
+        return seq
+
+    def reset(self):
+        super().reset()
+        self.state_work = 0.0
+        self.iteration = 0.0
+
+    def get_state_work(self, dimensionless=True):
+        return self._get_energy_with_units("state_work", dimensionless)
+
+    def set_state_work(self, work):
+        self.state_work = float(work)
+
+    def set_proposal_work(self, work):
+        self.proposal_work = float(work)

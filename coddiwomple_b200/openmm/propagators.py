@@ -98,3 +98,71 @@ class OMMBIP(Propagator):
         else:
             proposal_work = 0.
         return particle_state, proposal_work
+
+
+class OMMAISP(OMMBIP):
+    """Annealed Importance Sampling propagator — coddiwomple/openmm/propagators.py:264-344.
+
+    `apply` anneals the FULL protocol (fractional_iteration 0 -> 1) for one particle state and records the state-work
+    trajectory; `apply_batch` does the same for P particle states at once (one replica per team of GPU lanes) and
+    returns the (P, n_records) work matrix in kT."""
+
+    def __init__(self, openmm_pdf_state, integrator, record_state_work_interval=None, context_cache=None, reassign_velocities=False,
+                 n_restart_attempts=0, seed=None):
+        super().__init__(openmm_pdf_state, integrator, context_cache=context_cache, reassign_velocities=reassign_velocities,
+                         n_restart_attempts=n_restart_attempts, seed=seed)
+        pdf_state_parameters = list(self.pdf_state.get_parameters().keys())
+        function_parameters = self.integrator._function_parameters
+        assert set(pdf_state_parameters) == set(function_parameters), f"the pdf_state parameters ({pdf_state_parameters}) is not equal to the function parameters ({function_parameters})"
+        self._record_state_work_interval = record_state_work_interval
+        self._state_works = {}
+        self._state_works_counter = 0
+
+    @property
+    def state_works(self):
+        return self._state_works
+
+    def apply_batch(self, positions, n_steps=None, seed=None):
+        """positions: (P, A, 3) nm.  Returns (works[P][n_records] in kT, engine)."""
+        from ..engine import SMCEngine
+        n_steps = self.integrator._n_steps if n_steps is None else int(n_steps)
+        if n_steps != self.integrator._n_steps:
+            raise ValueError("n_steps must equal the integrator's protocol length")
+        seq = self.integrator.parameter_sequence(self.pdf_state.get_parameters())
+        P = np.asarray(positions).shape[0]
+        interval = self._record_state_work_interval
+        self._seed_counter = getattr(self, "_seed_counter", 0) + 1
+        eng = SMCEngine(self.pdf_state.device_system, P, seq, langevin=self.integrator, resampler="multinomial", floor_threshold=0.0,
+                        seed=(self._seed if seed is None else int(seed)) + 7919 * self._seed_counter, record_works_every=(interval or n_steps))
+        eng.anneal(positions)
+        works = eng.work_history()  # (n_records, P), first row = 0
+        return works.T, eng
+
+    def apply(self, particle_state, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, returnable_key=None, randomize_velocities=False,
+              **kwargs):
+        if reset_integrator:
+            self.integrator.reset()
+        works, eng = self.apply_batch(particle_state.positions[None], n_steps=n_steps)
+        self._current_state_works = [float(w) for w in works[0]]
+        self._state_works[self._state_works_counter] = list(self._current_state_works)
+        self._state_works_counter += 1
+        self.integrator.state_work = self._current_state_works[-1]
+        particle_state.positions = eng.ensemble.positions[0].double().cpu().numpy()
+        particle_state.velocities = eng.ensemble.velocities[0].double().cpu().numpy()
+        self.pdf_state.set_parameters({k: eng.parameter_sequence[-1][k] for k in self.pdf_state.get_parameters()})
+        return particle_state, 0.
+
+
+class OMMAISVP(OMMAISP):
+    """Verbose variant in the reference (coddiwomple/openmm/propagators.py:348-391); same arithmetic."""
+
+
+class OMMAISPR(OMMAISP):
+    """Trajectory-writing variant in the reference (coddiwomple/openmm/propagators.py:394-478); writing is out of scope,
+    the work bookkeeping is identical."""
+
+    def __init__(self, openmm_pdf_state, integrator, record_state_work_interval=None, reporter=None, trajectory_write_interval=1, context_cache=None,
+                 reassign_velocities=False, n_restart_attempts=0, seed=None):
+        super().__init__(openmm_pdf_state, integrator, record_state_work_interval=record_state_work_interval, context_cache=context_cache,
+                         reassign_velocities=reassign_velocities, n_restart_attempts=n_restart_attempts, seed=seed)
+        self._reporter = reporter

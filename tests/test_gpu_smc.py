@@ -227,3 +227,54 @@ def test_Resampler_on_python_particles_matches_the_reference(case):
     np.testing.assert_array_equal([p.ancestry[-1] for p in particles], c["after_thresholded"]["ancestry_last"])
     np.testing.assert_array_equal([p.auxiliary_work for p in particles], c["after_thresholded"]["auxiliary_work"])
     np.testing.assert_allclose([p.cumulative_work for p in particles], c["after_thresholded"]["cumulative_work"], rtol=1e-12, atol=1e-12)
+
+
+def test_annealed_importance_sampling_driver_and_propagator():
+    """AIS mode (coddiwomple/tests/legacy_tests.py:24-50 re-expressed): the state-work record has the
+    reference's shape, the works equal the oracle's resampling-free anneal at the first steps, and the Jarzynski estimate of
+    the harmonic test system is 1 kT."""
+    import os
+    from coddiwomple_b200.openmm.coddiwomple import annealed_importance_sampling
+    from coddiwomple_b200.openmm.integrators import OMMLIAIS
+    from coddiwomple_b200.openmm.propagators import OMMAISP
+    from coddiwomple_b200.openmm.states import HarmonicAlchemicalState, OpenMMParticleState, OpenMMPDFState, RelativeAlchemicalState
+    x = 'fractional_iteration'
+    alchemical_functions = {'lambda_sterics_core': x, 'lambda_electrostatics_core': x,
+                            'lambda_sterics_insert': f"select(step({x} - 0.5), 1.0, 2.0 * {x})",
+                            'lambda_sterics_delete': f"select(step({x} - 0.5), 2.0 * ({x} - 0.5), 0.0)",
+                            'lambda_electrostatics_insert': f"select(step({x} - 0.5), 2.0 * ({x} - 0.5), 0.0)",
+                            'lambda_electrostatics_delete': f"select(step({x} - 0.5), 1.0, 2.0 * {x})",
+                            'lambda_bonds': x, 'lambda_angles': x, 'lambda_torsions': x}
+    np.random.seed(3)
+    works = annealed_importance_sampling(system_xml("fluorobenzene"), os.path.join(GOLDEN, "fluorobenzene_cache.npy"), None, None, None, alchemical_functions,
+                                         number_of_applications=512, steps_per_application=10, endstate_parameters=0.0, record_state_work_interval=1, seed=5)
+    assert sorted(works) == list(range(512)) and all(len(w) == 11 and w[0] == 0.0 for w in works.values())
+    final = np.array([w[-1] for w in works.values()])
+    fe = -(np.log(np.mean(np.exp(-(final - final.min())))) - final.min())
+    assert abs(fe - 1.33) < 0.25, fe                                # same free energy as the SMC route (legacy_tests.py:90-94)
+    # first increment is deterministic: u_1(x_0) - u_0(x_0) on the chosen frames
+    np.random.seed(3)
+    frames = cache_frames()
+    chosen = np.random.choice(range(len(frames)), 512)
+    o = XmlSystemOracle(system_xml("fluorobenzene"))
+    seq = ts.relative_alchemical_sequence(11)
+    dw = o.reduced_potential(frames[chosen].astype(np.float64), seq[1]) - o.reduced_potential(frames[chosen].astype(np.float64), seq[0])
+    np.testing.assert_allclose([w[1] for w in works.values()], dw, rtol=1e-8, atol=1e-9)
+    # single-state propagator API on the harmonic oscillator + Jarzynski
+    prm = ts.harmonic_oscillator_parameters()
+    harmonic = {f"{ts.HO_PREFIX}_x0": f"(1-{x})*0.0 + {x}*{2 * prm['sigma']!r}", f"{ts.HO_PREFIX}_U0": f"(1-{x})*0.0 + {x}*{prm['kT']!r}"}
+    pdf_state = OpenMMPDFState(ts.harmonic_oscillator_xml(), alchemical_composability=HarmonicAlchemicalState, pressure=None)
+    integrator = OMMLIAIS(harmonic, 200, temperature=300.0, collision_rate=prm["collision_rate"], timestep=prm["timestep"])
+    prop = OMMAISP(pdf_state, integrator, record_state_work_interval=50, reassign_velocities=True, seed=2)
+    state = OpenMMParticleState(positions=np.zeros((1, 3)))
+    _, pw = prop.apply(state, n_steps=200, reset_integrator=True, apply_pdf_to_context=True)
+    assert pw == 0. and len(prop.state_works[0]) == 5 and prop.state_works[0][0] == 0.0
+    assert pdf_state.get_parameters()[f"{ts.HO_PREFIX}_U0"] == pytest.approx(prm["kT"])
+    pdf_state.set_parameters({k: 0.0 for k in pdf_state.get_parameters()})
+    x0 = np.random.RandomState(0).normal(0, prm["sigma"], (20000, 1, 3)).astype(np.float32)
+    w, _ = prop.apply_batch(x0, n_steps=200)
+    assert w.shape == (20000, 5)
+    fe = -np.log(np.mean(np.exp(-w[:, -1])))   # work std ~0.9 kT at 200 steps: the Jarzynski estimate is good to ~0.01 kT
+    assert abs(fe - 1.0) < 0.04, fe
+    with pytest.raises(AssertionError):
+        OMMAISP(OpenMMPDFState(system_xml("fluorobenzene"), alchemical_composability=RelativeAlchemicalState, pressure=None), integrator)
