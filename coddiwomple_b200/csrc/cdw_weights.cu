@@ -28,7 +28,11 @@ struct WsView {
     double* part_e2;
     unsigned long long* tile_sum;
     unsigned long long* tile_off;
+    unsigned long long* coarse;  // cdf sampled at the end of every group of kGroup entries: coarse[g] = cdf[min(n, kGroup (g + 1)) - 1]
 };
+
+constexpr int kGroup = 32, kGroupLog2 = 5;  // coarse table = n/4 bytes: L2-resident up to ~4e8 particles
+__host__ __device__ inline long long n_groups_for(long long n) { return (n + kGroup - 1) / kGroup; }
 
 __host__ __device__ inline long long n_tiles_for(long long n) { return (n + kTile - 1) / kTile; }
 
@@ -39,7 +43,9 @@ __host__ __device__ inline WsView ws_view(void* ws, long long n) {
     v.part_e = (double*)b; b += sizeof(double) * kMaxStatBlocks;
     v.part_e2 = (double*)b; b += sizeof(double) * kMaxStatBlocks;
     v.tile_sum = (unsigned long long*)b; b += sizeof(unsigned long long) * n_tiles_for(n);
-    v.tile_off = (unsigned long long*)b;
+    v.tile_off = (unsigned long long*)b; b += sizeof(unsigned long long) * (n_tiles_for(n) + 1);
+    b = (unsigned char*)(((size_t)b + 15) & ~(size_t)15);  // the coarse table is written with 16-byte stores
+    v.coarse = (unsigned long long*)b;
     return v;
 }
 
@@ -247,35 +253,156 @@ __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __r
             for (int k = 0; k < kItems; ++k)
                 if (i0 + k < n) cdf[i0 + k] = q[k] + off;
         }
+        // coarse table for the hierarchical search: the last cdf entry of every group of kGroup.  A group ends on the last
+        // item of a thread (kGroup is a multiple of kItems) or at n - 1.  The index uses an unsigned shift on purpose:
+        // nvcc 12.9 dropped the rounding of a signed `i / kGroup` in the n - 1 case (uniform datapath), giving a
+        // misaligned store for n = 2..7.
+        static_assert((1 << kGroupLog2) == kGroup && kGroup % kItems == 0, "groups are whole threads");
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const unsigned long long i = (unsigned long long)(i0 + k);
+            const bool ends = (k == kItems - 1 && ((i + 1) & (kGroup - 1)) == 0) || i + 1 == (unsigned long long)n;
+            if (i < (unsigned long long)n && ends) ws.coarse[i >> kGroupLog2] = q[k] + off;
+        }
     }
 }
 
-// vectorised search: ancestor = first j with cdf[j] > floor(u * T)  (== searchsorted(cdf, target, side='right'))
+// ancestor = first j with cdf[j] > target  (== searchsorted(cdf, target, side='right')), found hierarchically:
+//   level 0: a <= 2048-entry sample of the coarse table in shared memory            (11 steps, no global traffic)
+//   level 1: the coarse table (cdf at the end of every 32 entries; n/4 bytes: L2-resident)
+//   level 2: the 32 cdf entries of the group = one 256-byte run of the cdf            (5 steps)
+// so a lookup costs one DRAM sector of the cdf instead of log2(n) dependent probes scattered over 8n bytes.
+constexpr int kTop = 2048;
+
+struct TopTable {
+    long long m, stride;
+    int n_top;
+};
+
+__device__ __forceinline__ TopTable load_top(const unsigned long long* __restrict__ coarse, long long n, unsigned long long* top) {
+    TopTable t;
+    t.m = n_groups_for(n);
+    t.n_top = t.m < kTop ? (int)t.m : kTop;
+    t.stride = (t.m + t.n_top - 1) / t.n_top;
+    for (int k = threadIdx.x; k < t.n_top; k += blockDim.x) {
+        long long g = (long long)(k + 1) * t.stride - 1;
+        top[k] = __ldg(coarse + (g < t.m ? g : t.m - 1));
+    }
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ long long hier_search(unsigned long long target, const unsigned long long* __restrict__ cdf,
+                                                 const unsigned long long* __restrict__ coarse, const unsigned long long* top, const TopTable& t,
+                                                 long long n) {
+    int lo = 0, hi = t.n_top - 1;  // first k with top[k] > target (top[n_top - 1] == total > target)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (top[mid] > target) hi = mid; else lo = mid + 1;
+    }
+    long long glo = (long long)lo * t.stride, ghi = glo + t.stride - 1;
+    if (ghi > t.m - 1) ghi = t.m - 1;
+    while (glo < ghi) {  // first group whose last entry exceeds the target
+        const long long mid = (glo + ghi) >> 1;
+        if (__ldg(coarse + mid) > target) ghi = mid; else glo = mid + 1;
+    }
+    long long jlo = glo * kGroup, jhi = jlo + kGroup - 1;
+    if (jhi > n - 1) jhi = n - 1;
+    while (jlo < jhi) {
+        const long long mid = (jlo + jhi) >> 1;
+        if (__ldg(cdf + mid) > target) jhi = mid; else jlo = mid + 1;
+    }
+    return jlo;
+}
+
+// Multinomial (unsorted uniforms): one slot per thread, hierarchical search.
 __global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* __restrict__ w, const double* __restrict__ uniforms,
                                                         long long n, const double* __restrict__ stats, WsView ws,
                                                         const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
                                                         double* __restrict__ cum_out, int* __restrict__ anc) {
+    __shared__ unsigned long long top[kTop];
     const bool resample = stats[CDW_STAT_RESAMPLE] != 0.0;
     const double mean = stats[CDW_STAT_MEAN];
-    const unsigned long long total = resample ? ws.hdr[WS_TOTAL] : 0ull;
-    const double u0 = (resample && kind == CDW_RESAMPLE_SYSTEMATIC) ? uniforms[0] : 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        if (!resample) {
+    if (!resample) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
             if (anc) anc[i] = (int)i;
             if (cum_out) cum_out[i] = w[i];  // null update: cum += inc (resamplers.py:136-156)
-            continue;
         }
-        double u = kind == CDW_RESAMPLE_SYSTEMATIC ? __ddiv_rn(__dadd_rn((double)i, u0), (double)n) : uniforms[i];
-        const unsigned long long target = fixed_target(u, total);
-        long long lo = 0, hi = n - 1;  // invariant: answer in [lo, hi]; cdf[n-1] == total > target
-        while (lo < hi) {
-            long long mid = (lo + hi) >> 1;
-            if (__ldg(cdf + mid) > target) hi = mid; else lo = mid + 1;
-        }
-        anc[i] = (int)lo;
+        return;
+    }
+    const unsigned long long total = ws.hdr[WS_TOTAL];
+    const double u0 = kind == CDW_RESAMPLE_SYSTEMATIC ? uniforms[0] : 0.0;
+    const TopTable t = load_top(ws.coarse, n, top);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double u = kind == CDW_RESAMPLE_SYSTEMATIC ? __ddiv_rn(__dadd_rn((double)i, u0), (double)n) : uniforms[i];
+        anc[i] = (int)hier_search(fixed_target(u, total), cdf, ws.coarse, top, t, n);
         if (cum_out) {
-            double c = cum_in ? cum_in[i] : 0.0;
+            const double c = cum_in ? cum_in[i] : 0.0;
             cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
+        }
+    }
+}
+
+// Systematic (sorted targets): a block owns kSysSlots consecutive slots; their ancestors lie in one contiguous window
+// of the cdf, which is staged once in shared memory (8 B of cdf read per slot instead of log2(n) probes).  Windows that do
+// not fit (very uneven weights) fall back to the hierarchical search.
+constexpr int kSysPerThread = 4;
+constexpr int kSysSlots = kBlock * kSysPerThread;
+constexpr int kSysWindow = 3072;
+
+__global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double* __restrict__ w, const double* __restrict__ uniforms, long long n,
+                                                                   const double* __restrict__ stats, WsView ws,
+                                                                   const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
+                                                                   double* __restrict__ cum_out, int* __restrict__ anc) {
+    __shared__ unsigned long long top[kTop];
+    __shared__ unsigned long long win[kSysWindow];
+    __shared__ long long bounds[2];
+    if (stats[CDW_STAT_RESAMPLE] == 0.0) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            if (anc) anc[i] = (int)i;
+            if (cum_out) cum_out[i] = w[i];
+        }
+        return;
+    }
+    const double mean = stats[CDW_STAT_MEAN];
+    const unsigned long long total = ws.hdr[WS_TOTAL];
+    const double u0 = uniforms[0];
+    const TopTable t = load_top(ws.coarse, n, top);
+    const long long n_chunks = (n + kSysSlots - 1) / kSysSlots;
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const long long i0 = chunk * kSysSlots;
+        const long long i1 = i0 + kSysSlots < n ? i0 + kSysSlots : n;  // slots [i0, i1)
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const long long i = threadIdx.x == 0 ? i0 : i1 - 1;
+            const double u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
+            bounds[threadIdx.x] = hier_search(fixed_target(u, total), cdf, ws.coarse, top, t, n);
+        }
+        __syncthreads();
+        const long long jlo = bounds[0], jhi = bounds[1];
+        const bool fits = jhi - jlo + 1 <= kSysWindow;
+        if (fits)
+            for (long long j = jlo + threadIdx.x; j <= jhi; j += blockDim.x) win[j - jlo] = __ldg(cdf + j);
+        __syncthreads();
+        for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+            const double u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
+            const unsigned long long target = fixed_target(u, total);
+            long long a;
+            if (fits) {
+                int lo = 0, hi = (int)(jhi - jlo);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (win[mid] > target) hi = mid; else lo = mid + 1;
+                }
+                a = jlo + lo;
+            } else {
+                a = hier_search(target, cdf, ws.coarse, top, t, n);
+            }
+            anc[i] = (int)a;
+            if (cum_out) {
+                const double c = cum_in ? cum_in[i] : 0.0;
+                cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));
+            }
         }
     }
 }
@@ -490,7 +617,7 @@ using namespace cdw;
 extern "C" size_t cdw_weight_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
     return sizeof(unsigned long long) * WS_HEADER_WORDS + 2 * sizeof(double) * kMaxStatBlocks +
-           2 * sizeof(unsigned long long) * (size_t)(n_tiles_for(n) + 1);
+           2 * sizeof(unsigned long long) * (size_t)(n_tiles_for(n) + 1) + sizeof(unsigned long long) * (size_t)(n_groups_for(n) + 4) + 32;
 }
 
 extern "C" int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
@@ -531,11 +658,26 @@ extern "C" int cdw_resample_indices(int kind, const double* w, const double* uni
     cudaStream_t st = (cudaStream_t)stream;
     const long long nt = n_tiles_for(n);
     int grid_t = (int)(nt < (long long)sm_count() * 16 ? nt : (long long)sm_count() * 16);
+    static const bool dbg = getenv("CDW_DEBUG_SYNC") != nullptr;
+#define CDW_DBG(name)                                                                       \
+    if (dbg) {                                                                               \
+        cudaError_t e_ = cudaStreamSynchronize(st);                                          \
+        if (e_ == cudaSuccess) e_ = cudaGetLastError();                                      \
+        if (e_ != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e_)); return CDW_ECUDA; } \
+    }
     cdf_tile_sums_kernel<<<grid_t, kBlock, 0, st>>>(w, n, stats, ws);
+    CDW_DBG("cdf_tile_sums_kernel")
     cdf_scan_tiles_kernel<<<1, 1024, 0, st>>>(n, (double*)stats, ws);
+    CDW_DBG("cdf_scan_tiles_kernel")
     cdf_tile_scan_kernel<<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out);
-    int grid_s = blocks_for(n, kBlock, sm_count() * 16);
-    search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
+    CDW_DBG("cdf_tile_scan_kernel")
+    if (kind == CDW_RESAMPLE_SYSTEMATIC) {
+        int grid_s = blocks_for(n, kSysSlots, sm_count() * 8);
+        search_systematic_kernel<<<grid_s, kBlock, 0, st>>>(w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
+    } else {
+        int grid_s = blocks_for(n, kBlock * 4, sm_count() * 8);
+        search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
+    }
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }
