@@ -18,6 +18,10 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:  # one numpy worker per core: keep BLAS/OpenMP from oversubscribing the host
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(_k, "1")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -82,6 +86,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the propagate kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "propagate_traffic.json")) as fh:
+            return json.load(fh)
+    except OSError:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -106,27 +119,65 @@ def cpu_port_rate(n_particles, n_lambda, seed=0):
     return n_particles * (n_lambda - 1) / dt, dt, out["free_energy"]
 
 
+CPU_SAMPLE_PARTICLES = 128  # per worker and step: ~3 s of the numpy port per step on one core
+
+
+def _cpu_worker(job):
+    P, T, seed = job
+    _, dt, fe = cpu_port_rate(P, T, seed=seed)
+    return dt, fe
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's loop on ALL host cores.  The reference's own engine
+    (OpenMM's CPU platform) is not installable offline; the numpy port is single-threaded per anneal, so the host is
+    filled with one independent anneal of CPU_SAMPLE_PARTICLES particles per core and the rates are summed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    P, T = 64, N_LAMBDA  # bounded sample: 64 particles through the full 100-lambda protocol
-    for _ in range(args.warmup):
-        cpu_port_rate(8, 10)
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    cores = host_cores()
+    P, T = CPU_SAMPLE_PARTICLES, N_LAMBDA
     rates, times = [], []
-    for k in range(args.steps):
-        r, dt, _ = cpu_port_rate(P, T, seed=k)
-        rates.append(r); times.append(dt)
+    with ProcessPoolExecutor(cores, mp_context=mp.get_context("fork")) as pool:
+        for _ in range(max(args.warmup, 1)):
+            list(pool.map(_cpu_worker, [(8, 10, 0)] * cores))
+        for k in range(args.steps):
+            t0 = time.perf_counter()
+            list(pool.map(_cpu_worker, [(P, T, 1000 * k + c) for c in range(cores)]))
+            dt = time.perf_counter() - t0
+            times.append(dt); rates.append(cores * P * (T - 1) / dt)
     value = float(np.mean(rates))
+    sample = (f"oracle/ (fp64 numpy restatement of openmm/coddiwomple.py:312-331 + OpenMM's arithmetic), per step {cores} independent anneals "
+              f"(one per core) of {P} particles x {T} lambda, vectorised over particles; the reference itself cannot run: OpenMM is not installable offline")
     line = {"impl": "reference", "metric": "particle-Langevin-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{P} particles x {T} lambda per step"},
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{cores} x {P} particles x {T} lambda per step"},
             "anneals_per_s": value / (N_PARTICLES * (N_LAMBDA - 1)),
-            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-                             "sample": f"oracle/ (fp64 numpy restatement of openmm/coddiwomple.py:312-331 + OpenMM arithmetic), {P} particles x {T} lambda, "
-                                       "vectorised over particles, 1 thread; the reference itself cannot run: OpenMM is not installable offline"},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess():
+    """Run the reference arm in a child process (a fork pool after CUDA initialisation is not safe) on a bounded sample."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"], env=env,
+                         capture_output=True, text=True, timeout=600)
+    for ln in reversed(out.stdout.splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -231,9 +282,10 @@ def run_gpu(args):
         achieved = flops["per_iteration"] * P / (k_ms * 1e-3) / 1e12
         peaks, peaks_src = measured_peaks()
         share = k_ms * (eng.T - 1) / float(np.mean(ms))
+        traffic = measured_traffic()
         # ---- HBM-bound resampling kernels at sweep size (config 5), for the record
         sweep = resampling_sweep(torch, kernels, _lib, 1 << 24, spec.n_atoms if spec.n_atoms < 14 else 13) if world == 1 else None
-        cpu_rate, cpu_dt, _ = cpu_port_rate(48, N_LAMBDA) if world == 1 else (None, 0.0, None)
+        cpu_base = cpu_baseline_subprocess() if world == 1 else None
         line = {"metric": "particle-Langevin-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -244,13 +296,13 @@ def run_gpu(args):
                         "d2h_bytes_per_step": int(cum_host.numel() * 8), "api": "SMCEngine.anneal(pinned host rows) + cumulative works to host", "cuda_graph": use_graph},
                 "gpu_launches": int(args.steps * 2 * (1 + 2 * (N_LAMBDA - 1) + 1)),  # K1 + (propagate, fused resample) per iteration + final gather
                 "roofline": {"bound": "fp64", "kernel": "smc_propagate_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                             "frac": achieved / fp64_peak, "traffic": None, "avg_launch_ms": k_ms, "share_of_step": share,
+                             "frac": achieved / fp64_peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                             "avg_launch_ms": k_ms, "share_of_step": share,
                              "algorithmic_flop_per_particle_iteration": flops["per_iteration"],
                              "peak_source": "cdw_fma_peak(fp64) micro-benchmark run in this process (MEASURED_PEAKS.json has no FP pipe figure)",
                              "fp32_fma_peak_tflops": fp32_peak, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
                 "resampling_sweep": sweep,
-                "cpu_baseline": ({"value": cpu_rate, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-                                  "sample": f"oracle/ numpy port, 48 particles x {N_LAMBDA} lambda ({cpu_dt:.1f} s)"} if world == 1 else None),
+                "cpu_baseline": cpu_base,
                 "clocks": clocks.summary()}
         print(json.dumps(line))
     if world > 1:
