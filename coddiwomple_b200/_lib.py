@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("CDW_LIB") or os.path.join(HERE, "libcdw_b200.so")  # 
 
 CDW_FLAG_RANDOMIZE_VELOCITIES = 1
 CDW_FLAG_TRACK_WORKS = 2
+CDW_FLAG_ULA = 4
 CDW_RESAMPLE_MULTINOMIAL = 0
 CDW_RESAMPLE_SYSTEMATIC = 1
 STAT_WMIN, STAT_SUM_E, STAT_SUM_E2, STAT_NESS, STAT_MEAN, STAT_RESAMPLE, STAT_TOTAL, STAT_NNAN = range(8)

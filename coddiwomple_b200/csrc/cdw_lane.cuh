@@ -595,15 +595,19 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
     const double ca = exp(-a.gamma * a.dt), cb = sqrt(1.0 - exp(-2.0 * a.gamma * a.dt));
     const bool track = (a.flags & CDW_FLAG_TRACK_WORKS) != 0;
     const double inv_kT = 1.0 / a.kT;
-    enum { OP_E = 0, OP_V = 1, OP_R = 2, OP_O = 3, OP_MB = 4 };
+    enum { OP_E = 0, OP_V = 1, OP_R = 2, OP_O = 3, OP_MB = 4, OP_U = 5, OP_B = 6 };
+    const bool ula = (a.flags & CDW_FLAG_ULA) != 0;
     double U = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0;
-    const int n_ops = 1 + 6 * a.n_steps;
+    const int n_ops = ula ? 1 + 3 * a.n_steps : 1 + 6 * a.n_steps;
     // op -1 (only with RANDOMIZE): Context.setVelocitiesToTemperature (propagators.py:137-138)
-    for (int op = (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES) ? -1 : 0; op < n_ops; ++op) {
+    for (int op = (!ula && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0; op < n_ops; ++op) {
         int kind, slot = 0, st = 0;
         if (op < 0) kind = OP_MB;
         else if (op == 0) kind = OP_E;
-        else {
+        else if (ula) {
+            slot = (op - 1) % 3; st = (op - 1) / 3;  // U E B
+            kind = slot == 0 ? OP_U : (slot == 1 ? OP_E : OP_B);
+        } else {
             slot = (op - 1) % 6; st = (op - 1) / 6;  // V R O R E V
             kind = slot == 0 || slot == 5 ? OP_V : (slot == 1 || slot == 3 ? OP_R : (slot == 2 ? OP_O : OP_E));
         }
@@ -611,6 +615,42 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
             U = lane_energy<true>(s, T, M);
             if (op == 0) u_first = U;
             else if (track) shadow += pending + U;  // closes the second R of the step: (KE + U_new) - (KE_old + U_mid)
+            continue;
+        }
+        if (kind == OP_U || kind == OP_B) {
+            // Euler-Maruyama proposal (integrators.py:676-680, 741-745, 829-888); the v column holds x_old.
+            //   U : x' = x + tau beta F(x) + sqrt(2 tau) xi, tau_a = kT dt^2 / (2 m_a); constrain positions;
+            //       pending = log K(x'|x)  = -sum |x' - x - tau beta F(x)|^2 / (4 tau)
+            //   B : proposal += pending - log L(x|x'),  log L = -sum |x - x' - tau beta F(x')|^2 / (4 tau)
+            const bool fwd = kind == OP_U;
+            if (fwd) {
+                for (int q = tl; q < s.n_cons; q += T_) {
+                    const int bi = CDW_BASE(T.cons_atoms[2 * q]), bj = CDW_BASE(T.cons_atoms[2 * q + 1]), bq = CDW_BASE(q);
+                    M.r0[bq] = M.x[bi] - M.x[bj]; M.r0[bq + kR] = M.x[bi + kR] - M.x[bj + kR]; M.r0[bq + 2 * kR] = M.x[bi + 2 * kR] - M.x[bj + 2 * kR];
+                }
+                for (int at = tl; at < A; at += T_) {
+                    const int b = CDW_BASE(at);
+                    const double tau = 0.5 * a.kT * a.dt * a.dt * T.inv_m[at];
+                    double z0, z1, z2;
+                    normals3(a.seed, gid, (uint32_t)(a.step0 + st), (uint32_t)at, CDW_KIND_ULA, z0, z1, z2);
+                    const d3 x = ld3(M.x, b);
+                    st3(M.v, b, x);
+                    st3(M.x, b, x + ((tau * inv_kT) * ld3(M.f, b) + sqrt(2.0 * tau) * mk3(z0, z1, z2)));
+                }
+                CDW_TEAM_SYNC(M);
+                if (s.n_cons) lane_shake(s, T, M, a.tol, 0.0);
+            }
+            double acc = 0.0;
+            for (int at = tl; at < A; at += T_) {
+                const int b = CDW_BASE(at);
+                const double tau = 0.5 * a.kT * a.dt * a.dt * T.inv_m[at];
+                const d3 xn = ld3(M.x, b), xo = ld3(M.v, b);
+                const d3 d = (fwd ? xn - xo : xo - xn) - (tau * inv_kT) * ld3(M.f, b);
+                acc += dot(d, d) / (4.0 * tau);
+            }
+            acc = team_sum(M, acc);
+            if (fwd) pending = -acc;
+            else proposal += pending + acc;
             continue;
         }
         const double ke_before = track ? lane_kinetic(s, T, M) : 0.0;
@@ -656,7 +696,8 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         }
     }
     const double u_last = U;
-    const bool bad = a.n_steps > 0 && !(u_last - u_last == 0.0);  // NaN or inf
+    const double fin = ula ? u_last + proposal : u_last;
+    const bool bad = a.n_steps > 0 && !(fin - fin == 0.0);  // NaN or inf
     double aux = 0.0;
     int label = (int)src;
     if (a.peer_pos) {
@@ -667,7 +708,9 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         if (a.aux_in) aux = a.aux_in[src];
         if (a.label_in) label = a.label_in[src];
     }
-    const double inc = u_first * inv_kT + aux;
+    // MCMC move: work_inc = u_t(x_{t-1}) - u_{t-1}(x_{t-1}); Euler-Maruyama proposal: u_t(x_t) - u_{t-1}(x_{t-1}) + proposal work
+    // (distribution_factories.py:98-131); a reverted move is a rejected one (zero proposal work, state kept)
+    const double inc = (ula && !bad ? u_last * inv_kT + proposal : u_first * inv_kT) + aux;
     const double w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
     if (tl == 0) {
         M.bad[rid] = bad ? 1 : 0;
@@ -678,7 +721,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         if (a.u_first_out) a.u_first_out[p] = u_first * inv_kT;
         if (a.u_last_out) a.u_last_out[p] = u_last * inv_kT;
         if (a.shadow_out) a.shadow_out[p] = shadow * inv_kT;
-        if (a.proposal_out) a.proposal_out[p] = proposal * inv_kT;
+        if (a.proposal_out) a.proposal_out[p] = ula ? proposal : proposal * inv_kT;
         if (a.nan_flags) a.nan_flags[p] = bad ? 1 : 0;
         if (a.energy_out) a.energy_out[p] = u_first;
     }

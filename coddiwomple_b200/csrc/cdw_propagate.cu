@@ -182,10 +182,13 @@ extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, con
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     CDW_REQUIRE(!(anc && (pos_in == pos_out || (vel_in && vel_in == vel_out))), "gather-on-load needs distinct in/out buffers");
-    CDW_REQUIRE(vel_in || (prm->flags & CDW_FLAG_RANDOMIZE_VELOCITIES) || prm->n_steps == 0, "velocities required unless they are randomized");
-    CDW_REQUIRE(!pos_out || prm->n_steps == 0 || vel_out, "vel_out is required when positions are written");
+    const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;  // the Euler-Maruyama proposal has no velocities: the buffers are left untouched
+    CDW_REQUIRE(ula || vel_in || (prm->flags & CDW_FLAG_RANDOMIZE_VELOCITIES) || prm->n_steps == 0, "velocities required unless they are randomized");
+    CDW_REQUIRE(ula || !pos_out || prm->n_steps == 0 || vel_out, "vel_out is required when positions are written");
+    CDW_REQUIRE(!(ula && (prm->flags & CDW_FLAG_TRACK_WORKS)), "CDW_FLAG_TRACK_WORKS does not apply to the Euler-Maruyama proposal");
     PropArgs a = {};
-    a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out;
+    a.pos_in = (const float4*)pos_in; a.vel_in = ula ? nullptr : (const float4*)vel_in; a.pos_out = (float4*)pos_out;
+    a.vel_out = ula ? nullptr : (float4*)vel_out;
     a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.label_in = label_in; a.lambda = lambda;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
@@ -201,14 +204,16 @@ extern "C" int cdw_smc_propagate_sharded(const cdw_system* sys, const float* con
                                          int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream) {
     CDW_REQUIRE(sys && prm && n >= 0, "null argument");
     if (n == 0) return CDW_OK;
-    CDW_REQUIRE(peer_pos && peer_vel && pos_out && vel_out && anc && n_ranks > 0 && n_per_rank > 0, "null argument");
+    const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;
+    CDW_REQUIRE(peer_pos && pos_out && anc && n_ranks > 0 && n_per_rank > 0 && (ula || (peer_vel && vel_out)), "null argument");
+    CDW_REQUIRE(!(ula && (prm->flags & CDW_FLAG_TRACK_WORKS)), "CDW_FLAG_TRACK_WORKS does not apply to the Euler-Maruyama proposal");
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     PropArgs a = {};
     a.peer_pos = (const float4* const*)peer_pos; a.peer_vel = (const float4* const*)peer_vel; a.peer_aux = peer_aux; a.peer_label = peer_label;
     a.n_per_rank = n_per_rank;
-    a.vel_in = (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
-    a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
+    a.vel_in = ula ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
+    a.pos_out = (float4*)pos_out; a.vel_out = ula ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;

@@ -197,11 +197,14 @@ class ParticleEnsemble:
         self.wmin_key.fill_(-1)  # ~0ull: arm the running min; cdw_smc_resample re-arms it after every iteration
         return u0
 
-    def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None):
-        """Fused K3b-on-load + K1 + K4 + first half of K2 (include/cdw.h: cdw_smc_propagate).  Advances `iteration`."""
+    def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None, ula=False):
+        """Fused K3b-on-load + K1 + K4 + first half of K2 (include/cdw.h: cdw_smc_propagate).  Advances `iteration`.
+        ula=True swaps BAOAB for the Euler-Maruyama proposal and its generalised incremental work (CDW_FLAG_ULA)."""
         self.iteration += 1
         c, n = self.cur, 1 - self.cur
         flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0) | (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
+        if ula:
+            flags = _lib.CDW_FLAG_ULA
         prm = langevin.as_struct(flags)
         o = outputs or {}
         anc = self.anc if self.pending_gather else None
@@ -252,7 +255,11 @@ class SMCEngine:
     """
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5,
-                 always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None, record_works_every=None):
+                 always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None, record_works_every=None,
+                 proposal="baoab"):
+        if proposal not in ("baoab", "ula"):
+            raise ValueError("proposal must be 'baoab' (MCMC move, openmm/integrators.py:19-465) or 'ula' (Euler-Maruyama, :666-888)")
+        self.proposal = proposal
         self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history)
         self.system = self.ensemble.system
         self.langevin = langevin or LangevinParameters()
@@ -288,7 +295,7 @@ class SMCEngine:
 
     def propagate(self, t):
         """First kernel of iteration t (1-based): gather-on-load + E/F + incremental work + BAOAB + closing energy."""
-        self.ensemble.propagate_and_weigh(self.lam[t], self.langevin, self.seed, randomize_velocities=(t == 1))
+        self.ensemble.propagate_and_weigh(self.lam[t], self.langevin, self.seed, randomize_velocities=(t == 1), ula=(self.proposal == "ula"))
 
     def finish_iteration(self, t):
         """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + search, cum update."""

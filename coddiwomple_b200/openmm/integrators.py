@@ -97,3 +97,31 @@ class OMMLIAIS(OMMLI):
 
     def set_proposal_work(self, work):
         self.proposal_work = float(work)
+
+
+class OpenMMEulerMaruyamaIntegrator(LangevinParameters):
+    """Generalized Euler-Maruyama (unadjusted Langevin) integrator — coddiwomple/openmm/integrators.py:666-888.
+
+        x_(k+1) = x_k + tau * force(x_k | parameters) * beta + sqrt(2 tau) * R,   tau = D dt^2,  D = kT / (2 m)   (:676-680, 829-838)
+        proposal_work = log q(x_new | x_old) - log q(x_old | x_new)                                                (:864-888)
+
+    followed, when the system has constraints, by the position-constraint projection of the CustomIntegrator flavour
+    (:741-745).  The move and both kernel densities are computed by the fused kernel (CDW_FLAG_ULA); this class
+    carries the numbers.  There is no collision rate and there are no velocities.
+    """
+
+    def __init__(self, timestep=0.001, temperature=300.0, constraint_tolerance=1e-6, mass_vector=None, **kwargs):
+        super().__init__(temperature=units.strip(temperature), collision_rate=0.0, timestep=units.strip(timestep), constraint_tolerance=constraint_tolerance)
+        self.mass_vector = None if mass_vector is None else np.asarray(units.strip(mass_vector), dtype=np.float64).reshape(-1)
+        self.reset()
+
+    def reset(self):
+        self.proposal_work = 0.0
+
+    def tau(self, masses=None):
+        """tau_a = kT dt^2 / (2 m_a)  [nm^2]."""
+        m = self.mass_vector if masses is None else np.asarray(masses, dtype=np.float64)
+        return self.kT * self.timestep ** 2 / (2.0 * m)
+
+    def get_proposal_work(self, dimensionless=True):
+        return self.proposal_work if dimensionless else self.proposal_work * self.kT

@@ -166,3 +166,40 @@ class OMMAISPR(OMMAISP):
         super().__init__(openmm_pdf_state, integrator, record_state_work_interval=record_state_work_interval, context_cache=context_cache,
                          reassign_velocities=reassign_velocities, n_restart_attempts=n_restart_attempts, seed=seed)
         self._reporter = reporter
+
+
+class OMMEMP(OMMBIP):
+    """OpenMM Euler-Maruyama Propagator: `apply` proposes x' ~ K(.|x) with the unadjusted Langevin kernel of the
+    pdf_state's current target and returns the proposal work log K(x'|x) - log L(x|x')
+    (coddiwomple/openmm/integrators.py:780-888; the generalised weight of troubleshooting/csmc.py:174-191 is then
+    `TargetFactory.compute_incremental_work`'s u_t(x_t) + aux + proposal_work, distribution_factories.py:98-131)."""
+
+    def apply_batch(self, pos_rows, vel_rows=None, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, gid0=None, **kwargs):
+        if reset_integrator:
+            self.integrator.reset()
+        if apply_pdf_to_context:
+            self._context_lambda.copy_(self.pdf_state.lambda_device)
+        P = pos_rows.shape[0]
+        d = pos_rows.device
+        out = dict(u_first=torch.empty(P, dtype=torch.float64, device=d), u_last=torch.empty(P, dtype=torch.float64, device=d),
+                   proposal=torch.zeros(P, dtype=torch.float64, device=d), nan=torch.zeros(P, dtype=torch.int32, device=d))
+        prm = self.integrator.as_struct(_lib.CDW_FLAG_ULA, n_steps=n_steps)
+        if gid0 is None:
+            gid0 = self._gid_counter
+        _lib.check(self.lib.cdw_smc_propagate(self.pdf_state.device_system.handle, _lib.ptr(pos_rows), None, _lib.ptr(pos_rows), None, P, None, None, None,
+                                             None, _lib.ptr(self._context_lambda), C.byref(prm), C.c_uint64(self._seed), C.c_uint64(self._step_counter),
+                                             C.c_int64(gid0), None, None, None, None, _lib.ptr(out["u_first"]), _lib.ptr(out["u_last"]), None,
+                                             _lib.ptr(out["proposal"]), _lib.ptr(out["nan"]), None, _lib.current_stream()), "cdw_smc_propagate")
+        self._step_counter += max(int(n_steps), 1)
+        return out
+
+    def apply(self, particle_state, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, **kwargs):
+        assert isinstance(particle_state, OpenMMParticleState)
+        pos = positions_to_rows(particle_state.positions[None])
+        out = self.apply_batch(pos, n_steps=n_steps, reset_integrator=reset_integrator, apply_pdf_to_context=apply_pdf_to_context)
+        work = 0.0
+        if not int(out["nan"].item()):
+            work = float(out["proposal"].item())
+            self.integrator.proposal_work += work
+        particle_state.positions = pos[0, :, :3].double().cpu().numpy()
+        return particle_state, work

@@ -83,7 +83,10 @@ class ShardedSMCEngine:
     """Same loop as SMCEngine over `n_particles` GLOBAL particles, sharded over the ranks of `group` (NCCL)."""
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5, always_resample=False,
-                 seed=0, resample_seed=1, group=None):
+                 seed=0, resample_seed=1, group=None, proposal="baoab"):
+        if proposal not in ("baoab", "ula"):
+            raise ValueError("proposal must be 'baoab' or 'ula'")
+        self.proposal = proposal
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (backend nccl, one process per GPU)")
         self.group = group
@@ -177,7 +180,7 @@ class ShardedSMCEngine:
     def propagate(self, t):
         self.iteration = t
         c, n = self.cur, 1 - self.cur
-        flags = _lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0
+        flags = _lib.CDW_FLAG_ULA if self.proposal == "ula" else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
         prm = self.langevin.as_struct(flags)
         self.wmin_key.fill_(-1)
         _lib.check(self.lib.cdw_smc_propagate_sharded(

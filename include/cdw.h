@@ -114,6 +114,12 @@ typedef struct cdw_langevin_params {
 
 #define CDW_FLAG_RANDOMIZE_VELOCITIES 1u /* Context.setVelocitiesToTemperature before stepping (propagators.py:137-138) */
 #define CDW_FLAG_TRACK_WORKS 2u          /* accumulate shadow_work / proposal_work (integrators.py:315,336,350) */
+/* Euler-Maruyama (unadjusted Langevin) proposal instead of BAOAB (integrators.py:676-680, 741-745, 829-888):
+ *   x' = x + tau beta F(x) + sqrt(2 tau) xi, tau_a = kT dt^2 / (2 m_a), then position constraints; n_steps moves per call.
+ * proposal_out = sum over moves of log K(x'|x) - log L(x|x') (dimensionless), and the incremental work becomes
+ *   inc = u_t(x_t) + aux + proposal_work   (distribution_factories.py:98-131; troubleshooting/csmc.py:174-191).
+ * Velocities are not used (vel_in / vel_out may be NULL); gamma is ignored. */
+#define CDW_FLAG_ULA 4u
 
 #define CDW_RESAMPLE_MULTINOMIAL 0
 #define CDW_RESAMPLE_SYSTEMATIC 1

@@ -26,7 +26,7 @@ def lambda_table(parameter_sequence, names):
 
 def anneal(system, x0, parameter_sequence, masses=None, constraints=None, temperature=300.0, dt=0.002, gamma=1.0,
            n_steps=1, tol=1e-6, seed=0, resample_seed=1, resampler="multinomial", always_resample=False,
-           floor_threshold=0.5, gid0=0, trace=None):
+           floor_threshold=0.5, gid0=0, trace=None, proposal="baoab"):
     """Run one anneal.  `system.energy_forces(x, lambdas)`; x0 (P, A, 3) nm (fp32-representable values).
 
     Returns dict(x, v, cum, aux, labels, resampled_at, nESS_trace, free_energy).
@@ -45,9 +45,16 @@ def anneal(system, x0, parameter_sequence, masses=None, constraints=None, temper
     resampled_at, ness_trace = [], []
     for t in range(1, T):
         lam = parameter_sequence[t]
-        out = langevin.baoab(lambda xx: system.energy_forces(xx, lam), x, v, masses, constraints, dt, gamma, kT, n_steps,
-                             seed, gids, step0=t * n_steps, tol=tol, randomize_velocities=(t == 1))
-        inc = weights.incremental_work(out["u_first"] / kT, aux)
+        if proposal == "ula":  # Euler-Maruyama proposal + generalised weight (oracle/ula.py)
+            from . import ula
+            out = ula.ula(lambda xx: system.energy_forces(xx, lam), x, masses, constraints, dt, kT, n_steps, seed, gids, step0=t * n_steps, tol=tol)
+            inc = np.where(out["nan"], weights.incremental_work(out["u_first"] / kT, aux),
+                           ula.incremental_work(out["u_last"] / kT, aux, out["proposal_work"]))
+            out["v"] = v
+        else:
+            out = langevin.baoab(lambda xx: system.energy_forces(xx, lam), x, v, masses, constraints, dt, gamma, kT, n_steps,
+                                 seed, gids, step0=t * n_steps, tol=tol, randomize_velocities=(t == 1))
+            inc = weights.incremental_work(out["u_first"] / kT, aux)
         x, v = out["x"], out["v"]
         aux_next = -out["u_last"] / kT
         # revert-on-NaN keeps the pre-move state; its aux is -u_t(x_{t-1})
