@@ -82,6 +82,8 @@ _SIGNATURES = {
     "cdw_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "cdw_system_create": (C.c_int, [C.POINTER(SystemDesc), C.POINTER(_P)]),
     "cdw_system_destroy": (C.c_int, [_P]),
+    "cdw_system_register_protocol": (C.c_int, [_P, _P, C.c_int32, C.c_double, _P]),
+    "cdw_system_clear_protocol": (C.c_int, [_P]),
     "cdw_system_n_atoms": (C.c_int, [_P]),
     "cdw_system_n_lambda": (C.c_int, [_P]),
     "cdw_reduced_potential": (C.c_int, [_P, _P, C.c_int64, _P, C.c_double, _P, _P]),

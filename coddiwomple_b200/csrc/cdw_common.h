@@ -34,4 +34,10 @@ struct cdw_system {
     cdw::SysDev dev;
     void* blob;          // single device allocation holding every table
     size_t blob_bytes;
+    // optional registered lambda protocol (cdw_system_register_protocol): prebuilt effective-term tables per row
+    const double* proto_lambda = nullptr;
+    int proto_rows = 0;
+    double proto_kT = 0.0;
+    unsigned char* proto_tables = nullptr;
+    size_t proto_stride = 0;
 };

@@ -497,6 +497,7 @@ struct PropArgs {
     long long n;
     const int* anc; const double* aux_in; const double* cum_in; const int* label_in;
     const double* lambda;
+    const unsigned char* tables;  // prebuilt image of the CTA-shared table region for this lambda (or NULL: build in the prologue)
     double dt, gamma, kT, tol;
     int n_steps; unsigned flags;
     unsigned long long seed, step0; long long gid0;

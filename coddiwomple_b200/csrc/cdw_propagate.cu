@@ -43,6 +43,38 @@ __global__ void __launch_bounds__(kMaxThreads) reduced_potential_kernel(SysDev s
     }
 }
 
+// ---- prebuilt tables: one block per protocol row resolves lambda into the table image once; the propagate kernel then
+// fetches the image with a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) that overlaps the row loads.
+__global__ void __launch_bounds__(128) build_tables_kernel(SysDev s, const double* lambda_rows, double kT, unsigned char* out, size_t stride) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Layout L = make_layout(s, true, kR, 1);
+    const Tables T = table_pointers(L, smem);
+    build_tables(s, T, lambda_rows + (size_t)blockIdx.x * s.n_lambda, kT, true);
+    __syncthreads();
+    const uint4* src = (const uint4*)smem;
+    uint4* dst = (uint4*)(out + (size_t)blockIdx.x * stride);
+    for (size_t i = threadIdx.x; i < L.x / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_load_tables(unsigned char* smem, const unsigned char* src, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = smem_addr(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem)), "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+
+__device__ __forceinline__ void wait_tables(unsigned long long* bar) {
+    const unsigned b = smem_addr(bar);
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(b) : "memory");
+    }
+}
+
 // Two register budgets: teams of <= 4 lanes run 128-thread CTAs, three of which must be co-resident for a batch of
 // 10^4 replicas to run as one wave (<= 170 registers); teams of 8 run 256-thread CTAs (<= 128 registers, two per SM).
 #ifndef CDW_MINBLOCKS_SMALL
@@ -52,16 +84,28 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, PropArgs a, Shape sh) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long cta_min[MAXT / 32];
+    __shared__ __align__(8) unsigned long long table_bar;
     const int T_ = sh.T, sw = 32 / T_;
     const Layout L = make_layout(s, true, kR, T_);
     const Tables T = table_pointers(L, smem);
-    build_tables(s, T, a.lambda, a.kT, true);
+    bool tables_in_flight = false;
+    if (a.tables) {
+        if (threadIdx.x == 0) bulk_load_tables(smem, a.tables, (unsigned)L.x, &table_bar);
+        tables_in_flight = true;
+        __syncthreads();  // the barrier is initialised before anyone polls it
+    } else {
+        build_tables(s, T, a.lambda, a.kT, true);
+    }
     LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
     unsigned long long my_min = ~0ull;
     for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
         const long long left = a.n - p0;
         const int count = left < kR ? (int)left : kR;
         cta_load_rows(s, a, smem, L, sw, p0, count, true);
+        if (tables_in_flight) {
+            wait_tables(&table_bar);
+            tables_in_flight = false;
+        }
         const bool valid = M.rid < count;
         M.mask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -106,7 +150,19 @@ static Shape pick_shape(const SysDev& dev, bool forces, long long n, int sms) {
     return sh;
 }
 
+// `lambda` points at a row of the registered protocol (and kT matches): use that row's prebuilt tables
+static const unsigned char* registered_tables(const cdw_system* sys, const double* lambda, double kT) {
+    if (!sys->proto_tables || !lambda || kT != sys->proto_kT || sys->dev.n_lambda <= 0) return nullptr;
+    const ptrdiff_t off = lambda - sys->proto_lambda;
+    if (lambda < sys->proto_lambda || off % sys->dev.n_lambda != 0) return nullptr;
+    const ptrdiff_t row = off / sys->dev.n_lambda;
+    if (row >= sys->proto_rows) return nullptr;
+    return sys->proto_tables + (size_t)row * sys->proto_stride;
+}
+
 static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t st) {
+    static const bool no_tables = getenv("CDW_NO_PREBUILT_TABLES") != nullptr;
+    if (forces && !no_tables) a.tables = registered_tables(sys, a.lambda, a.kT);
     int devid = 0, sms = 148;
     cudaGetDevice(&devid);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
@@ -156,6 +212,34 @@ extern "C" int cdw_reduced_potential(const cdw_system* sys, const float* pos, in
     PropArgs a = {};
     a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.beta = beta; a.energy_out = u_out;
     return launch(sys, a, false, (cudaStream_t)stream);
+}
+
+extern "C" int cdw_system_register_protocol(cdw_system* sys, const double* lambda_rows, int32_t n_rows, double kT, cdw_stream stream) {
+    CDW_REQUIRE(sys && lambda_rows && n_rows > 0 && kT > 0.0, "null argument");
+    CDW_REQUIRE(sys->dev.n_lambda > 0, "the system has no global parameters");
+    const Layout L = make_layout(sys->dev, true, kR, 1);
+    CDW_REQUIRE(L.x <= 200 * 1024, "table image too large");
+    cudaFree(sys->proto_tables);
+    sys->proto_tables = nullptr; sys->proto_lambda = nullptr; sys->proto_rows = 0;
+    unsigned char* buf = nullptr;
+    CDW_CUDA(cudaMalloc(&buf, L.x * (size_t)n_rows));
+    cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.x);
+    build_tables_kernel<<<n_rows, 128, L.x, (cudaStream_t)stream>>>(sys->dev, lambda_rows, kT, buf, L.x);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFree(buf);
+        set_error("build_tables_kernel: %s", cudaGetErrorString(e));
+        return CDW_ECUDA;
+    }
+    sys->proto_tables = buf; sys->proto_stride = L.x; sys->proto_lambda = lambda_rows; sys->proto_rows = n_rows; sys->proto_kT = kT;
+    return CDW_OK;
+}
+
+extern "C" int cdw_system_clear_protocol(cdw_system* sys) {
+    CDW_REQUIRE(sys, "null argument");
+    cudaFree(sys->proto_tables);
+    sys->proto_tables = nullptr; sys->proto_lambda = nullptr; sys->proto_rows = 0; sys->proto_stride = 0;
+    return CDW_OK;
 }
 
 extern "C" int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_t n, const double* lambda, double* energy_out,

@@ -74,6 +74,7 @@ extern "C" int cdw_system_create(const cdw_system_desc* d, cdw_system** out) {
 extern "C" int cdw_system_destroy(cdw_system* sys) {
     if (!sys) return CDW_OK;
     cudaFree(sys->blob);
+    cudaFree(sys->proto_tables);
     delete sys;
     return CDW_OK;
 }

@@ -43,6 +43,16 @@ class DeviceSystem:
         rows = [self.spec.lambda_vector(p) for p in parameter_sequence]
         return torch.from_numpy(np.stack(rows)).to(device)
 
+    def register_protocol(self, lambda_table, kT):
+        """Precompute the effective term tables of every row of `lambda_table` ([T][n_lambda] fp64 device tensor):
+        propagate calls whose lambda pointer is a row of it then skip the per-CTA table build
+        (cdw_system_register_protocol).  The tensor is kept alive here and must not be modified afterwards."""
+        if self.n_lambda == 0:
+            return
+        self._protocol = lambda_table
+        _lib.check(self.lib.cdw_system_register_protocol(self.handle, _lib.ptr(lambda_table), int(lambda_table.shape[0]), float(kT),
+                                                        _lib.current_stream()), "cdw_system_register_protocol")
+
     def __del__(self):
         try:
             if self.handle:
@@ -266,6 +276,7 @@ class SMCEngine:
         self.parameter_sequence = list(parameter_sequence)
         self.T = len(self.parameter_sequence)
         self.lam = self.system.lambda_table(self.parameter_sequence, self.ensemble.device)
+        self.system.register_protocol(self.lam, self.langevin.kT)
         self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)

@@ -102,6 +102,7 @@ class ShardedSMCEngine:
         self.T = len(self.parameter_sequence)
         self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
         self.lam = self.system.lambda_table(self.parameter_sequence, self.device)
+        self.system.register_protocol(self.lam, self.langevin.kT)
         self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)

@@ -143,6 +143,16 @@ CDW_API int cdw_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* replaces: OpenMMPDFState.__init__ building the ThermodynamicState + Context (openmm/states.py:50-86) */
 CDW_API int cdw_system_create(const cdw_system_desc* desc, cdw_system** out);
 CDW_API int cdw_system_destroy(cdw_system* sys);
+/* Optional.  Precompute the effective term tables of every row of a lambda protocol: `lambda_rows` is a DEVICE array
+ * [n_rows][n_lambda] (the parameter_sequence of openmm/coddiwomple.py:283-297 lowered to numbers), kT in kJ/mol.
+ * Afterwards any cdw_smc_propagate / cdw_smc_propagate_sharded / cdw_baoab call whose `lambda` points AT A ROW of that
+ * array and whose kT matches fetches the row's prebuilt tables with one bulk copy instead of re-deriving them in every
+ * thread block (what OpenMMPDFState.set_parameters + apply_to_context cost the reference P times per iteration,
+ * openmm/states.py:89-103).  Results are bit-identical either way.  The array must stay unchanged until
+ * cdw_system_clear_protocol or the next registration; registering is not thread-safe against concurrent launches on
+ * the same handle.  Enqueues on `stream`. */
+CDW_API int cdw_system_register_protocol(cdw_system* sys, const double* lambda_rows, int32_t n_rows, double kT, cdw_stream stream);
+CDW_API int cdw_system_clear_protocol(cdw_system* sys);
 CDW_API int cdw_system_n_atoms(const cdw_system* sys);
 CDW_API int cdw_system_n_lambda(const cdw_system* sys);
 

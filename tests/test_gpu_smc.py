@@ -278,3 +278,20 @@ def test_annealed_importance_sampling_driver_and_propagator():
     assert abs(fe - 1.0) < 0.04, fe
     with pytest.raises(AssertionError):
         OMMAISP(OpenMMPDFState(system_xml("fluorobenzene"), alchemical_composability=RelativeAlchemicalState, pressure=None), integrator)
+
+
+def test_prebuilt_protocol_tables_are_bit_identical():
+    """cdw_system_register_protocol only changes WHERE the effective term tables come from (one bulk copy of a prebuilt
+    image instead of the per-CTA prologue): every output of the anneal is bitwise the same."""
+    frames = cache_frames()
+    x0 = frames[np.random.RandomState(2).randint(0, len(frames), 700)]
+    seq = ts.relative_alchemical_sequence(8)
+    runs = []
+    for clear in (False, True):
+        eng = _engine(system_xml("fluorobenzene"), 700, seq, seed=5, resample_seed=6)
+        if clear:
+            _lib.check(eng.system.lib.cdw_system_clear_protocol(eng.system.handle), "cdw_system_clear_protocol")
+        eng.anneal(x0)
+        runs.append((eng.ensemble.cum.cpu().numpy().copy(), eng.ensemble.positions.cpu().numpy().copy(), eng.ensemble.auxiliary_work.cpu().numpy().copy()))
+    for a, b in zip(*runs):
+        np.testing.assert_array_equal(a, b)
