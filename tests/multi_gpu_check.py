@@ -28,10 +28,13 @@ def main():
     xml = load_xml(os.path.join(root, "tests", "golden", "systems", "fluorobenzene.vacuum.xml.gz"))
     frames = np.load(os.path.join(root, "tests", "golden", "fluorobenzene_cache.npy"))
     ok = True
-    for kind, thr, P, T in (("multinomial", 0.9999, 4096, 8), ("systematic", 0.9999, 4096, 8), ("multinomial", 0.5, 2048 * world, 12)):
+    cases = (("multinomial", 0.9999, 4096, 8, "baoab"), ("systematic", 0.9999, 4096, 8, "baoab"), ("multinomial", 0.5, 2048 * world, 12, "baoab"),
+             ("multinomial", 0.9999, 4096, 8, "ula"))   # BASELINE configs[3]: the Euler-Maruyama proposal, sharded
+    for kind, thr, P, T, proposal in cases:
         x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
         seq = ts.relative_alchemical_sequence(T)
-        sharded = ShardedSMCEngine(xml, P, seq, langevin=LangevinParameters(), resampler=kind, floor_threshold=thr, seed=3, resample_seed=4)
+        lang = LangevinParameters(timestep=0.0005) if proposal == "ula" else LangevinParameters()
+        sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
         sharded.anneal(x0[sharded.first:sharded.last])
         pos_parts = [torch.empty_like(sharded.local("pos")) for _ in range(world)]
         dist.all_gather(pos_parts, sharded.local("pos").contiguous())
@@ -40,12 +43,12 @@ def main():
         lab_parts = [torch.empty_like(sharded.local("label")) for _ in range(world)]
         dist.all_gather(lab_parts, sharded.local("label").contiguous())
         if rank == 0:
-            single = SMCEngine(xml, P, seq, langevin=LangevinParameters(), resampler=kind, floor_threshold=thr, seed=3, resample_seed=4)
+            single = SMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
             single.anneal(x0)
             e = single.ensemble
             same = (torch.equal(torch.cat(pos_parts), e.pos[e.cur]) and torch.equal(torch.cat(vel_parts), e.vel[e.cur]) and
                     torch.equal(torch.cat(lab_parts), e.labels) and torch.equal(sharded.cum, e.cum) and torch.equal(sharded.stats, single.stats))
-            print(f"[multi_gpu_check] world={world} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
+            print(f"[multi_gpu_check] world={world} {proposal} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
                   f"resampled at {sharded.resampled_iterations()} FE={sharded.free_energy():.6f}", flush=True)
             ok &= bool(same) and len(sharded.resampled_iterations()) > 0 or (thr == 0.5 and bool(same))
         sharded.close()

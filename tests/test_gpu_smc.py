@@ -295,3 +295,62 @@ def test_prebuilt_protocol_tables_are_bit_identical():
         runs.append((eng.ensemble.cum.cpu().numpy().copy(), eng.ensemble.positions.cpu().numpy().copy(), eng.ensemble.auxiliary_work.cpu().numpy().copy()))
     for a, b in zip(*runs):
         np.testing.assert_array_equal(a, b)
+
+
+def test_config3_full_size_perses_vacuum_1e5_particles():
+    """BASELINE configs[2] at full size (10^5 particles, fluorobenzene hybrid, the reference's 10-lambda protocol), checked
+    through size-independent properties: the G5 free-energy band, the constraint manifold, aux = -u_T(x_T) against the
+    oracle on a sample, root labels, and the weight bookkeeping of the last iteration."""
+    frames = cache_frames()
+    P = 100_000
+    x0 = frames[np.random.RandomState(3).randint(0, len(frames), P)]
+    seq = ts.relative_alchemical_sequence(10)
+    eng = _engine(system_xml("fluorobenzene"), P, seq, seed=21, resample_seed=22)
+    eng.anneal(x0)
+    assert abs(eng.free_energy() - 1.33) < 0.2, eng.free_energy()
+    assert int(eng.ensemble.nan_flags.sum()) == 0
+    x = eng.ensemble.positions.double().cpu().numpy()
+    o = XmlSystemOracle(system_xml("fluorobenzene"))
+    for (i, j, d) in o.constraints:
+        assert np.abs(np.linalg.norm(x[:, i] - x[:, j], axis=-1) / d - 1).max() < 5e-6
+    sample = np.random.RandomState(0).randint(0, P, 256)
+    np.testing.assert_allclose(eng.ensemble.auxiliary_work.cpu().numpy()[sample], -o.reduced_potential(x[sample], seq[-1]), rtol=1e-9)
+    labels = eng.ensemble.labels.cpu().numpy()
+    assert labels.min() >= 0 and labels.max() < P
+    stats = eng.stats.cpu().numpy()
+    ness = stats[1:, _lib.STAT_NESS]
+    assert np.all((ness > 0) & (ness <= 1 + 1e-12))
+    cum = eng.ensemble.cum.cpu().numpy()
+    assert np.isfinite(cum).all()
+    if stats[len(seq) - 1, _lib.STAT_RESAMPLE]:      # after a resampling every particle carries the same cumulative work
+        assert np.ptp(cum) == 0.0
+
+
+def test_config2_full_size_graph_replay_equals_eager_loop():
+    """BASELINE configs[1] (the bench workload: 10^4 alanine-dipeptide-shaped replicas, 100 lambdas): the CUDA-graph
+    replay and the eager loop give bitwise the same anneal; no NaN; constraints hold; nESS and labels are sane."""
+    from coddiwomple_b200.engine import LangevinParameters
+    xml, _ = ts.alanine_dipeptide_shaped_xml()
+    P = 10_000
+    x0 = ts.alanine_dipeptide_shaped_ensemble(P, seed=2)
+    seq = ts.relative_alchemical_sequence(100)
+    lang = LangevinParameters(temperature=300.0, collision_rate=1.0, timestep=0.002, n_steps=1)
+    eager = _engine(xml, P, seq, langevin=lang, seed=0, resample_seed=1)
+    eager.anneal(x0)
+    graph = _engine(xml, P, seq, langevin=lang, seed=0, resample_seed=1)
+    from coddiwomple_b200.engine import positions_to_rows
+    rows = positions_to_rows(x0)
+    graph.load(rows)
+    graph.capture()
+    graph.anneal(rows)
+    np.testing.assert_array_equal(eager.ensemble.cum.cpu().numpy(), graph.ensemble.cum.cpu().numpy())
+    np.testing.assert_array_equal(eager.ensemble.positions.cpu().numpy(), graph.ensemble.positions.cpu().numpy())
+    assert eager.free_energy() == graph.free_energy() and np.isfinite(eager.free_energy())
+    assert int(eager.ensemble.nan_flags.sum()) == 0
+    x = eager.ensemble.positions.double().cpu().numpy()
+    o = XmlSystemOracle(xml)
+    for (i, j, d) in o.constraints:
+        assert np.abs(np.linalg.norm(x[:, i] - x[:, j], axis=-1) / d - 1).max() < 5e-6
+    assert len(eager.resampled_iterations()) >= 1
+    labels = eager.ensemble.labels.cpu().numpy()
+    assert labels.min() >= 0 and labels.max() < P
