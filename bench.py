@@ -219,10 +219,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
-    if use_graph:
+    use_graph = not args.no_graph
+    if use_graph and world == 1:
         eng.load(x0_dev)
         eng.capture()   # the whole anneal (no host decisions inside) as one CUDA graph
+    elif use_graph:
+        eng.capture(x0_dev)   # per rank: T-1 x (fused propagate over peer memory, NCCL all-gather of W, global resample)
 
     def anneal_resident():
         eng.anneal(x0_dev)
@@ -263,7 +265,7 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel: the fused propagate kernel, timed with CUDA events on its stream
     flops = algorithmic_flops(spec, langevin.n_steps)
-    eng.graph = None if world == 1 else getattr(eng, "graph", None)  # per-launch timing uses the eager loop
+    eng.graph = None  # per-launch timing uses the eager loop
     eng.initialize(x0_dev)
     evs = []
     for t in range(1, eng.T):
@@ -294,7 +296,9 @@ def run_gpu(args):
                 "anneals_per_s": 1e3 / float(np.mean(ms)), "free_energy_kT": fe, "resampled_iterations": len(eng.resampled_iterations()),
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": float(np.mean(ms_e2e)), "h2d_bytes_per_step": int(x0_pinned.numel() * 4),
                         "d2h_bytes_per_step": int(cum_host.numel() * 8), "api": "SMCEngine.anneal(pinned host rows) + cumulative works to host", "cuda_graph": use_graph},
-                "gpu_launches": int(args.steps * 2 * (1 + 2 * (N_LAMBDA - 1) + 1)),  # K1 + (propagate, fused resample) per iteration + final gather
+                # both timed loops; single GPU: K1 + (propagate, fused resample) per iteration + final gather; sharded: K1 + (propagate,
+                # weight_update, fused resample or its 7-kernel form above 24576 particles) per iteration + final peer gather
+                "gpu_launches": int(args.steps * 2 * (1 + (2 if world == 1 else (3 if P * world <= 24576 else 9)) * (N_LAMBDA - 1) + 1)),
                 "roofline": {"bound": "fp64", "kernel": "smc_propagate_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                              "avg_launch_ms": k_ms, "share_of_step": share,

@@ -139,11 +139,11 @@ static Shape pick_shape(const SysDev& dev, bool forces, long long n, int sms) {
     if (env && atoi(env) > 0) {
         sh.T = atoi(env);
     } else {
-        // measured on B200 (tools/tune_step.py): T = 4 is the sweet spot for 13-22 atom systems at every
-        // batch size (fewer lanes starve the SM of resident warps, more lanes pay for force copies and idle tails);
-        // tiny systems have nothing to split, and tiny batches need wider teams just to occupy the SM sub-partitions.
+        // measured on B200 (tools/tune_step.py): T = 4 is the sweet spot for 13-22 atom systems (fewer lanes
+        // starve the SM of resident warps, more lanes pay for force copies and idle tails); tiny systems have nothing to
+        // split.  The choice depends on the SYSTEM only, never on the batch size: the summation order of energies and
+        // forces follows the team size, and results must not change with how particles are sharded over GPUs.
         sh.T = dev.n_atoms >= 8 ? 4 : (dev.n_atoms >= 4 ? 2 : 1);
-        while (sh.T < 8 && dev.n_atoms >= 2 * sh.T && (n * sh.T + 31) / 32 < (long long)sms * 4) sh.T *= 2;
     }
     if (sh.T > 8) sh.T = 8;
     while (sh.T > 1 && make_layout(dev, forces, sh.R, sh.T).total > 227 * 1024) sh.T /= 2;

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double*
 // Same integer algorithm as the multi-kernel path => same ancestors bit for bit; for batches this small the
 // multi-kernel path is pure launch latency (7 launches for ~30 us of work at n = 1e4).
 constexpr int kFusedThreads = 1024;
-constexpr int kFusedMax = 16384;
+constexpr int kFusedMax = 24576;  // cdf in shared memory: 192 KB (covers 2 x 10^4 particles sharded over two GPUs)
 
 __device__ __forceinline__ double philox_uniform53(unsigned long long seed, unsigned long long stream_id, long long i) {
     u4 c;

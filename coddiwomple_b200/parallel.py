@@ -229,8 +229,38 @@ class ShardedSMCEngine:
 
     graph = None
 
+    def capture(self, positions_local, velocities_local=None):
+        """Capture iterations 1..T-1 (fused propagate with peer-mapped gather, NCCL all-gather of W, global resample)
+        into one CUDA graph per rank; every rank must call this collectively.  `anneal` then replays it."""
+        self.graph = None
+        self.initialize(positions_local, velocities_local)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy loading, NCCL channel setup, cudaFuncSetAttribute)
+            for t in range(1, self.T):
+                self.step(t)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.initialize(positions_local, velocities_local)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            for t in range(1, self.T):
+                self.step(t)
+        self._graph_final = (self.cur, self.pending_gather, self.iteration)
+        self.graph = g
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        return self
+
     def anneal(self, positions_local, velocities_local=None):
         self.initialize(positions_local, velocities_local)
+        if self.graph is not None:
+            self.graph.replay()
+            self.cur, self.pending_gather, self.iteration = self._graph_final
+            self.materialize()
+            return self
         return self.run()
 
     # ------------------------------------------------------------------ results

@@ -29,13 +29,21 @@ def main():
     frames = np.load(os.path.join(root, "tests", "golden", "fluorobenzene_cache.npy"))
     ok = True
     cases = (("multinomial", 0.9999, 4096, 8, "baoab"), ("systematic", 0.9999, 4096, 8, "baoab"), ("multinomial", 0.5, 2048 * world, 12, "baoab"),
-             ("multinomial", 0.9999, 4096, 8, "ula"))   # BASELINE configs[3]: the Euler-Maruyama proposal, sharded
+             ("multinomial", 0.9999, 4096, 8, "ula"),
+             ("systematic", 0.9999, 1024 * 12 * world, 6, "baoab"))   # a batch whose per-rank share is launched very differently from the whole   # BASELINE configs[3]: the Euler-Maruyama proposal, sharded
     for kind, thr, P, T, proposal in cases:
         x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
         seq = ts.relative_alchemical_sequence(T)
         lang = LangevinParameters(timestep=0.0005) if proposal == "ula" else LangevinParameters()
         sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
         sharded.anneal(x0[sharded.first:sharded.last])
+        if os.environ.get("CDW_CHECK_GRAPH") and proposal == "baoab" and kind == "multinomial" and thr != 0.5:
+            eager_cum = sharded.cum.clone()
+            sharded.capture(x0[sharded.first:sharded.last])
+            sharded.anneal(x0[sharded.first:sharded.last])
+            if rank == 0:
+                print(f"[multi_gpu_check] CUDA-graph replay of the sharded loop == eager: {torch.equal(eager_cum, sharded.cum)}", flush=True)
+            ok &= torch.equal(eager_cum, sharded.cum)
         pos_parts = [torch.empty_like(sharded.local("pos")) for _ in range(world)]
         dist.all_gather(pos_parts, sharded.local("pos").contiguous())
         vel_parts = [torch.empty_like(sharded.local("vel")) for _ in range(world)]
