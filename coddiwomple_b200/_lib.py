@@ -42,6 +42,20 @@ class LangevinParams(C.Structure):
                 ("n_steps", C.c_int32), ("flags", C.c_uint32)]
 
 
+class StaticCache(C.Structure):
+    """struct cdw_static_cache (include/cdw.h): static-term forces / energies at the input and output rows."""
+    _fields_ = [("force_in", C.c_void_p), ("energy_in", C.c_void_p), ("force_out", C.c_void_p), ("energy_out", C.c_void_p),
+                ("peer_force_in", C.c_void_p), ("peer_energy_in", C.c_void_p)]
+
+
+def _addr(t):
+    return None if t is None else (t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+
+
+def static_cache(force_in, energy_in, force_out, energy_out, peer_force_in=None, peer_energy_in=None):
+    return StaticCache(_addr(force_in), _addr(energy_in), _addr(force_out), _addr(energy_out), _addr(peer_force_in), _addr(peer_energy_in))
+
+
 def make_desc(spec):
     """Build a SystemDesc whose pointers reference `spec`'s numpy arrays (kept alive through the returned tuple)."""
     keep = []
@@ -90,6 +104,10 @@ _SIGNATURES = {
     "cdw_energy_forces": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "cdw_smc_propagate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64,
                                     C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cdw_smc_propagate_cached": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64,
+                                           C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), _P]),
+    "cdw_smc_propagate_sharded_cached": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams),
+                                                   C.c_uint64, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), _P]),
     "cdw_smc_propagate_sharded": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64,
                                             C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "cdw_baoab": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P]),

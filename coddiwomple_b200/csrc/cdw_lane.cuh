@@ -248,35 +248,47 @@ CDW_HD void add3ff(float* arr, int base, f3 v) { arr[base] += v.x; arr[base + kR
 // Potential energy (kJ/mol) of the team's replica (same value in every lane of the team).  With F the forces end up
 // in force copy 0: each lane accumulates the terms it evaluates into its own copy, then the copies are summed.
 // Entered and left with the team synchronised.
+//
+// `part` selects the terms: PART_ALL, PART_STATIC (the leading lambda-independent terms of every table) or PART_DYNAMIC
+// (the rest).  PART_DYNAMIC ADDS to what force copy 0 already holds (the static forces: preloaded from the particle's
+// cache row or left there by a PART_STATIC pass), so STATIC followed by DYNAMIC equals ALL up to summation order.
+enum { PART_ALL = 0, PART_STATIC = 1, PART_DYNAMIC = 2 };
+
 template <bool F>
-CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
+CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M, int part = PART_ALL) {
     CDW_UNPACK(M);
     const int A = s.n_atoms;
     const float* __restrict__ x = M.x;
     float* __restrict__ f = M.f + tl * (3 * kR) * A;  // this lane's force copy
+    const bool dyn = part == PART_DYNAMIC, sta = part == PART_STATIC;
+    const int b0 = dyn ? s.n_bonds_s : 0, b1 = sta ? s.n_bonds_s : s.n_bonds;
+    const int a0 = dyn ? s.n_angles_s : 0, a1 = sta ? s.n_angles_s : s.n_angles;
+    const int t0 = dyn ? s.n_torsions_s : 0, t1 = sta ? s.n_torsions_s : s.n_torsions;
+    const int p0 = dyn ? s.n_pairs_s : 0, p1 = sta ? s.n_pairs_s : s.n_pairs;
+    const int e0 = dyn ? s.n_ext_s : 0, e1 = sta ? s.n_ext_s : s.n_ext;
     CDW_TEAM_SYNC(M);
-    if (F) {
+    if (F && !(dyn && tl == 0)) {
         for (int a = 0; a < A; ++a) {
             const int b = CDW_BASE(a);
             f[b] = 0.f; f[b + kR] = 0.f; f[b + 2 * kR] = 0.f;
         }
     }
     double e = 0.0;
-    for (int q = tl; q < s.n_bonds; q += T_) {
+    for (int q = b0 + tl; q < b1; q += T_) {
         const EffBond b = T.bonds[q];
         const int bi = CDW_BASE(b.i), bj = CDW_BASE(b.j);
         d3 fi;
         e += bond_term<F>(ld3(x, bi), ld3(x, bj), b.K, b.L, fi);
         if (F) { add3f(f, bi, fi); add3f(f, bj, -1.0 * fi); }
     }
-    for (int q = tl; q < s.n_angles; q += T_) {
+    for (int q = a0 + tl; q < a1; q += T_) {
         const EffAngle a = T.angles[q];
         const int bi = CDW_BASE(a.i), bj = CDW_BASE(a.j), bk = CDW_BASE(a.k);
         d3 fi, fk;
         e += angle_term<F>(ld3(x, bi), ld3(x, bj), ld3(x, bk), a.K, a.T0, fi, fk);
         if (F) { add3f(f, bi, fi); add3f(f, bj, -1.0 * (fi + fk)); add3f(f, bk, fk); }
     }
-    for (int q = tl; q < s.n_torsions; q += T_) {
+    for (int q = t0 + tl; q < t1; q += T_) {
         const EffTorsion t = T.torsions[q];
         const int bi = CDW_BASE(t.i), bj = CDW_BASE(t.j), bk = CDW_BASE(t.k), bl = CDW_BASE(t.l);
         d3 fi, fj, fk, fl;
@@ -286,8 +298,8 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
     {
         // pairs are sorted by (i, j); each lane takes a contiguous block, so runs of pairs share atom i: its position is
         // loaded once and its force is accumulated in registers (fp64) and flushed when the run ends
-        const int per = (s.n_pairs + T_ - 1) / T_;
-        const int q0 = tl * per, q1 = q0 + per < s.n_pairs ? q0 + per : s.n_pairs;
+        const int per = (p1 - p0 + T_ - 1) / T_;
+        const int q0 = p0 + tl * per, q1 = q0 + per < p1 ? q0 + per : p1;
         // Geometry and energy in fp64 from the fp32 coordinates; the FORCE vector is formed in fp32 (g rounded once, fp32
         // coordinate differences) because it is accumulated in fp32 anyway: one fp64->fp32 conversion per pair instead of
         // three (conversions run on the quarter-rate XU pipe, the busiest pipe of this kernel).
@@ -342,7 +354,7 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M) {
 #undef CDW_PAIR_RUN
 #undef CDW_PAIR_APPLY
     }
-    for (int q = tl; q < s.n_ext; q += T_) {
+    for (int q = e0 + tl; q < e1; q += T_) {
         const EffExt w = T.exts[q];
         const int bw = CDW_BASE(w.atom);
         d3 fw;
@@ -510,6 +522,10 @@ struct PropArgs {
     // reachable through peer-mapped pointers (CUDA IPC over NVLink).  NULL peer_pos = single-GPU addressing.
     const float4* const* peer_pos; const float4* const* peer_vel; const double* const* peer_aux; const int* const* peer_label;
     long long n_per_rank;
+    // static-term cache (cdw_static_cache): forces / energy of the lambda-independent terms at the INPUT rows (may be NULL:
+    // then they are evaluated) and at the OUTPUT rows.  Indexed like pos_in / pos_out (input through the ancestor).
+    const float4* fs_in; const double* us_in; float4* fs_out; double* us_out;
+    const float4* const* peer_fs; const double* const* peer_us;
 };
 
 // where row `src` (a global particle id when the run is sharded) lives
@@ -541,6 +557,11 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
             if (with_v) {
                 const float4 w = a.vel_in ? row_ptr(a, a.vel_in, a.peer_vel, src, A)[at] : make_float4(0.f, 0.f, 0.f, 0.f);
                 V[b] = w.x; V[b + kR] = w.y; V[b + 2 * kR] = w.z;
+                if (a.fs_in) {  // static forces of the ancestor's coordinates -> force copy 0
+                    float* Fc = (float*)(smem + L.f);
+                    const float4 g = row_ptr(a, a.fs_in, a.peer_fs, src, A)[at];
+                    Fc[b] = g.x; Fc[b + kR] = g.y; Fc[b + 2 * kR] = g.z;
+                }
             }
         }
     }
@@ -571,6 +592,7 @@ CDW_HD void cta_store_rows(const SysDev& s, const PropArgs& a, unsigned char* sm
                 }
                 a.pos_out[(p0 + r) * A + at] = q;
                 if (a.vel_out) a.vel_out[(p0 + r) * A + at] = w;
+                if (a.fs_out && a.fs_in && BAD[r]) a.fs_out[(p0 + r) * A + at] = row_ptr(a, a.fs_in, a.peer_fs, SRC[r], A)[at];
             }
         }
     }
@@ -598,23 +620,45 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
     const double inv_kT = 1.0 / a.kT;
     enum { OP_E = 0, OP_V = 1, OP_R = 2, OP_O = 3, OP_MB = 4, OP_U = 5, OP_B = 6 };
     const bool ula = (a.flags & CDW_FLAG_ULA) != 0;
-    double U = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0;
-    const int n_ops = ula ? 1 + 3 * a.n_steps : 1 + 6 * a.n_steps;
+    // Static-term cache: with `split` every evaluation is two passes of the ONE lane_energy call site, static terms then
+    // dynamic terms (ops E E), and the opening evaluation skips the static pass when the particle's cache row is given.
+    const bool split = a.fs_out != nullptr && !track;
+    const bool cached_open = split && a.fs_in != nullptr && a.n_steps > 0;
+    const int n_open = split && !cached_open ? 2 : 1;                 // [ES] ED | E
+    const int n_body = (ula ? 3 : 6) + (split ? 1 : 0);               // V R O R [ES] E(D) V | U [ES] E(D) B
+    const int e_slot = ula ? 1 : 4;                                   // slot of the (first) evaluation inside a step
+    double U = 0.0, Us = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0;
+    if (cached_open) Us = a.peer_pos ? a.peer_us[src / a.n_per_rank][src % a.n_per_rank] : a.us_in[src];
+    const int n_ops = n_open + n_body * a.n_steps;
     // op -1 (only with RANDOMIZE): Context.setVelocitiesToTemperature (propagators.py:137-138)
     for (int op = (!ula && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0; op < n_ops; ++op) {
-        int kind, slot = 0, st = 0;
+        int kind, slot = 0, st = 0, part = PART_ALL;
         if (op < 0) kind = OP_MB;
-        else if (op == 0) kind = OP_E;
-        else if (ula) {
-            slot = (op - 1) % 3; st = (op - 1) / 3;  // U E B
-            kind = slot == 0 ? OP_U : (slot == 1 ? OP_E : OP_B);
+        else if (op < n_open) {
+            kind = OP_E;
+            part = !split ? PART_ALL : (cached_open || op == 1 ? PART_DYNAMIC : PART_STATIC);
         } else {
-            slot = (op - 1) % 6; st = (op - 1) / 6;  // V R O R E V
-            kind = slot == 0 || slot == 5 ? OP_V : (slot == 1 || slot == 3 ? OP_R : (slot == 2 ? OP_O : OP_E));
+            slot = (op - n_open) % n_body; st = (op - n_open) / n_body;
+            if (split && slot > e_slot) slot -= 1, part = PART_DYNAMIC;   // the second pass of the evaluation
+            else if (split && slot == e_slot) part = PART_STATIC;
+            if (ula) kind = slot == 0 ? OP_U : (slot == 1 ? OP_E : OP_B);                                               // U E B
+            else kind = slot == 0 || slot == 5 ? OP_V : (slot == 1 || slot == 3 ? OP_R : (slot == 2 ? OP_O : OP_E));   // V R O R E V
+            if (kind != OP_E) part = PART_ALL;
         }
         if (kind == OP_E) {
-            U = lane_energy<true>(s, T, M);
-            if (op == 0) u_first = U;
+            const double e = lane_energy<true>(s, T, M, part);
+            if (part == PART_STATIC) {
+                Us = e;
+                if (st == a.n_steps - 1 || a.n_steps == 0) {  // static forces (force copy 0 right now) at the output coordinates -> cache row
+                    for (int at = tl; at < A; at += T_) {
+                        const int b = CDW_BASE(at);
+                        a.fs_out[p * A + at] = make_float4(M.f[b], M.f[b + kR], M.f[b + 2 * kR], 0.f);
+                    }
+                }
+                continue;
+            }
+            U = part == PART_DYNAMIC ? Us + e : e;
+            if (op < n_open) u_first = U;
             else if (track) shadow += pending + U;  // closes the second R of the step: (KE + U_new) - (KE_old + U_mid)
             continue;
         }
@@ -725,6 +769,11 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         if (a.proposal_out) a.proposal_out[p] = ula ? proposal : proposal * inv_kT;
         if (a.nan_flags) a.nan_flags[p] = bad ? 1 : 0;
         if (a.energy_out) a.energy_out[p] = u_first;
+        if (split && a.us_out) {  // a reverted move keeps the ancestor's cache (its static-force row is restored by cta_store_rows)
+            double us_keep = Us;
+            if (bad && cached_open) us_keep = a.peer_pos ? a.peer_us[src / a.n_per_rank][src % a.n_per_rank] : a.us_in[src];
+            a.us_out[p] = us_keep;
+        }
     }
     return ordered_key(w);
 }

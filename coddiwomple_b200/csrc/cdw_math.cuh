@@ -323,7 +323,7 @@ struct SysDev {
     int n_bonds, n_angles, n_torsions, n_pairs, n_ext, n_exceptions, n_cons, n_clusters;
     int n_atom_off, n_exc_off, n_coef;
     int slot_core, slot_insert, slot_delete, slot_alpha;
-    int n_slots;       // force-scratch slots
+    int n_bonds_s, n_angles_s, n_torsions_s, n_pairs_s, n_ext_s;  // leading STATIC (lambda-independent) terms of each table
     int a_pad;         // n_atoms rounded up to even (16 B alignment of double rows)
     const double* masses;      // [A]
     const double* inv_mass;    // [A]
@@ -346,9 +346,6 @@ struct SysDev {
     const double* cluster_coef;     // c_qr = d(iq,ir)/m_ir - d(iq,jr)/m_jr - d(jq,ir)/m_ir + d(jq,jr)/m_jr
     const int* cons_atoms;      // [n_cons][2], sorted by cluster
     const double* cons_d2;      // [n_cons] d^2
-    // force gather: atom -> scratch slots
-    const int* atom_slot_start; // [A+1]
-    const int* atom_slots;      // [n_slots]
 };
 
 

@@ -1,5 +1,5 @@
 // cdw_pack.h — host-side construction of one replica's device tables (pure C++, no CUDA): validation, CSR of the
-// lambda offsets, constraint clusters, force-scratch slot map; everything packed into ONE blob so that the same
+// lambda offsets, constraint clusters, static/dynamic term split; everything packed into ONE blob so that the same
 // bytes serve the GPU (cudaMemcpy) and the host test harness.
 #pragma once
 #include <string.h>
@@ -158,25 +158,47 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     }
     cluster_coef_start[n_clusters] = (int)cluster_coef.size();
 
-    // ---- force scratch slots: slot(type, pos, idx) = base(type) + pos * n_type + idx; CSR atom -> slots
+    // ---- static / dynamic split.  A term is STATIC when no global parameter enters it: its energy and forces at given
+    // coordinates are the same for every lambda, so the closing evaluation of one SMC iteration can hand them to the
+    // opening evaluation of the next (same coordinates, next lambda).  Every term table is reordered static-first
+    // (stable: pairs stay sorted by (i, j) inside each part).
     const int nb = d->n_bonds, na = d->n_angles, nt = d->n_torsions, np = d->n_pairs, ne = d->n_ext;
-    const int base_b = 0, base_a = 2 * nb, base_t = base_a + 3 * na, base_p = base_t + 4 * nt, base_e = base_p + 2 * np;
-    const int n_slots = base_e + ne;
-    std::vector<std::vector<int>> per_atom(A);
-    for (int q = 0; q < nb; ++q)
-        for (int c = 0; c < 2; ++c) per_atom[d->bond_atoms[2 * q + c]].push_back(base_b + c * nb + q);
-    for (int q = 0; q < na; ++q)
-        for (int c = 0; c < 3; ++c) per_atom[d->angle_atoms[3 * q + c]].push_back(base_a + c * na + q);
-    for (int q = 0; q < nt; ++q)
-        for (int c = 0; c < 4; ++c) per_atom[d->torsion_atoms[4 * q + c]].push_back(base_t + c * nt + q);
-    for (int q = 0; q < np; ++q)
-        for (int c = 0; c < 2; ++c) per_atom[d->pair_atoms[2 * q + c]].push_back(base_p + c * np + q);
-    for (int q = 0; q < ne; ++q) per_atom[d->ext_atom[q]].push_back(base_e + q);
-    std::vector<int> atom_slot_start(A + 1, 0), atom_slots;
-    for (int a = 0; a < A; ++a) {
-        atom_slots.insert(atom_slots.end(), per_atom[a].begin(), per_atom[a].end());
-        atom_slot_start[a + 1] = (int)atom_slots.size();
+    auto static_first = [](int n, const std::vector<char>& dyn) {
+        std::vector<int> perm(n);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int p, int q) { return dyn[p] < dyn[q]; });
+        return perm;
+    };
+    std::vector<char> dyn_b(nb), dyn_a(na), dyn_t(nt), dyn_p(np), dyn_e(ne);
+    for (int q = 0; q < nb; ++q) dyn_b[q] = d->bond_slot[q] >= 0 && (d->bond_par[4 * q + 1] != 0.0 || d->bond_par[4 * q + 3] != 0.0);
+    for (int q = 0; q < na; ++q) dyn_a[q] = d->angle_slot[q] >= 0 && (d->angle_par[4 * q + 1] != 0.0 || d->angle_par[4 * q + 3] != 0.0);
+    for (int q = 0; q < nt; ++q) dyn_t[q] = d->torsion_slot[q] >= 0 && d->torsion_par[3 * q + 1] != 0.0;
+    for (int q = 0; q < ne; ++q) {
+        dyn_e[q] = 0;
+        for (int c = 0; c < 3; ++c) dyn_e[q] |= d->ext_slot[3 * q + c] >= 0 && d->ext_par[6 * q + 2 * c + 1] != 0.0;
     }
+    for (int q = 0; q < np; ++q) {
+        const int i = d->pair_atoms[2 * q], j = d->pair_atoms[2 * q + 1], k = d->pair_nb[q];
+        bool dy = d->pair_sc_class[q] >= 0;
+        if (k == -2) dy |= atom_off_start[i + 1] > atom_off_start[i] || atom_off_start[j + 1] > atom_off_start[j];
+        if (k >= 0) dy |= exc_off_start[k + 1] > exc_off_start[k];
+        dyn_p[q] = dy;
+    }
+    const std::vector<int> perm_b = static_first(nb, dyn_b), perm_a = static_first(na, dyn_a), perm_t = static_first(nt, dyn_t),
+                           perm_p = static_first(np, dyn_p), perm_e = static_first(ne, dyn_e);
+    auto n_static = [](const std::vector<char>& dyn) { return (int)std::count(dyn.begin(), dyn.end(), (char)0); };
+    auto permuted_i = [](const int32_t* src, const std::vector<int>& perm, int width) {
+        std::vector<int> out;
+        for (int q : perm)
+            for (int c = 0; c < width; ++c) out.push_back(src[width * q + c]);
+        return out;
+    };
+    auto permuted_d = [](const double* src, const std::vector<int>& perm, int width) {
+        std::vector<double> out;
+        for (int q : perm)
+            for (int c = 0; c < width; ++c) out.push_back(src[width * q + c]);
+        return out;
+    };
 
     std::vector<double> masses = vec(d->masses, A), inv_mass(A);
     for (int a = 0; a < A; ++a) inv_mass[a] = 1.0 / masses[a];
@@ -184,20 +206,20 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     // ---- pack everything into one device blob
     Packer pk;
     size_t o_m = pk.add(masses), o_im = pk.add(inv_mass);
-    size_t o_ba = pk.add(vec(d->bond_atoms, 2 * nb)), o_bs = pk.add(vec(d->bond_slot, nb)), o_bp = pk.add(vec(d->bond_par, 4 * nb));
-    size_t o_aa = pk.add(vec(d->angle_atoms, 3 * na)), o_as = pk.add(vec(d->angle_slot, na)), o_ap = pk.add(vec(d->angle_par, 4 * na));
-    size_t o_ta = pk.add(vec(d->torsion_atoms, 4 * nt)), o_ts = pk.add(vec(d->torsion_slot, nt)), o_tn = pk.add(vec(d->torsion_n, nt)),
-           o_tp = pk.add(vec(d->torsion_par, 3 * nt));
+    size_t o_ba = pk.add(permuted_i(d->bond_atoms, perm_b, 2)), o_bs = pk.add(permuted_i(d->bond_slot, perm_b, 1)), o_bp = pk.add(permuted_d(d->bond_par, perm_b, 4));
+    size_t o_aa = pk.add(permuted_i(d->angle_atoms, perm_a, 3)), o_as = pk.add(permuted_i(d->angle_slot, perm_a, 1)), o_ap = pk.add(permuted_d(d->angle_par, perm_a, 4));
+    size_t o_ta = pk.add(permuted_i(d->torsion_atoms, perm_t, 4)), o_ts = pk.add(permuted_i(d->torsion_slot, perm_t, 1)),
+           o_tn = pk.add(permuted_i(d->torsion_n, perm_t, 1)), o_tp = pk.add(permuted_d(d->torsion_par, perm_t, 3));
     std::vector<double> nbpar = d->nb_atom_par ? vec(d->nb_atom_par, 3 * A) : std::vector<double>(3 * A, 0.0);
     size_t o_nb = pk.add(nbpar), o_aos = pk.add(atom_off_start), o_aosl = pk.add(atom_off_slot), o_aop = pk.add(atom_off_par);
     size_t o_ep = pk.add(vec(d->exc_par, 3 * d->n_exceptions)), o_eos = pk.add(exc_off_start), o_eosl = pk.add(exc_off_slot),
            o_eop = pk.add(exc_off_par);
-    size_t o_pa = pk.add(vec(d->pair_atoms, 2 * np)), o_pn = pk.add(vec(d->pair_nb, np)), o_pc = pk.add(vec(d->pair_sc_class, np)),
-           o_pp = pk.add(vec(d->pair_sc_par, 4 * np));
-    size_t o_ea = pk.add(vec(d->ext_atom, ne)), o_es = pk.add(vec(d->ext_slot, 3 * ne)), o_epar = pk.add(vec(d->ext_par, 6 * ne));
+    size_t o_pa = pk.add(permuted_i(d->pair_atoms, perm_p, 2)), o_pn = pk.add(permuted_i(d->pair_nb, perm_p, 1)),
+           o_pc = pk.add(permuted_i(d->pair_sc_class, perm_p, 1)),
+           o_pp = pk.add(d->pair_sc_par ? permuted_d(d->pair_sc_par, perm_p, 4) : std::vector<double>(4 * (size_t)np, 0.0));
+    size_t o_ea = pk.add(permuted_i(d->ext_atom, perm_e, 1)), o_es = pk.add(permuted_i(d->ext_slot, perm_e, 3)), o_epar = pk.add(permuted_d(d->ext_par, perm_e, 6));
     size_t o_cs = pk.add(cluster_start), o_ca = pk.add(cons_atoms), o_cd = pk.add(cons_d2);
     size_t o_ccs = pk.add(cluster_coef_start), o_cc = pk.add(cluster_coef);
-    size_t o_ss = pk.add(atom_slot_start), o_sl = pk.add(atom_slots);
 
 
     const unsigned char* B = nullptr;
@@ -206,7 +228,7 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     v.n_cons = d->n_constraints; v.n_clusters = n_clusters;
     v.n_atom_off = (int)atom_off_slot.size(); v.n_exc_off = (int)exc_off_slot.size(); v.n_coef = (int)cluster_coef.size();
     v.slot_core = d->slot_sterics_core; v.slot_insert = d->slot_sterics_insert; v.slot_delete = d->slot_sterics_delete; v.slot_alpha = d->slot_softcore_alpha;
-    v.n_slots = n_slots;
+    v.n_bonds_s = n_static(dyn_b); v.n_angles_s = n_static(dyn_a); v.n_torsions_s = n_static(dyn_t); v.n_pairs_s = n_static(dyn_p); v.n_ext_s = n_static(dyn_e);
     v.a_pad = (A + 1) & ~1;
     v.masses = (const double*)(B + o_m); v.inv_mass = (const double*)(B + o_im);
     v.bond_atoms = (const int*)(B + o_ba); v.bond_slot = (const int*)(B + o_bs); v.bond_par = (const double*)(B + o_bp);
@@ -218,7 +240,6 @@ inline int pack_system(const cdw_system_desc* d, std::vector<unsigned char>& blo
     v.ext_atom = (const int*)(B + o_ea); v.ext_slot = (const int*)(B + o_es); v.ext_par = (const double*)(B + o_epar);
     v.cluster_coef_start = (const int*)(B + o_ccs); v.cluster_coef = (const double*)(B + o_cc);
     v.cluster_start = (const int*)(B + o_cs); v.cons_atoms = (const int*)(B + o_ca); v.cons_d2 = (const double*)(B + o_cd);
-    v.atom_slot_start = (const int*)(B + o_ss); v.atom_slots = (const int*)(B + o_sl);
 
     blob.swap(pk.buf);
     return CDW_OK;
@@ -237,7 +258,6 @@ inline void rebase_system(SysDev& v, const unsigned char* base) {
     CDW_RB(ext_atom); CDW_RB(ext_slot); CDW_RB(ext_par);
     CDW_RB(cluster_coef_start); CDW_RB(cluster_coef);
     CDW_RB(cluster_start); CDW_RB(cons_atoms); CDW_RB(cons_d2);
-    CDW_RB(atom_slot_start); CDW_RB(atom_slots);
 #undef CDW_RB
 }
 

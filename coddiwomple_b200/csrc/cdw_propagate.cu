@@ -254,12 +254,36 @@ extern "C" int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_
     return launch(sys, a, true, (cudaStream_t)stream);
 }
 
-extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
+static int apply_cache(PropArgs& a, const cdw_static_cache* c, bool sharded, bool gather) {
+    if (!c) return CDW_OK;
+    CDW_REQUIRE(c->force_out && c->energy_out, "cdw_static_cache: force_out and energy_out are required");
+    CDW_REQUIRE(!(a.flags & CDW_FLAG_TRACK_WORKS), "cdw_static_cache cannot be combined with CDW_FLAG_TRACK_WORKS");
+    const bool have_in = sharded ? (c->peer_force_in && c->peer_energy_in) : (c->force_in && c->energy_in);
+    CDW_REQUIRE(have_in || a.n_steps == 0, "cdw_static_cache: seed the cache with an n_steps = 0 call before stepping");
+    CDW_REQUIRE(!(gather && have_in && !sharded && c->force_in == c->force_out), "cdw_static_cache: gather-on-load needs distinct in/out rows");
+    a.fs_out = (float4*)c->force_out; a.us_out = c->energy_out;
+    if (have_in && a.n_steps > 0) {
+        if (sharded) { a.peer_fs = (const float4* const*)c->peer_force_in; a.peer_us = c->peer_energy_in; a.fs_in = (const float4*)1; a.us_in = (const double*)1; }
+        else { a.fs_in = (const float4*)c->force_in; a.us_in = c->energy_in; }
+    }
+    return CDW_OK;
+}
+
+extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out, int64_t n,
+                                 const int32_t* anc, const double* aux_in, const double* cum_in, const int32_t* label_in, const double* lambda,
+                                 const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
+                                 double* aux_out, int32_t* label_out, double* u_first_out, double* u_last_out, double* shadow_out,
+                                 double* proposal_out, int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream) {
+    return cdw_smc_propagate_cached(sys, pos_in, vel_in, pos_out, vel_out, n, anc, aux_in, cum_in, label_in, lambda, prm, seed, step0, gid0, inc_out, w_out,
+                                    aux_out, label_out, u_first_out, u_last_out, shadow_out, proposal_out, nan_flags, wmin_key, nullptr, stream);
+}
+
+extern "C" int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
                                  int64_t n, const int32_t* anc, const double* aux_in, const double* cum_in, const int32_t* label_in,
                                  const double* lambda, const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0,
                                  double* inc_out, double* w_out, double* aux_out, int32_t* label_out, double* u_first_out,
                                  double* u_last_out, double* shadow_out, double* proposal_out, int32_t* nan_flags, uint64_t* wmin_key,
-                                 cdw_stream stream) {
+                                 const cdw_static_cache* cache, cdw_stream stream) {
     CDW_REQUIRE(sys && prm && n >= 0, "null argument");
     if (n == 0) return CDW_OK;
     CDW_REQUIRE(pos_in, "null argument");
@@ -278,6 +302,7 @@ extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, con
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
+    if (int rc = apply_cache(a, cache, false, anc != nullptr)) return rc;
     return launch(sys, a, true, (cudaStream_t)stream);
 }
 
@@ -286,6 +311,15 @@ extern "C" int cdw_smc_propagate_sharded(const cdw_system* sys, const float* con
                                          const int32_t* anc, const double* cum_in, const double* lambda, const cdw_langevin_params* prm, uint64_t seed,
                                          uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out, int32_t* label_out,
                                          int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream) {
+    return cdw_smc_propagate_sharded_cached(sys, peer_pos, peer_vel, peer_aux, peer_label, n_ranks, n_per_rank, pos_out, vel_out, n, anc, cum_in, lambda, prm,
+                                            seed, step0, gid0, inc_out, w_out, aux_out, label_out, nan_flags, wmin_key, nullptr, stream);
+}
+
+extern "C" int cdw_smc_propagate_sharded_cached(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
+                                         const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, float* pos_out, float* vel_out, int64_t n,
+                                         const int32_t* anc, const double* cum_in, const double* lambda, const cdw_langevin_params* prm, uint64_t seed,
+                                         uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out, int32_t* label_out,
+                                         int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache, cdw_stream stream) {
     CDW_REQUIRE(sys && prm && n >= 0, "null argument");
     if (n == 0) return CDW_OK;
     const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;
@@ -301,6 +335,7 @@ extern "C" int cdw_smc_propagate_sharded(const cdw_system* sys, const float* con
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
+    if (int rc = apply_cache(a, cache, true, true)) return rc;
     return launch(sys, a, true, (cudaStream_t)stream);
 }
 

@@ -118,7 +118,7 @@ class ParticleEnsemble:
     gather-on-load of the next propagate call.
     """
 
-    def __init__(self, system, n_particles, gid0=0, device=None, record_history=False):
+    def __init__(self, system, n_particles, gid0=0, device=None, record_history=False, static_cache=True):
         _require_cuda()
         self.system = system if isinstance(system, DeviceSystem) else DeviceSystem(system)
         self.lib = self.system.lib
@@ -141,6 +141,12 @@ class ParticleEnsemble:
         self.cdf = torch.zeros(P, dtype=torch.int64, device=d)
         self.ws_bytes = int(self.lib.cdw_weight_workspace_bytes(P))
         self.workspace = torch.zeros((self.ws_bytes + 7) // 8, dtype=torch.int64, device=d)
+        # static-term cache (include/cdw.h: cdw_static_cache): forces / energy of the lambda-independent terms at pos[k],
+        # double-buffered with the rows they belong to and gathered with them
+        self.static_cache = bool(static_cache)
+        self.fs = torch.zeros(2, P, A, 4, dtype=torch.float32, device=d) if self.static_cache else None
+        self.us = torch.zeros(2, P, dtype=torch.float64, device=d) if self.static_cache else None
+        self.cache_valid = False
         self.cur = 0
         self.pending_gather = False  # anc has not been applied to (pos, vel, aux, label) yet
         self.iteration = 0
@@ -152,6 +158,7 @@ class ParticleEnsemble:
         rows = positions if torch.is_tensor(positions) else positions_to_rows(positions, self.device)
         assert tuple(rows.shape) == (self.P, self.A, 4), rows.shape
         self.pos[self.cur].copy_(rows, non_blocking=True)
+        self.cache_valid = False
         if velocities is not None:
             vrows = velocities if torch.is_tensor(velocities) else positions_to_rows(velocities, self.device)
             self.vel[self.cur].copy_(vrows, non_blocking=True)
@@ -168,6 +175,7 @@ class ParticleEnsemble:
                                                     _lib.ptr(self.label[n]), self.P, self.A, _lib.current_stream()), "cdw_gather_particles")
             self.cur = n
             self.pending_gather = False
+            self.cache_valid = False  # the static-term rows were not gathered
 
     @property
     def positions(self):
@@ -198,10 +206,27 @@ class ParticleEnsemble:
                                                  _lib.ptr(u), _lib.current_stream()), "cdw_reduced_potential")
         return u
 
+    def seed_static_cache(self, lam_row, kT, aux_out=None):
+        """Evaluate the static terms at the current rows (an n_steps = 0 cdw_smc_propagate_cached call): fills fs/us[cur]
+        and, optionally, aux_out = -u(x; lambda)."""
+        self.materialize()
+        c = self.cur
+        prm = _lib.LangevinParams(0.0, 0.0, float(kT), 1e-6, 0, 0)
+        cache = _lib.static_cache(None, None, self.fs[c], self.us[c])
+        _lib.check(self.lib.cdw_smc_propagate_cached(
+            self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), None, None, self.P, None, None, None, None, _lib.ptr(lam_row), C.byref(prm),
+            C.c_uint64(0), C.c_uint64(0), C.c_int64(self.gid0), None, None, _lib.ptr(aux_out), None, None, None, None, None, None, None, C.byref(cache),
+            _lib.current_stream()), "cdw_smc_propagate_cached")
+        self.cache_valid = True
+
     def equip_initial(self, lam_row, beta):
         """aux = -u_0(x_0); cum = 0 (ProposalFactory.equip_initial_sample, distribution_factories.py:180-220)."""
-        u0 = self.reduced_potential(lam_row, beta)
-        self.aux[self.cur].copy_(-u0)
+        if self.static_cache:
+            self.seed_static_cache(lam_row, 1.0 / beta, aux_out=self.aux[self.cur])
+            u0 = -self.aux[self.cur]
+        else:
+            u0 = self.reduced_potential(lam_row, beta)
+            self.aux[self.cur].copy_(-u0)
         self.cum.zero_()
         self.iteration = 0
         self.wmin_key.fill_(-1)  # ~0ull: arm the running min; cdw_smc_resample re-arms it after every iteration
@@ -217,13 +242,20 @@ class ParticleEnsemble:
             flags = _lib.CDW_FLAG_ULA
         prm = langevin.as_struct(flags)
         o = outputs or {}
+        use_cache = self.static_cache and not track_works and langevin.n_steps > 0
+        if use_cache and not self.cache_valid:
+            self.seed_static_cache(lam_row, langevin.kT)
+            c, n = self.cur, 1 - self.cur
+        cache = _lib.static_cache(self.fs[c], self.us[c], self.fs[n], self.us[n]) if use_cache else None
         anc = self.anc if self.pending_gather else None
-        _lib.check(self.lib.cdw_smc_propagate(
+        _lib.check(self.lib.cdw_smc_propagate_cached(
             self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.pos[n]), _lib.ptr(self.vel[n]), self.P,
             _lib.ptr(anc), _lib.ptr(self.aux[c]), _lib.ptr(self.cum), _lib.ptr(self.label[c]), _lib.ptr(lam_row), C.byref(prm),
             C.c_uint64(seed), C.c_uint64(self.iteration * max(langevin.n_steps, 1)), C.c_int64(self.gid0), _lib.ptr(self.inc), _lib.ptr(self.W),
             _lib.ptr(self.aux[n]), _lib.ptr(self.label[n]), _lib.ptr(o.get("u_first")), _lib.ptr(o.get("u_last")), _lib.ptr(o.get("shadow")),
-            _lib.ptr(o.get("proposal")), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), _lib.current_stream()), "cdw_smc_propagate")
+            _lib.ptr(o.get("proposal")), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), C.byref(cache) if cache is not None else None,
+            _lib.current_stream()), "cdw_smc_propagate_cached")
+        self.cache_valid = use_cache
         self.cur = n
         self.pending_gather = False
 
@@ -266,11 +298,11 @@ class SMCEngine:
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5,
                  always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None, record_works_every=None,
-                 proposal="baoab"):
+                 proposal="baoab", static_cache=True):
         if proposal not in ("baoab", "ula"):
             raise ValueError("proposal must be 'baoab' (MCMC move, openmm/integrators.py:19-465) or 'ula' (Euler-Maruyama, :666-888)")
         self.proposal = proposal
-        self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history)
+        self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history, static_cache=static_cache)
         self.system = self.ensemble.system
         self.langevin = langevin or LangevinParameters()
         self.parameter_sequence = list(parameter_sequence)

@@ -111,7 +111,7 @@ class ShardedSMCEngine:
         self._opened = []
         self._bufs = {name: [_IpcBuffer(self.lib, shape, dt) for _ in range(2)]
                       for name, shape, dt in (("pos", (Pl, A, 4), torch.float32), ("vel", (Pl, A, 4), torch.float32), ("aux", (Pl,), torch.float64),
-                                              ("label", (Pl,), torch.int32))}
+                                              ("label", (Pl,), torch.int32), ("fs", (Pl, A, 4), torch.float32), ("us", (Pl,), torch.float64))}
         self.peer = {name: [self._exchange(name, b) for b in range(2)] for name in self._bufs}
         # ---- replicated weights (global length on every rank)
         self.W = torch.zeros(P, dtype=torch.float64, device=d)
@@ -166,10 +166,13 @@ class ShardedSMCEngine:
             self.local("vel").zero_()
         else:
             self.local("vel").copy_(velocities_local if torch.is_tensor(velocities_local) else positions_to_rows(velocities_local, self.device))
-        u0 = torch.empty(self.P_loc, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.cdw_reduced_potential(self.system.handle, _lib.ptr(self.local("pos")), self.P_loc, _lib.ptr(self.lam[0]), self.beta, _lib.ptr(u0),
-                                                 _lib.current_stream()), "cdw_reduced_potential")
-        self.local("aux").copy_(-u0)
+        # aux = -u_0(x_0) and the static-term cache of the initial rows, in one n_steps = 0 call (as SMCEngine does)
+        prm = _lib.LangevinParams(0.0, 0.0, float(self.langevin.kT), 1e-6, 0, 0)
+        cache = _lib.static_cache(None, None, self.local("fs"), self.local("us"))
+        _lib.check(self.lib.cdw_smc_propagate_cached(
+            self.system.handle, _lib.ptr(self.local("pos")), _lib.ptr(self.local("vel")), None, None, self.P_loc, None, None, None, None, _lib.ptr(self.lam[0]),
+            C.byref(prm), C.c_uint64(0), C.c_uint64(0), C.c_int64(self.first), None, None, _lib.ptr(self.local("aux")), None, None, None, None, None, None, None,
+            C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_cached")
         self.local("label").copy_(torch.arange(self.first, self.last, dtype=torch.int32, device=self.device))
         self.cum.zero_()
         self.anc.copy_(torch.arange(self.P, dtype=torch.int32, device=self.device))
@@ -184,12 +187,14 @@ class ShardedSMCEngine:
         flags = _lib.CDW_FLAG_ULA if self.proposal == "ula" else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
         prm = self.langevin.as_struct(flags)
         self.wmin_key.fill_(-1)
-        _lib.check(self.lib.cdw_smc_propagate_sharded(
+        cache = _lib.static_cache(None, None, self.local("fs", n), self.local("us", n), self.peer["fs"][c], self.peer["us"][c])
+        _lib.check(self.lib.cdw_smc_propagate_sharded_cached(
             self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]),
             self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), self.P_loc, _lib.ptr(self.anc[self.first:self.last]),
             _lib.ptr(self.cum[self.first:self.last]), _lib.ptr(self.lam[t]), C.byref(prm), C.c_uint64(self.seed),
             C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc), _lib.ptr(self.W_loc), _lib.ptr(self.local("aux", n)),
-            _lib.ptr(self.local("label", n)), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), _lib.current_stream()), "cdw_smc_propagate_sharded")
+            _lib.ptr(self.local("label", n)), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), C.byref(cache), _lib.current_stream()),
+            "cdw_smc_propagate_sharded_cached")
         self.cur = n
 
     def finish_iteration(self, t):

@@ -184,6 +184,32 @@ CDW_API int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const 
                       double* u_first_out, double* u_last_out, double* shadow_out, double* proposal_out,
                       int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream);
 
+/* Static-term cache.  Terms into which no global parameter enters (in a perses hybrid: every bond, angle, torsion and pair
+ * of the unchanged environment) have the same energy and forces at given coordinates for every lambda, and the closing
+ * evaluation of SMC iteration t (lambda_t, x_t) sees the same coordinates as the opening evaluation of iteration t + 1
+ * (lambda_{t+1}, x_t).  With a cache the kernel evaluates every force as a static pass plus a dynamic pass, writes the
+ * static part at the OUTPUT rows to (force_out, energy_out), and, when (force_in, energy_in) hold the static part at the
+ * INPUT rows, skips the static pass of the opening evaluation.  Rows are float4 [P][A] (kJ/mol/nm) and doubles [P]
+ * (kJ/mol), indexed like pos_in / pos_out (force_in through `anc`), and must be distinct buffers.
+ * Seed a cache with an n_steps = 0 call (force_in = NULL); calls with n_steps > 0 need force_in.  Results equal the
+ * uncached call up to summation order.  For the sharded form the inputs are per-rank base pointers. */
+typedef struct cdw_static_cache {
+    const float* force_in;
+    const double* energy_in;
+    float* force_out;
+    double* energy_out;
+    const float* const* peer_force_in;   /* cdw_smc_propagate_sharded_cached only */
+    const double* const* peer_energy_in;
+} cdw_static_cache;
+
+/* cdw_smc_propagate with a static-term cache (cache == NULL: identical to cdw_smc_propagate). */
+CDW_API int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
+                             int64_t n_particles, const int32_t* anc, const double* aux_in, const double* cum_in,
+                             const int32_t* label_in, const double* lambda, const cdw_langevin_params* params, uint64_t seed,
+                             uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out, int32_t* label_out,
+                             double* u_first_out, double* u_last_out, double* shadow_out, double* proposal_out,
+                             int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache, cdw_stream stream);
+
 /* Sharded form of cdw_smc_propagate for one rank of a multi-GPU run (particles are partitioned in contiguous blocks
  * of n_per_rank by global id; this rank propagates its n local slots, whose global ids start at gid0).
  * `anc[p]` is the GLOBAL ancestor of local slot p; its row, aux and label are read straight from the owning rank's
@@ -195,6 +221,14 @@ CDW_API int cdw_smc_propagate_sharded(const cdw_system* sys, const float* const*
                                       const double* cum_in, const double* lambda, const cdw_langevin_params* params, uint64_t seed,
                                       uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out,
                                       int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key, cdw_stream stream);
+
+CDW_API int cdw_smc_propagate_sharded_cached(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel,
+                                             const double* const* peer_aux, const int32_t* const* peer_label, int32_t n_ranks,
+                                             int64_t n_per_rank, float* pos_out, float* vel_out, int64_t n_particles, const int32_t* anc,
+                                             const double* cum_in, const double* lambda, const cdw_langevin_params* params, uint64_t seed,
+                                             uint64_t step0, int64_t gid0, double* inc_out, double* w_out, double* aux_out,
+                                             int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache,
+                                             cdw_stream stream);
 
 /* replaces: OMMBIP.apply (openmm/propagators.py:89-219) for a batch, in place.  Thin wrapper over the kernel above. */
 CDW_API int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_particles, const double* lambda,

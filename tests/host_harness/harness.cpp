@@ -40,7 +40,7 @@ extern "C" int hh_system_destroy(hh_system* s) {
 }
 
 extern "C" int hh_system_info(const hh_system* s, int* n_slots, int* n_clusters, size_t* smem_energy, size_t* smem_step) {
-    *n_slots = s->dev.n_slots;
+    *n_slots = s->dev.n_bonds_s + s->dev.n_angles_s + s->dev.n_torsions_s + s->dev.n_pairs_s + s->dev.n_ext_s;  // static terms
     *n_clusters = s->dev.n_clusters;
     *smem_energy = make_layout(s->dev, false, 32, 8).total;
     *smem_step = make_layout(s->dev, true, 32, 8).total;
@@ -95,6 +95,25 @@ extern "C" int hh_smc_propagate(const hh_system* s, const float* pos_in, const f
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
     if (a.flags & CDW_FLAG_ULA) { a.vel_in = nullptr; a.vel_out = nullptr; }  // as cdw_smc_propagate does
+    return run(s, a, true);
+}
+
+// the same with a static-term cache (cdw_smc_propagate_cached): fs/us rows in and out
+extern "C" int hh_smc_propagate_cached(const hh_system* s, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out, int64_t n,
+                                       const int32_t* anc, const double* aux_in, const double* cum_in, const double* lambda,
+                                       const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
+                                       double* aux_out, double* u_first_out, double* u_last_out, double* proposal_out, int32_t* nan_flags,
+                                       const float* fs_in, const double* us_in, float* fs_out, double* us_out) {
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out;
+    a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.lambda = lambda;
+    a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
+    a.seed = seed; a.step0 = step0; a.gid0 = gid0;
+    a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
+    a.proposal_out = proposal_out; a.nan_flags = nan_flags;
+    if (a.flags & CDW_FLAG_ULA) { a.vel_in = nullptr; a.vel_out = nullptr; }
+    a.fs_out = (float4*)fs_out; a.us_out = us_out;
+    if (fs_in && a.n_steps > 0) { a.fs_in = (const float4*)fs_in; a.us_in = us_in; }
     return run(s, a, true);
 }
 
