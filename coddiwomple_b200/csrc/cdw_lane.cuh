@@ -535,6 +535,20 @@ CDW_HD const float4* row_ptr(const PropArgs& a, const float4* local, const float
     return peers[r] + (src - r * a.n_per_rank) * A;
 }
 
+// (x, y, z) of one float4 row element -> three shared-memory columns
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void cdw_copy3(float* arr, int base, const float* g) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(arr + base);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * kR), "l"(g + 1) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8u * kR), "l"(g + 2) : "memory");
+}
+__device__ __forceinline__ void cdw_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+inline void cdw_copy3(float* arr, int base, const float* g) { arr[base] = g[0]; arr[base + kR] = g[1]; arr[base + 2 * kR] = g[2]; }
+inline void cdw_copy_wait() {}
+#endif
+
 // CTA-cooperative, coalesced load of `count` rows starting at particle p0 into the [element][replica] layout.
 // Row r comes from particle anc[p0 + r] when anc != NULL: this load IS the resampling gather (resamplers.py:123-129).
 CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* smem, const Layout& L, int sw, long long p0, int count, bool with_v) {
@@ -547,23 +561,24 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
             for (int r = tid; r < count; r += nt) SRC[r] = a.anc ? (long long)a.anc[p0 + r] : p0 + r;
         }
     }
+    // The rows are gathered (latency, not bandwidth, is the cost): on the device every component goes global -> shared
+    // with a 4-byte cp.async (LDGSTS), no register staging, so ALL of a thread's loads are in flight at once; one
+    // wait_all before the CTA barrier.
     CDW_CTA_THREADS(tid, nt) {
+        float* Fc = (float*)(smem + L.f);
+        const bool with_f = with_v && a.fs_in != nullptr;
         for (int idx = tid; idx < count * A; idx += nt) {
             const int r = idx / A, at = idx - r * A;
             const long long src = with_v ? SRC[r] : p0 + r;
             const int b = CDW_BASE_R(at, r);
-            const float4 q = row_ptr(a, a.pos_in, a.peer_pos, src, A)[at];  // NVLink load when the ancestor lives on a peer
-            X[b] = q.x; X[b + kR] = q.y; X[b + 2 * kR] = q.z;
+            cdw_copy3(X, b, (const float*)(row_ptr(a, a.pos_in, a.peer_pos, src, A) + at));  // NVLink load when the ancestor lives on a peer
             if (with_v) {
-                const float4 w = a.vel_in ? row_ptr(a, a.vel_in, a.peer_vel, src, A)[at] : make_float4(0.f, 0.f, 0.f, 0.f);
-                V[b] = w.x; V[b + kR] = w.y; V[b + 2 * kR] = w.z;
-                if (a.fs_in) {  // static forces of the ancestor's coordinates -> force copy 0
-                    float* Fc = (float*)(smem + L.f);
-                    const float4 g = row_ptr(a, a.fs_in, a.peer_fs, src, A)[at];
-                    Fc[b] = g.x; Fc[b + kR] = g.y; Fc[b + 2 * kR] = g.z;
-                }
+                if (a.vel_in) cdw_copy3(V, b, (const float*)(row_ptr(a, a.vel_in, a.peer_vel, src, A) + at));
+                else { V[b] = 0.f; V[b + kR] = 0.f; V[b + 2 * kR] = 0.f; }
             }
+            if (with_f) cdw_copy3(Fc, b, (const float*)(row_ptr(a, a.fs_in, a.peer_fs, src, A) + at));  // static forces of the ancestor's coordinates -> copy 0
         }
+        cdw_copy_wait();
     }
 }
 
