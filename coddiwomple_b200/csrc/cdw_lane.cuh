@@ -208,13 +208,14 @@ CDW_HD void build_tables(const SysDev& s, const Tables& T, const double* lam_g, 
         for (int q = tid; q < s.n_pairs; q += nt) {
             EffPair p;
             p.i = s.pair_atoms[2 * q]; p.j = s.pair_atoms[2 * q + 1]; p.flags = 0; p.pad = 0;
-            p.qqC = p.sig = p.eps = 0.0;
-            p.sc_sig = p.sc_eps = p.sc_rlj = p.sc_F = p.sc_U = 0.0;
+            double sig = 0.0, eps = 0.0;
+            p.qqC = 0.0;
+            p.sc_sig2 = p.sc_eps4 = p.sc_rlj = p.sc_F = p.sc_U = 0.0;
             int nbk = s.pair_nb[q];
             if (nbk == -2) {
                 p.qqC = CDW_ONE_4PI_EPS0 * (T.nbeff[3 * p.i] * T.nbeff[3 * p.j]);
-                p.sig = 0.5 * (T.nbeff[3 * p.i + 1] + T.nbeff[3 * p.j + 1]);
-                p.eps = sqrt(T.nbeff[3 * p.i + 2] * T.nbeff[3 * p.j + 2]);
+                sig = 0.5 * (T.nbeff[3 * p.i + 1] + T.nbeff[3 * p.j + 1]);
+                eps = sqrt(T.nbeff[3 * p.i + 2] * T.nbeff[3 * p.j + 2]);
                 p.flags |= CDW_PAIR_NB;
             } else if (nbk >= 0) {
                 double qq = s.exc_par[3 * nbk], sg = s.exc_par[3 * nbk + 1], ep = s.exc_par[3 * nbk + 2];
@@ -222,10 +223,11 @@ CDW_HD void build_tables(const SysDev& s, const Tables& T, const double* lam_g, 
                     double l = lam[s.exc_off_slot[o]];
                     qq += l * s.exc_off_par[3 * o]; sg += l * s.exc_off_par[3 * o + 1]; ep += l * s.exc_off_par[3 * o + 2];
                 }
-                p.qqC = CDW_ONE_4PI_EPS0 * qq; p.sig = sg; p.eps = ep;
+                p.qqC = CDW_ONE_4PI_EPS0 * qq; sig = sg; eps = ep;
                 p.flags |= CDW_PAIR_NB;
             }
-            if (p.eps != 0.0) p.flags |= CDW_PAIR_LJ;
+            if (eps != 0.0) p.flags |= CDW_PAIR_LJ;
+            p.sig2 = sig * sig; p.eps4 = 4.0 * eps;
             int cls = s.pair_sc_class[q];
             if (cls >= 0)
                 lower_softcore(p, cls, s.pair_sc_par + 4 * q, lam[s.slot_core], lam[s.slot_insert], lam[s.slot_delete], lam[s.slot_alpha]);

@@ -64,8 +64,9 @@ struct EffTorsion {
 #define CDW_PAIR_CAP 8  // r_LJ > 0: quadratic cap is reachable
 struct EffPair {
     int i, j, flags, pad;
-    double qqC, sig, eps;                        // 138.935456*qq, sigma, epsilon
-    double sc_sig, sc_eps, sc_rlj, sc_F, sc_U;   // soft-core sigma, epsilon, r_LJ, Force, U_sterics_cut
+    // as the pair loop consumes them (prepare_pair): sigma^2 and 4 epsilon instead of sigma and epsilon
+    double qqC, sig2, eps4;                        // 138.935456*qq, sigma^2, 4 epsilon
+    double sc_sig2, sc_eps4, sc_rlj, sc_F, sc_U;   // soft-core sigma^2, 4 epsilon, r_LJ, Force, U_sterics_cut
 };
 struct EffExt {
     int atom, pad;
@@ -81,8 +82,8 @@ CDW_HD void lower_softcore(EffPair& e, int cls, const double* par /*sigA,epsA,si
     double ldep = cls == 0 ? 0.0 : (cls == 1 ? (1.0 - l_insert) : l_delete);
     double eps = (1.0 - ls) * par[1] + ls * par[3];
     double sig = (1.0 - ls) * par[0] + ls * par[2];
-    e.sc_sig = sig;
-    e.sc_eps = eps;
+    e.sc_sig2 = sig * sig;
+    e.sc_eps4 = 4.0 * eps;
     e.flags |= CDW_PAIR_SC;
     double s2 = sig * sig, s6 = s2 * s2 * s2;
     double arg = (26.0 / 7.0) * s6 * ldep;
@@ -172,19 +173,24 @@ CDW_HD double pair_term(const EffPair& p, d3 d, double& g) {
     const double ir = CDW_RSQRT(r2);
     const double ir2 = ir * ir;
     const double ec = p.qqC * ir;                                   // 138.935456 qq / r
-    const double s2 = p.sig * p.sig * ir2, s6 = s2 * s2 * s2;       // plain LJ (NonbondedForce)
-    const double t2 = p.sc_sig * p.sc_sig * ir2, x6 = t2 * t2 * t2; // soft-core LJ outside r_LJ
-    double e = ec + 4.0 * p.eps * s6 * (s6 - 1.0);
-    double esc = 4.0 * p.sc_eps * x6 * (x6 - 1.0);
-    if (F) g = (-ec + 4.0 * p.eps * (6.0 * s6 - 12.0 * s6 * s6)) * ir2;
-    double gsc = F ? 4.0 * p.sc_eps * (6.0 * x6 - 12.0 * x6 * x6) * ir2 : 0.0;
+    const double s2 = p.sig2 * ir2, s6 = s2 * s2 * s2;              // plain LJ (NonbondedForce): 4 eps (s6^2 - s6)
+    const double t2 = p.sc_sig2 * ir2, x6 = t2 * t2 * t2;           // soft-core LJ outside r_LJ
+    const double e = fma(p.eps4, fma(s6, s6, -s6), ec);
+    double esc = p.sc_eps4 * fma(x6, x6, -x6);
+    double gsc = 0.0;
+    if (F) {                                                        // g = -(dU/dr)/r: 4 eps (6 s6 - 12 s6^2) / r^2 - ec / r^2
+        g = fma(p.eps4, s6 * fma(-12.0, s6, 6.0), -ec);
+        gsc = p.sc_eps4 * (x6 * fma(-12.0, x6, 6.0));
+    }
     // quadratic cap inside r_LJ (r_LJ = 0 when the pair is not softened: never taken); selects, not branches, so that
     // two pairs can be evaluated in one basic block (instruction-level parallelism)
-    const double dr = r2 * ir - p.sc_rlj;
+    const double dr = fma(r2, ir, -p.sc_rlj);
     const bool cap = dr < 0.0;
-    esc = cap ? p.sc_F * (0.5 * dr * dr - dr) + p.sc_U : esc;
-    gsc = cap ? p.sc_F * (dr - 1.0) * ir : gsc;
-    if (F) g += gsc;
+    esc = cap ? fma(p.sc_F, dr * fma(0.5, dr, -1.0), p.sc_U) : esc;  // F (dr^2 / 2 - dr) + U_cut
+    if (F) {
+        const double gcap = p.sc_F * (dr - 1.0) * (r2 * ir);        // expressed per r^2 like the other two: (F (dr - 1) / r) r^2
+        g = (g + (cap ? gcap : gsc)) * ir2;
+    }
     return e + esc;
 }
 
