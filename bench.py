@@ -271,9 +271,13 @@ def run_gpu(args):
     for t in range(1, eng.T):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.propagate(t)
-        e1.record()
-        eng.finish_iteration(t)
+        if world == 1:
+            eng.step(t)          # ONE launch: the propagate kernel with the in-launch resample block (cdw_smc_iteration)
+            e1.record()
+        else:
+            eng.propagate(t)
+            e1.record()
+            eng.finish_iteration(t)
         evs.append((e0, e1))
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
@@ -292,13 +296,14 @@ def run_gpu(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "particles_per_gpu": P, "parallelism": (f"particles sharded over {world} GPUs; all-gather of W + peer-mapped gather-on-load" if world > 1 else "single GPU"), "n_lambda": N_LAMBDA, "atoms": spec.n_atoms, "resampler": "multinomial@nESS<=0.5",
-                           "step": "one full anneal = 99 SMC iterations", "l2": "flushed between anneals by a 256 MiB write", "terms": spec.counts()},
+                           "step": "one full anneal = 99 SMC iterations (single GPU: one kernel launch each)", "l2": "flushed between anneals by a 256 MiB write", "terms": spec.counts()},
                 "anneals_per_s": 1e3 / float(np.mean(ms)), "free_energy_kT": fe, "resampled_iterations": len(eng.resampled_iterations()),
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": float(np.mean(ms_e2e)), "h2d_bytes_per_step": int(x0_pinned.numel() * 4),
                         "d2h_bytes_per_step": int(cum_host.numel() * 8), "api": "SMCEngine.anneal(pinned host rows) + cumulative works to host", "cuda_graph": use_graph},
-                # both timed loops; single GPU: K1 + (propagate, fused resample) per iteration + final gather; sharded: K1 + (propagate,
-                # weight_update, fused resample or its 7-kernel form above 24576 particles) per iteration + final peer gather
-                "gpu_launches": int(args.steps * 2 * (1 + (2 if world == 1 else (3 if P * world <= 24576 else 9)) * (N_LAMBDA - 1) + 1)),
+                # both timed loops; single GPU: seed + ONE launch per iteration (propagate with the in-launch resample block) + final
+                # gather; sharded: seed + (propagate, weight_update, fused resample or its 7-kernel form above 24576 particles) per
+                # iteration + final peer gather
+                "gpu_launches": int(args.steps * 2 * (1 + (1 if world == 1 else (3 if P * world <= 24576 else 9)) * (N_LAMBDA - 1) + 1)),
                 "roofline": {"bound": "fp64", "kernel": "smc_propagate_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                              "avg_launch_ms": k_ms, "share_of_step": share,

@@ -106,6 +106,9 @@ _SIGNATURES = {
                                     C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cdw_smc_propagate_cached": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64,
                                            C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), _P]),
+    "cdw_smc_iteration": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64, C.c_int64,
+                                    _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), C.c_int, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P,
+                                    C.c_size_t, _P]),
     "cdw_smc_propagate_sharded_cached": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams),
                                                    C.c_uint64, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), _P]),
     "cdw_smc_propagate_sharded": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64,

@@ -109,9 +109,15 @@ struct Tables {  // pointers into the CTA-shared tables
     int* cl_start; int* cons_atoms; double* cons_d2; int* cl_coef_start; double* cl_coef;
 };
 
+struct CtaSignal {  // shared memory, one per CTA
+    unsigned long long min_key;  // running min of the order-preserving keys of this CTA's weights
+    unsigned int warps_done, n_warps;
+};
+
 struct LaneMem {  // this thread's view of its replica's columns
     float* x; float* v; float* f; float* r0;
     long long* src; int* bad;
+    struct CtaSignal* sig;  // in-launch resampling: where this CTA collects "my weights are final" (NULL otherwise)
     int rid;           // this replica's column (0 .. kR-1)
     int T, tl, sw;     // team size, lane within the team, bank rotation (32 / T, 0 on the host)
     unsigned mask;     // lanes of this warp whose replica is valid
@@ -133,6 +139,7 @@ CDW_HD LaneMem lane_pointers(const Layout& L, unsigned char* smem, int T, int ti
     M.src = (long long*)(smem + L.src); M.bad = (int*)(smem + L.bad);
     M.T = T; M.rid = tid / T; M.tl = tid - M.rid * T; M.sw = kR > 1 ? 32 / T : 0;
     M.mask = 0xffffffffu;
+    M.sig = nullptr;
     return M;
 }
 
@@ -528,6 +535,7 @@ struct PropArgs {
     // then they are evaluated) and at the OUTPUT rows.  Indexed like pos_in / pos_out (input through the ancestor).
     const float4* fs_in; const double* us_in; float4* fs_out; double* us_out;
     const float4* const* peer_fs; const double* const* peer_us;
+    ResampleArgs rs;  // rs.enabled: the last CTA of the launch resamples as soon as every weight is final (cdw_smc_iteration)
 };
 
 // where row `src` (a global particle id when the run is sharded) lives
@@ -615,6 +623,28 @@ CDW_HD void cta_store_rows(const SysDev& s, const PropArgs& a, unsigned char* sm
     }
 }
 
+// In-launch resampling: a warp whose weights are final records their min in the CTA's CtaSignal; the last warp of the
+// CTA folds it into the global running min and bumps the launch-wide counter the resample CTA is waiting on.
+CDW_HD void lane_signal_weights(const LaneMem& M, const PropArgs& a, unsigned long long key) {
+#if defined(__CUDA_ARCH__)
+    if (!M.sig) return;
+    __threadfence();  // this lane's inc_out / w_out stores, before the counter moves
+    if (key != ~0ull) atomicMin(&M.sig->min_key, key);
+    __syncwarp(M.mask);
+    if ((threadIdx.x & 31) == 0) {  // valid lanes are a prefix of the warp: lane 0 is in every non-empty warp
+        const unsigned int before = atomicAdd(&M.sig->warps_done, 1u);
+        if (before + 1 == M.sig->n_warps) {
+            __threadfence();
+            atomicMin(a.wmin_key, atomicMin(&M.sig->min_key, ~0ull));
+            __threadfence();
+            atomicAdd(a.rs.done, 1u);
+        }
+    }
+#else
+    (void)M; (void)a; (void)key;
+#endif
+}
+
 // K4 body (+ first half of K2) for the replica already staged in this team's column.
 // Returns the order-preserving key of W[p] (for the running min).
 //
@@ -645,6 +675,16 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
     const int n_body = (ula ? 3 : 6) + (split ? 1 : 0);               // V R O R [ES] E(D) V | U [ES] E(D) B
     const int e_slot = ula ? 1 : 4;                                   // slot of the (first) evaluation inside a step
     double U = 0.0, Us = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0;
+    double aux = 0.0, inc = 0.0, w = 0.0;
+    int label = (int)src;
+    if (a.peer_pos) {
+        const long long r = src / a.n_per_rank, l = src - r * a.n_per_rank;
+        if (a.peer_aux) aux = a.peer_aux[r][l];
+        if (a.peer_label) label = a.peer_label[r][l];
+    } else {
+        if (a.aux_in) aux = a.aux_in[src];
+        if (a.label_in) label = a.label_in[src];
+    }
     if (cached_open) Us = a.peer_pos ? a.peer_us[src / a.n_per_rank][src % a.n_per_rank] : a.us_in[src];
     const int n_ops = n_open + n_body * a.n_steps;
     // op -1 (only with RANDOMIZE): Context.setVelocitiesToTemperature (propagators.py:137-138)
@@ -675,8 +715,20 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                 continue;
             }
             U = part == PART_DYNAMIC ? Us + e : e;
-            if (op < n_open) u_first = U;
-            else if (track) shadow += pending + U;  // closes the second R of the step: (KE + U_new) - (KE_old + U_mid)
+            if (op < n_open) {
+                u_first = U;
+                if (!ula) {
+                    // MCMC move: work_inc = u_t(x_{t-1}) - u_{t-1}(x_{t-1}) (distribution_factories.py:98-131) is final as soon as the
+                    // opening evaluation is: publish W now, so that the resampling can overlap the integration
+                    inc = u_first * inv_kT + aux;
+                    w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
+                    if (tl == 0) {
+                        if (a.inc_out) a.inc_out[p] = inc;
+                        if (a.w_out) a.w_out[p] = w;
+                    }
+                    lane_signal_weights(M, a, tl == 0 ? ordered_key(w) : ~0ull);
+                }
+            } else if (track) shadow += pending + U;  // closes the second R of the step: (KE + U_new) - (KE_old + U_mid)
             continue;
         }
         if (kind == OP_U || kind == OP_B) {
@@ -760,24 +812,16 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
     const double u_last = U;
     const double fin = ula ? u_last + proposal : u_last;
     const bool bad = a.n_steps > 0 && !(fin - fin == 0.0);  // NaN or inf
-    double aux = 0.0;
-    int label = (int)src;
-    if (a.peer_pos) {
-        const long long r = src / a.n_per_rank, l = src - r * a.n_per_rank;
-        if (a.peer_aux) aux = a.peer_aux[r][l];
-        if (a.peer_label) label = a.peer_label[r][l];
-    } else {
-        if (a.aux_in) aux = a.aux_in[src];
-        if (a.label_in) label = a.label_in[src];
+    if (ula) {
+        // Euler-Maruyama proposal: u_t(x_t) - u_{t-1}(x_{t-1}) + proposal work (distribution_factories.py:98-131); a reverted move is a
+        // rejected one (zero proposal work, state kept)
+        inc = (!bad ? u_last * inv_kT + proposal : u_first * inv_kT) + aux;
+        w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
     }
-    // MCMC move: work_inc = u_t(x_{t-1}) - u_{t-1}(x_{t-1}); Euler-Maruyama proposal: u_t(x_t) - u_{t-1}(x_{t-1}) + proposal work
-    // (distribution_factories.py:98-131); a reverted move is a rejected one (zero proposal work, state kept)
-    const double inc = (ula && !bad ? u_last * inv_kT + proposal : u_first * inv_kT) + aux;
-    const double w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
     if (tl == 0) {
         M.bad[rid] = bad ? 1 : 0;
-        if (a.inc_out) a.inc_out[p] = inc;
-        if (a.w_out) a.w_out[p] = w;
+        if (ula && a.inc_out) a.inc_out[p] = inc;
+        if (ula && a.w_out) a.w_out[p] = w;
         if (a.aux_out) a.aux_out[p] = -(bad ? u_first : u_last) * inv_kT;
         if (a.label_out) a.label_out[p] = label;
         if (a.u_first_out) a.u_first_out[p] = u_first * inv_kT;

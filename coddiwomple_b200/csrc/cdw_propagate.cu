@@ -13,6 +13,7 @@
 
 #include "cdw_common.h"
 #include "cdw_lane.cuh"
+#include "cdw_resample.cuh"
 
 namespace cdw {
 
@@ -85,8 +86,24 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long cta_min[MAXT / 32];
     __shared__ __align__(8) unsigned long long table_bar;
+    __shared__ CtaSignal cta_sig;
     const int T_ = sh.T, sw = 32 / T_;
     const Layout L = make_layout(s, true, kR, T_);
+    if (a.rs.enabled && blockIdx.x == gridDim.x - 1) {
+        // resample role (cdw_smc_iteration): wait until every main CTA has published its weights (they are final right after
+        // the opening evaluation), then do the whole second half of the SMC iteration while the others integrate.  All
+        // CTAs of the launch are co-resident (checked by the host), so the wait cannot starve anyone.
+        if (threadIdx.x == 0) {
+            while (atomicAdd(a.rs.done, 0u) < a.rs.n_main) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        resample_cta<MAXT>(a.rs, (unsigned long long*)smem, (int)(L.total / sizeof(unsigned long long)));
+        __syncthreads();
+        if (threadIdx.x == 0) *a.rs.done = 0u;
+        return;
+    }
+    const int n_main = (int)gridDim.x - (a.rs.enabled ? 1 : 0);
     const Tables T = table_pointers(L, smem);
     bool tables_in_flight = false;
     if (a.tables) {
@@ -97,10 +114,14 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
         build_tables(s, T, a.lambda, a.kT, true);
     }
     LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
+    if (a.rs.enabled) M.sig = &cta_sig;
     unsigned long long my_min = ~0ull;
-    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
+    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)n_main * kR) {
         const long long left = a.n - p0;
         const int count = left < kR ? (int)left : kR;
+        if (a.rs.enabled && threadIdx.x == 0) {  // published to the CTA by the barrier inside cta_load_rows
+            cta_sig.min_key = ~0ull; cta_sig.warps_done = 0u; cta_sig.n_warps = (unsigned)((count * T_ + 31) / 32);
+        }
         cta_load_rows(s, a, smem, L, sw, p0, count, true);
         if (tables_in_flight) {
             wait_tables(&table_bar);
@@ -123,7 +144,7 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     }
     if ((threadIdx.x & 31) == 0) cta_min[threadIdx.x >> 5] = my_min;
     __syncthreads();
-    if (a.wmin_key && threadIdx.x == 0) {
+    if (a.wmin_key && !a.rs.enabled && threadIdx.x == 0) {  // (with the resample role the min was published with the weights)
         unsigned long long m = cta_min[0];
         for (int w = 1; w < ((int)blockDim.x + 31) / 32; ++w) m = cta_min[w] < m ? cta_min[w] : m;
         if (m != ~0ull) atomicMin(a.wmin_key, m);
@@ -186,7 +207,14 @@ static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t 
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, nthr, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
     const long long need = (a.n + sh.R - 1) / sh.R, cap = (long long)sms * per_sm;
-    const int grid = (int)(need < cap ? need : cap);
+    int grid = (int)(need < cap ? need : cap);
+    // in-launch resampling needs every CTA co-resident (the resample CTA waits for the others), MCMC weights (final after
+    // the opening evaluation) and room for the statistics scratch in the CTA's shared memory
+    static const bool no_inline = getenv("CDW_NO_INLINE_RESAMPLE") != nullptr;
+    const bool fuse = a.rs.enabled && forces && !no_inline && !(a.flags & CDW_FLAG_ULA) && need + 1 <= cap && a.n < (1ll << 30) &&
+                      L.total >= sizeof(unsigned long long) * kVirtualThreads;
+    a.rs.enabled = fuse ? 1 : 0;
+    if (fuse) { grid = (int)need + 1; a.rs.n_main = (unsigned)need; }
     if (forces && small && dense)
         smc_propagate_kernel<128, 4><<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
     else if (forces && small)
@@ -304,6 +332,46 @@ extern "C" int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
     if (int rc = apply_cache(a, cache, false, anc != nullptr)) return rc;
     return launch(sys, a, true, (cudaStream_t)stream);
+}
+
+extern "C" int cdw_smc_iteration(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out, int64_t n,
+                                 const int32_t* anc_in, const double* aux_in, double* cum, const int32_t* label_in, const double* lambda,
+                                 const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
+                                 double* aux_out, int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache, int kind,
+                                 double floor_threshold, uint64_t resample_seed, uint64_t stream_id, double* stats, int32_t* anc_out, uint64_t* cdf,
+                                 double* uniforms, void* workspace, size_t workspace_bytes, cdw_stream stream) {
+    CDW_REQUIRE(sys && prm && n > 0, "null argument or n == 0");
+    CDW_REQUIRE(pos_in && pos_out && cum && w_out && wmin_key && stats && anc_out && cdf && uniforms && workspace, "null argument");
+    CDW_REQUIRE(kind == CDW_RESAMPLE_MULTINOMIAL || kind == CDW_RESAMPLE_SYSTEMATIC, "unknown resampler kind");
+    CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
+    CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+    CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
+    CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
+    CDW_REQUIRE(!(anc_in && (pos_in == pos_out || (vel_in && vel_in == vel_out))), "gather-on-load needs distinct in/out buffers");
+    const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;
+    CDW_REQUIRE(ula || vel_in || (prm->flags & CDW_FLAG_RANDOMIZE_VELOCITIES) || prm->n_steps == 0, "velocities required unless they are randomized");
+    CDW_REQUIRE(ula || prm->n_steps == 0 || vel_out, "vel_out is required when positions are written");
+    CDW_REQUIRE(!(prm->flags & CDW_FLAG_TRACK_WORKS), "cdw_smc_iteration does not track shadow / proposal works: use cdw_smc_propagate");
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos_in; a.vel_in = ula ? nullptr : (const float4*)vel_in; a.pos_out = (float4*)pos_out;
+    a.vel_out = ula ? nullptr : (float4*)vel_out;
+    a.n = n; a.anc = anc_in; a.aux_in = aux_in; a.cum_in = cum; a.label_in = label_in; a.lambda = lambda;
+    a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
+    a.seed = seed; a.step0 = step0; a.gid0 = gid0;
+    a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
+    if (int rc = apply_cache(a, cache, false, anc_in != nullptr)) return rc;
+    int b = 0;
+    while ((1ll << b) < n) ++b;
+    ResampleArgs& r = a.rs;
+    r.enabled = 1;  // a request: launch() keeps it only if the whole grid is co-resident
+    r.kind = kind; r.n = (int)n; r.s1 = 61 - b; r.threshold = floor_threshold; r.w = w_out; r.wmin_key = (unsigned long long*)wmin_key;
+    r.seed = resample_seed; r.stream_id = stream_id; r.stats = stats; r.cum_in = cum; r.cum_out = cum; r.anc = anc_out; r.uniforms_out = uniforms;
+    r.cdf_spill = (unsigned long long*)cdf;
+    r.done = (unsigned int*)workspace + 2 * 4;  // header word 4 of the weight workspace (zero at rest)
+    if (int rc = launch(sys, a, true, (cudaStream_t)stream)) return rc;
+    if (a.rs.enabled) return CDW_OK;
+    return cdw_smc_resample(kind, w_out, n, floor_threshold, wmin_key, resample_seed, stream_id, stats, cum, cum, anc_out, cdf, uniforms, workspace,
+                            workspace_bytes, stream);
 }
 
 extern "C" int cdw_smc_propagate_sharded(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,

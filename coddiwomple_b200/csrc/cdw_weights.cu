@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "cdw_common.h"
+#include "cdw_resample.cuh"
 
 namespace cdw {
 
@@ -49,12 +50,6 @@ __host__ __device__ inline WsView ws_view(void* ws, long long n) {
     return v;
 }
 
-__device__ __forceinline__ double pow2(int e) { return bits_to_double((uint64_t)(e + 1023) << 52); }
-
-__device__ __forceinline__ unsigned long long quantise(double w, double wmin, double scale) {
-    double e = det_exp(CDW_ADD(wmin, -w));
-    return __double2ull_rn(CDW_MUL(e, scale));
-}
 
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce(T v, Op op, T* sh /*[kBlock/32]*/) {
@@ -415,116 +410,9 @@ __global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double*
 constexpr int kFusedThreads = 1024;
 constexpr int kFusedMax = 24576;  // cdf in shared memory: 192 KB (covers 2 x 10^4 particles sharded over two GPUs)
 
-__device__ __forceinline__ double philox_uniform53(unsigned long long seed, unsigned long long stream_id, long long i) {
-    u4 c;
-    const long long pair = i >> 1;
-    c.x = (uint32_t)pair; c.y = (uint32_t)((unsigned long long)pair >> 32); c.z = (uint32_t)stream_id; c.w = 0x5EEDu;
-    const u4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const unsigned long long bits = (i & 1) ? ((((unsigned long long)r.z << 32) | r.w) >> 11) : ((((unsigned long long)r.x << 32) | r.y) >> 11);
-    return (double)bits * 1.1102230246251565e-16;
-}
-
-__global__ void __launch_bounds__(kFusedThreads) fused_resample_kernel(int kind, const double* __restrict__ w, int n, double threshold,
-                                                                      unsigned long long* wmin_key, unsigned long long seed, unsigned long long stream_id,
-                                                                      double* stats, const double* cum_in, double* cum_out, int* __restrict__ anc,
-                                                                      double* __restrict__ uniforms_out, int s1) {
-    extern __shared__ __align__(16) unsigned long long cdf[];  // [n]
-    __shared__ double shd[kFusedThreads / 32];
-    __shared__ unsigned long long shu[kFusedThreads / 32];
-    __shared__ unsigned long long carry_sh;
-    __shared__ double bc[4];
-    __shared__ int shift_sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double wmin = ordered_key_inverse(*wmin_key);
-    const double scale1 = pow2(s1);
-    double se = 0.0, se2 = 0.0;
-    unsigned long long t1 = 0;
-    for (int i = tid; i < n; i += kFusedThreads) {
-        const double e = det_exp(CDW_ADD(wmin, -w[i]));
-        se += e;
-        se2 += e * e;
-        t1 += __double2ull_rn(CDW_MUL(e, scale1));
-    }
-    se = block_reduce(se, [](double a, double b) { return a + b; }, shd);
-    se2 = block_reduce(se2, [](double a, double b) { return a + b; }, shd);
-    t1 = block_reduce(t1, [](unsigned long long a, unsigned long long b) { return a + b; }, shu);
-    if (tid == 0) {
-        const int bitlen = 64 - __clzll((long long)t1);
-        int shift = 60 - bitlen;
-        shift = shift < 0 ? 0 : shift;
-        shift_sh = s1 + shift;
-        const double ness = (se * se) / ((double)n * se2);
-        const double mean = wmin - log(se) + log((double)n);
-        const double res = (threshold < 0.0 || ness <= threshold) ? 1.0 : 0.0;
-        stats[CDW_STAT_WMIN] = wmin; stats[CDW_STAT_SUM_E] = se; stats[CDW_STAT_SUM_E2] = se2; stats[CDW_STAT_NESS] = ness;
-        stats[CDW_STAT_MEAN] = mean; stats[CDW_STAT_RESAMPLE] = res; stats[CDW_STAT_TOTAL] = 0.0; stats[CDW_STAT_NNAN] = 0.0;
-        bc[0] = res; bc[1] = mean;
-        carry_sh = 0;
-        *wmin_key = ~0ull;  // re-arm the running min for the next propagate launch
-    }
-    __syncthreads();
-    const bool resample = bc[0] != 0.0;
-    const double mean = bc[1];
-    if (!resample) {
-        for (int i = tid; i < n; i += kFusedThreads) {
-            anc[i] = i;
-            if (cum_out) cum_out[i] = w[i];  // null update (resamplers.py:136-156)
-        }
-        return;
-    }
-    const double scale = pow2(shift_sh);
-    // integer cdf in shared memory: chunks of 1024 consecutive elements, block-wide inclusive scan + running carry
-    for (int base = 0; base < n; base += kFusedThreads) {
-        const int i = base + tid;
-        const unsigned long long v = i < n ? quantise(w[i], wmin, scale) : 0ull;
-        unsigned long long incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) shu[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const unsigned long long t = shu[lane];
-            unsigned long long sc = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long u = __shfl_up_sync(0xffffffffu, sc, o);
-                if (lane >= o) sc += u;
-            }
-            shu[lane] = sc - t;
-        }
-        __syncthreads();
-        const unsigned long long mine = carry_sh + shu[warp] + incl;
-        if (i < n) cdf[i] = mine;
-        __syncthreads();
-        if (tid == kFusedThreads - 1) carry_sh = mine;
-        __syncthreads();
-    }
-    const unsigned long long total = carry_sh;
-    if (tid == 0) stats[CDW_STAT_TOTAL] = (double)total;
-    const double u0 = kind == CDW_RESAMPLE_SYSTEMATIC ? philox_uniform53(seed, stream_id, 0) : 0.0;
-    if (tid == 0 && uniforms_out && kind == CDW_RESAMPLE_SYSTEMATIC) uniforms_out[0] = u0;
-    for (int i = tid; i < n; i += kFusedThreads) {
-        double u;
-        if (kind == CDW_RESAMPLE_SYSTEMATIC) u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
-        else {
-            u = philox_uniform53(seed, stream_id, i);
-            if (uniforms_out) uniforms_out[i] = u;
-        }
-        const unsigned long long target = fixed_target(u, total);
-        int lo = 0, hi = n - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cdf[mid] > target) hi = mid; else lo = mid + 1;
-        }
-        anc[i] = lo;
-        if (cum_out) {
-            const double c = cum_in ? cum_in[i] : 0.0;
-            cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
-        }
-    }
+__global__ void __launch_bounds__(kFusedThreads) fused_resample_kernel(ResampleArgs r) {
+    extern __shared__ __align__(16) unsigned long long cdf[];  // [max(n, 1024)]: the whole cdf stays in shared memory
+    resample_cta<kFusedThreads>(r, cdf, r.n < kVirtualThreads ? kVirtualThreads : r.n);
 }
 
 // ------------------------------------------------------------------------------------------------ K3b: gather
@@ -698,8 +586,11 @@ extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double flo
             CDW_CUDA(cudaFuncSetAttribute((const void*)fused_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kFusedMax)));
             attr_set = true;
         }
-        fused_resample_kernel<<<1, kFusedThreads, sizeof(unsigned long long) * (size_t)n, st>>>(kind, w, (int)n, floor_threshold, (unsigned long long*)wmin_key, seed,
-                                                                                                  stream_id, stats, cum_in, cum_out, anc_out, uniforms, 61 - b);
+        ResampleArgs r = {};
+        r.kind = kind; r.n = (int)n; r.s1 = 61 - b; r.threshold = floor_threshold; r.w = w; r.wmin_key = (unsigned long long*)wmin_key;
+        r.seed = seed; r.stream_id = stream_id; r.stats = stats; r.cum_in = cum_in; r.cum_out = cum_out; r.anc = anc_out; r.uniforms_out = uniforms;
+        const size_t entries = n < kVirtualThreads ? (size_t)kVirtualThreads : (size_t)n;
+        fused_resample_kernel<<<1, kFusedThreads, sizeof(unsigned long long) * entries, st>>>(r);
         CDW_CUDA(cudaGetLastError());
         return CDW_OK;
     }

@@ -259,6 +259,30 @@ class ParticleEnsemble:
         self.cur = n
         self.pending_gather = False
 
+    def iterate(self, lam_row, langevin, seed, stats_row, kind, floor_threshold, resample_seed, stream_id, randomize_velocities=False, ula=False):
+        """One whole SMC iteration in one call (include/cdw.h: cdw_smc_iteration): propagate_and_weigh + resample_fused.
+        For MCMC moves on a batch that fits the GPU at once this is a single kernel launch in which one extra thread block
+        resamples while the others are still integrating."""
+        self.iteration += 1
+        flags = _lib.CDW_FLAG_ULA if ula else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0)
+        prm = langevin.as_struct(flags)
+        use_cache = self.static_cache and langevin.n_steps > 0
+        if use_cache and not self.cache_valid:
+            self.seed_static_cache(lam_row, langevin.kT)
+        c, n = self.cur, 1 - self.cur
+        cache = _lib.static_cache(self.fs[c], self.us[c], self.fs[n], self.us[n]) if use_cache else None
+        anc = self.anc if self.pending_gather else None
+        _lib.check(self.lib.cdw_smc_iteration(
+            self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.pos[n]), _lib.ptr(self.vel[n]), self.P, _lib.ptr(anc),
+            _lib.ptr(self.aux[c]), _lib.ptr(self.cum), _lib.ptr(self.label[c]), _lib.ptr(lam_row), C.byref(prm), C.c_uint64(seed),
+            C.c_uint64(self.iteration * max(langevin.n_steps, 1)), C.c_int64(self.gid0), _lib.ptr(self.inc), _lib.ptr(self.W), _lib.ptr(self.aux[n]),
+            _lib.ptr(self.label[n]), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), C.byref(cache) if cache is not None else None, int(kind),
+            float(floor_threshold), C.c_uint64(resample_seed), C.c_uint64(stream_id), _lib.ptr(stats_row), _lib.ptr(self.anc), _lib.ptr(self.cdf),
+            _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_smc_iteration")
+        self.cache_valid = use_cache
+        self.cur = n
+        self.pending_gather = True
+
     def resample_fused(self, stats_row, kind, floor_threshold, seed, stream_id):
         """K2 second half + K3a (+ uniforms, + re-arming the running min) in one call: cdw_smc_resample."""
         _lib.check(self.lib.cdw_smc_resample(int(kind), _lib.ptr(self.W), self.P, float(floor_threshold), _lib.ptr(self.wmin_key), C.c_uint64(seed),
@@ -342,8 +366,11 @@ class SMCEngine:
 
     def finish_iteration(self, t):
         """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + search, cum update."""
+        self.ensemble.resample_fused(self.stats[t], self.kind, self.threshold, self.resample_seed, t)
+        self._after_iteration(t)
+
+    def _after_iteration(self, t):
         e = self.ensemble
-        e.resample_fused(self.stats[t], self.kind, self.threshold, self.resample_seed, t)
         if self.record_works_every and t in self._work_rows:
             self._works[self._work_rows.index(t) + 1].copy_(e.cum)
         n_u = e.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
@@ -351,9 +378,10 @@ class SMCEngine:
             e.history.append(dict(t=t, inc=e.inc.clone(), W=e.W.clone(), cum=e.cum.clone(), anc=e.anc.clone(), uniforms=e.uniforms[:n_u].clone()))
 
     def step(self, t):
-        """Iteration t of the reference loop (openmm/coddiwomple.py:314-328)."""
-        self.propagate(t)
-        self.finish_iteration(t)
+        """Iteration t of the reference loop (openmm/coddiwomple.py:314-328): one cdw_smc_iteration call."""
+        self.ensemble.iterate(self.lam[t], self.langevin, self.seed, self.stats[t], self.kind, self.threshold, self.resample_seed, t,
+                              randomize_velocities=(t == 1), ula=(self.proposal == "ula"))
+        self._after_iteration(t)
 
     def run(self):
         for t in range(1, self.T):

@@ -210,6 +210,23 @@ CDW_API int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_in,
                              double* u_first_out, double* u_last_out, double* shadow_out, double* proposal_out,
                              int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache, cdw_stream stream);
 
+/* One whole SMC iteration of the reference loop (openmm/coddiwomple.py:314-328): cdw_smc_propagate_cached followed by
+ * cdw_smc_resample on its weights, with `cum` updated in place and the new ancestors in anc_out (anc_in, the ancestors
+ * still to be applied to the input rows, may be the same buffer or NULL).  For MCMC moves the incremental work is final
+ * right after the opening evaluation; when the whole batch fits the GPU at once the library therefore adds ONE thread
+ * block to the propagate launch that waits for the weights and resamples while the other blocks are still integrating:
+ * the iteration is a single kernel launch and the resampling costs no time.  Otherwise (Euler-Maruyama proposal, batches
+ * of several waves) the two kernels are launched back to back.  Results are identical either way.  `workspace` as for
+ * cdw_weight_stats (zero-initialised once); w_out, wmin_key (armed with ~0 before the first call), stats, cdf, uniforms
+ * are required. */
+CDW_API int cdw_smc_iteration(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
+                              int64_t n_particles, const int32_t* anc_in, const double* aux_in, double* cum, const int32_t* label_in,
+                              const double* lambda, const cdw_langevin_params* params, uint64_t seed, uint64_t step0, int64_t gid0,
+                              double* inc_out, double* w_out, double* aux_out, int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key,
+                              const cdw_static_cache* cache, int kind, double floor_threshold, uint64_t resample_seed, uint64_t stream_id,
+                              double* stats, int32_t* anc_out, uint64_t* cdf, double* uniforms, void* workspace, size_t workspace_bytes,
+                              cdw_stream stream);
+
 /* Sharded form of cdw_smc_propagate for one rank of a multi-GPU run (particles are partitioned in contiguous blocks
  * of n_per_rank by global id; this rank propagates its n local slots, whose global ids start at gid0).
  * `anc[p]` is the GLOBAL ancestor of local slot p; its row, aux and label are read straight from the owning rank's

@@ -354,3 +354,29 @@ def test_config2_full_size_graph_replay_equals_eager_loop():
     assert len(eager.resampled_iterations()) >= 1
     labels = eager.ensemble.labels.cpu().numpy()
     assert labels.min() >= 0 and labels.max() < P
+
+
+@pytest.mark.parametrize("kind,P", [("multinomial", 3000), ("systematic", 10000), ("multinomial", 12001)])
+def test_one_launch_iteration_equals_two_launches(kind, P):
+    """cdw_smc_iteration resamples inside the propagate launch (one extra thread block that waits for the weights);
+    every output is bitwise what cdw_smc_propagate_cached + cdw_smc_resample give."""
+    from coddiwomple_b200.engine import LangevinParameters
+    xml, _ = ts.alanine_dipeptide_shaped_xml()
+    x0 = ts.alanine_dipeptide_shaped_ensemble(P, seed=4)
+    seq = ts.relative_alchemical_sequence(9)
+    runs = []
+    for one_launch in (True, False):
+        eng = _engine(xml, P, seq, langevin=LangevinParameters(), resampler=kind, seed=8, resample_seed=9, floor_threshold=0.9999)
+        eng.initialize(x0)
+        for t in range(1, eng.T):
+            if one_launch:
+                eng.step(t)
+            else:
+                eng.propagate(t)
+                eng.finish_iteration(t)
+        e = eng.ensemble
+        e.materialize()
+        runs.append([v.cpu().numpy().copy() for v in (e.cum, eng.stats, e.anc, e.pos[e.cur], e.vel[e.cur], e.aux[e.cur], e.label[e.cur], e.inc, e.W)])
+        assert len(eng.resampled_iterations()) >= 2
+    for a, b in zip(*runs):
+        np.testing.assert_array_equal(a, b)
