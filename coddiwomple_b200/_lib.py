@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get("CDW_LIB") or os.path.join(HERE, "libcdw_b200.so")  # 
 CDW_FLAG_RANDOMIZE_VELOCITIES = 1
 CDW_FLAG_TRACK_WORKS = 2
 CDW_FLAG_ULA = 4
+CDW_FLAG_PHASE_OPEN = 8
+CDW_FLAG_PHASE_REST = 16
 CDW_RESAMPLE_MULTINOMIAL = 0
 CDW_RESAMPLE_SYSTEMATIC = 1
 STAT_WMIN, STAT_SUM_E, STAT_SUM_E2, STAT_NESS, STAT_MEAN, STAT_RESAMPLE, STAT_TOTAL, STAT_NNAN = range(8)
@@ -45,15 +47,16 @@ class LangevinParams(C.Structure):
 class StaticCache(C.Structure):
     """struct cdw_static_cache (include/cdw.h): static-term forces / energies at the input and output rows."""
     _fields_ = [("force_in", C.c_void_p), ("energy_in", C.c_void_p), ("force_out", C.c_void_p), ("energy_out", C.c_void_p),
-                ("peer_force_in", C.c_void_p), ("peer_energy_in", C.c_void_p)]
+                ("peer_force_in", C.c_void_p), ("peer_energy_in", C.c_void_p), ("force_open", C.c_void_p), ("u_open", C.c_void_p)]
 
 
 def _addr(t):
     return None if t is None else (t.data_ptr() if hasattr(t, "data_ptr") else int(t))
 
 
-def static_cache(force_in, energy_in, force_out, energy_out, peer_force_in=None, peer_energy_in=None):
-    return StaticCache(_addr(force_in), _addr(energy_in), _addr(force_out), _addr(energy_out), _addr(peer_force_in), _addr(peer_energy_in))
+def static_cache(force_in, energy_in, force_out, energy_out, peer_force_in=None, peer_energy_in=None, force_open=None, u_open=None):
+    return StaticCache(_addr(force_in), _addr(energy_in), _addr(force_out), _addr(energy_out), _addr(peer_force_in), _addr(peer_energy_in),
+                       _addr(force_open), _addr(u_open))
 
 
 def make_desc(spec):

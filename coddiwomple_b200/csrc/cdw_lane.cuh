@@ -535,6 +535,9 @@ struct PropArgs {
     // then they are evaluated) and at the OUTPUT rows.  Indexed like pos_in / pos_out (input through the ancestor).
     const float4* fs_in; const double* us_in; float4* fs_out; double* us_out;
     const float4* const* peer_fs; const double* const* peer_us;
+    // split launches (CDW_FLAG_PHASE_OPEN / CDW_FLAG_PHASE_REST): the opening evaluation's total forces and energy, handed from
+    // the first launch to the second through HBM, indexed by the LOCAL slot (they are already gathered)
+    float4* f_open; double* u_open;
     ResampleArgs rs;  // rs.enabled: the last CTA of the launch resamples as soon as every weight is final (cdw_smc_iteration)
 };
 
@@ -576,7 +579,8 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
     // wait_all before the CTA barrier.
     CDW_CTA_THREADS(tid, nt) {
         float* Fc = (float*)(smem + L.f);
-        const bool with_f = with_v && a.fs_in != nullptr;
+        const bool rest = with_v && (a.flags & CDW_FLAG_PHASE_REST) != 0;   // the opening evaluation's forces come from the first launch
+        const bool with_f = with_v && a.fs_in != nullptr && !rest;
         for (int idx = tid; idx < count * A; idx += nt) {
             const int r = idx / A, at = idx - r * A;
             const long long src = with_v ? SRC[r] : p0 + r;
@@ -587,6 +591,7 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
                 else { V[b] = 0.f; V[b + kR] = 0.f; V[b + 2 * kR] = 0.f; }
             }
             if (with_f) cdw_copy3(Fc, b, (const float*)(row_ptr(a, a.fs_in, a.peer_fs, src, A) + at));  // static forces of the ancestor's coordinates -> copy 0
+            if (rest) cdw_copy3(Fc, b, (const float*)(a.f_open + (p0 + r) * A + at));
         }
         cdw_copy_wait();
     }
@@ -686,10 +691,15 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         if (a.label_in) label = a.label_in[src];
     }
     if (cached_open) Us = a.peer_pos ? a.peer_us[src / a.n_per_rank][src % a.n_per_rank] : a.us_in[src];
-    const int n_ops = n_open + n_body * a.n_steps;
+    // split launches: PHASE_OPEN stops after the opening evaluation (weights, total forces and energy out); PHASE_REST
+    // resumes behind it with those forces preloaded in force copy 0
+    const bool phase_open = (a.flags & CDW_FLAG_PHASE_OPEN) != 0, phase_rest = (a.flags & CDW_FLAG_PHASE_REST) != 0;
+    const int n_ops = phase_open ? n_open : n_open + n_body * a.n_steps;
+    if (phase_rest) U = u_first = a.u_open[p];
     // op -1 (only with RANDOMIZE): Context.setVelocitiesToTemperature (propagators.py:137-138)
-    for (int op = (!ula && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0; op < n_ops; ++op) {
+    for (int op = (!ula && !phase_open && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0; op < n_ops; ++op) {
         int kind, slot = 0, st = 0, part = PART_ALL;
+        if (phase_rest && op >= 0 && op < n_open) continue;
         if (op < 0) kind = OP_MB;
         else if (op < n_open) {
             kind = OP_E;
@@ -808,6 +818,14 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                 U = U_mid;
             } else pending = ke_after - (ke_before + U);                         // second R: U here is U_mid; closed by the next E
         }
+    }
+    if (phase_open) {  // hand the opening evaluation over to the PHASE_REST launch
+        for (int at = tl; at < A; at += T_) {
+            const int b = CDW_BASE(at);
+            a.f_open[p * A + at] = make_float4(M.f[b], M.f[b + kR], M.f[b + 2 * kR], 0.f);
+        }
+        if (tl == 0) a.u_open[p] = u_first;
+        return ordered_key(w);
     }
     const double u_last = U;
     const double fin = ula ? u_last + proposal : u_last;

@@ -367,7 +367,8 @@ struct ResampleArgs {
     const double* cum_in; double* cum_out;
     int* anc;                // [n] out
     double* uniforms_out;    // [n] (multinomial) / [1] (systematic), may be NULL
-    unsigned long long* cdf_spill;  // [n] global: cdf entries that do not fit the CTA's shared memory
+    unsigned long long* cdf_spill;  // [n] global: the cdf (slice-local inclusive prefixes)
+    void* ws;                // weight workspace (cdw_weight_workspace_bytes): scratch of the cooperating CTAs
     unsigned int* done;      // in-launch use: CTAs whose weights are final
     unsigned int n_main;     // ... out of this many
 };

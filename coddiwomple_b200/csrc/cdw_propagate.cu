@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     __shared__ CtaSignal cta_sig;
     const int T_ = sh.T, sw = 32 / T_;
     const Layout L = make_layout(s, true, kR, T_);
-    if (a.rs.enabled && blockIdx.x == gridDim.x - 1) {
-        // resample role (cdw_smc_iteration): wait until every main CTA has published its weights (they are final right after
+    constexpr int kRoles = kVirtualThreads / MAXT;  // resample team: kRoles CTAs x MAXT threads = the 1024 virtual threads
+    if (a.rs.enabled && blockIdx.x >= gridDim.x - kRoles) {
+        // resample roles (cdw_smc_iteration): wait until every main CTA has published its weights (they are final right after
         // the opening evaluation), then do the whole second half of the SMC iteration while the others integrate.  All
         // CTAs of the launch are co-resident (checked by the host), so the wait cannot starve anyone.
         if (threadIdx.x == 0) {
@@ -98,12 +99,10 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
             __threadfence();
         }
         __syncthreads();
-        resample_cta<MAXT>(a.rs, (unsigned long long*)smem, (int)(L.total / sizeof(unsigned long long)));
-        __syncthreads();
-        if (threadIdx.x == 0) *a.rs.done = 0u;
+        resample_coop<MAXT>(a.rs, (int)(blockIdx.x - (gridDim.x - kRoles)), kRoles, (unsigned long long*)smem);
         return;
     }
-    const int n_main = (int)gridDim.x - (a.rs.enabled ? 1 : 0);
+    const int n_main = (int)gridDim.x - (a.rs.enabled ? kRoles : 0);
     const Tables T = table_pointers(L, smem);
     bool tables_in_flight = false;
     if (a.tables) {
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     }
     if ((threadIdx.x & 31) == 0) cta_min[threadIdx.x >> 5] = my_min;
     __syncthreads();
-    if (a.wmin_key && !a.rs.enabled && threadIdx.x == 0) {  // (with the resample role the min was published with the weights)
+    if (a.wmin_key && !a.rs.enabled && !(a.flags & CDW_FLAG_PHASE_REST) && threadIdx.x == 0) {  // (with the resample role the min was published with the weights)
         unsigned long long m = cta_min[0];
         for (int w = 1; w < ((int)blockDim.x + 31) / 32; ++w) m = cta_min[w] < m ? cta_min[w] : m;
         if (m != ~0ull) atomicMin(a.wmin_key, m);
@@ -211,10 +210,11 @@ static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t 
     // in-launch resampling needs every CTA co-resident (the resample CTA waits for the others), MCMC weights (final after
     // the opening evaluation) and room for the statistics scratch in the CTA's shared memory
     static const bool no_inline = getenv("CDW_NO_INLINE_RESAMPLE") != nullptr;
-    const bool fuse = a.rs.enabled && forces && !no_inline && !(a.flags & CDW_FLAG_ULA) && need + 1 <= cap && a.n < (1ll << 30) &&
-                      L.total >= sizeof(unsigned long long) * kVirtualThreads;
+    const int roles = kVirtualThreads / (small ? 128 : 256);
+    const bool fuse = a.rs.enabled && forces && !no_inline && !(a.flags & CDW_FLAG_ULA) && need + roles <= cap && a.n < (1ll << 30) &&
+                      L.total >= sizeof(unsigned long long) * 3 * kVirtualThreads;
     a.rs.enabled = fuse ? 1 : 0;
-    if (fuse) { grid = (int)need + 1; a.rs.n_main = (unsigned)need; }
+    if (fuse) { grid = (int)need + roles; a.rs.n_main = (unsigned)need; }
     if (forces && small && dense)
         smc_propagate_kernel<128, 4><<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
     else if (forces && small)
@@ -283,13 +283,22 @@ extern "C" int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_
 }
 
 static int apply_cache(PropArgs& a, const cdw_static_cache* c, bool sharded, bool gather) {
-    if (!c) return CDW_OK;
+    if (!c) {
+        CDW_REQUIRE(!(a.flags & (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST)), "split launches need a cdw_static_cache");
+        return CDW_OK;
+    }
     CDW_REQUIRE(c->force_out && c->energy_out, "cdw_static_cache: force_out and energy_out are required");
     CDW_REQUIRE(!(a.flags & CDW_FLAG_TRACK_WORKS), "cdw_static_cache cannot be combined with CDW_FLAG_TRACK_WORKS");
     const bool have_in = sharded ? (c->peer_force_in && c->peer_energy_in) : (c->force_in && c->energy_in);
     CDW_REQUIRE(have_in || a.n_steps == 0, "cdw_static_cache: seed the cache with an n_steps = 0 call before stepping");
     CDW_REQUIRE(!(gather && have_in && !sharded && c->force_in == c->force_out), "cdw_static_cache: gather-on-load needs distinct in/out rows");
     a.fs_out = (float4*)c->force_out; a.us_out = c->energy_out;
+    if (a.flags & (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST)) {
+        CDW_REQUIRE(c->force_open && c->u_open, "cdw_static_cache: split launches need force_open and u_open");
+        CDW_REQUIRE(!(a.flags & CDW_FLAG_ULA) && a.n_steps > 0 && have_in, "split launches: MCMC moves with n_steps > 0 and a seeded cache only");
+        CDW_REQUIRE((a.flags & (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST)) != (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST), "choose one phase");
+        a.f_open = (float4*)c->force_open; a.u_open = c->u_open;
+    }
     if (have_in && a.n_steps > 0) {
         if (sharded) { a.peer_fs = (const float4* const*)c->peer_force_in; a.peer_us = c->peer_energy_in; a.fs_in = (const float4*)1; a.us_in = (const double*)1; }
         else { a.fs_in = (const float4*)c->force_in; a.us_in = c->energy_in; }
@@ -366,7 +375,7 @@ extern "C" int cdw_smc_iteration(const cdw_system* sys, const float* pos_in, con
     r.enabled = 1;  // a request: launch() keeps it only if the whole grid is co-resident
     r.kind = kind; r.n = (int)n; r.s1 = 61 - b; r.threshold = floor_threshold; r.w = w_out; r.wmin_key = (unsigned long long*)wmin_key;
     r.seed = resample_seed; r.stream_id = stream_id; r.stats = stats; r.cum_in = cum; r.cum_out = cum; r.anc = anc_out; r.uniforms_out = uniforms;
-    r.cdf_spill = (unsigned long long*)cdf;
+    r.cdf_spill = (unsigned long long*)cdf; r.ws = workspace;
     r.done = (unsigned int*)workspace + 2 * 4;  // header word 4 of the weight workspace (zero at rest)
     if (int rc = launch(sys, a, true, (cudaStream_t)stream)) return rc;
     if (a.rs.enabled) return CDW_OK;
@@ -391,15 +400,16 @@ extern "C" int cdw_smc_propagate_sharded_cached(const cdw_system* sys, const flo
     CDW_REQUIRE(sys && prm && n >= 0, "null argument");
     if (n == 0) return CDW_OK;
     const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;
-    CDW_REQUIRE(peer_pos && pos_out && anc && n_ranks > 0 && n_per_rank > 0 && (ula || (peer_vel && vel_out)), "null argument");
+    const bool open_only = (prm->flags & CDW_FLAG_PHASE_OPEN) != 0;  // the opening launch of a split call writes no rows
+    CDW_REQUIRE(peer_pos && anc && n_ranks > 0 && n_per_rank > 0 && (open_only || (pos_out && (ula || (peer_vel && vel_out)))), "null argument");
     CDW_REQUIRE(!(ula && (prm->flags & CDW_FLAG_TRACK_WORKS)), "CDW_FLAG_TRACK_WORKS does not apply to the Euler-Maruyama proposal");
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     PropArgs a = {};
     a.peer_pos = (const float4* const*)peer_pos; a.peer_vel = (const float4* const*)peer_vel; a.peer_aux = peer_aux; a.peer_label = peer_label;
     a.n_per_rank = n_per_rank;
-    a.vel_in = ula ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
-    a.pos_out = (float4*)pos_out; a.vel_out = ula ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
+    a.vel_in = ula || open_only ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
+    a.pos_out = open_only ? nullptr : (float4*)pos_out; a.vel_out = ula || open_only ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;

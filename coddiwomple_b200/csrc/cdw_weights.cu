@@ -403,16 +403,16 @@ __global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double*
 }
 
 // ------------------------------------------------------------------------------------------------ K2 + K3a fused (small n)
-// One CTA does everything after the propagate kernel for n <= kFusedMax particles: log-sum-exp / nESS / decision,
-// Philox uniforms, integer cdf (kept in shared memory), search, cum update, and re-arming of the running-min key.
+// One launch of 8 cooperating CTAs (cdw_resample.cuh) does everything after the propagate kernel for n <= kFusedMax
+// particles: log-sum-exp / nESS / decision, Philox uniforms, integer cdf, search, cum update, re-arming of the running-min key.
 // Same integer algorithm as the multi-kernel path => same ancestors bit for bit; for batches this small the
 // multi-kernel path is pure launch latency (7 launches for ~30 us of work at n = 1e4).
-constexpr int kFusedThreads = 1024;
+constexpr int kFusedThreads = 128;   // x 8 cooperating CTAs = the 1024 virtual threads of the canonical statistics order
 constexpr int kFusedMax = 24576;  // cdf in shared memory: 192 KB (covers 2 x 10^4 particles sharded over two GPUs)
 
 __global__ void __launch_bounds__(kFusedThreads) fused_resample_kernel(ResampleArgs r) {
-    extern __shared__ __align__(16) unsigned long long cdf[];  // [max(n, 1024)]: the whole cdf stays in shared memory
-    resample_cta<kFusedThreads>(r, cdf, r.n < kVirtualThreads ? kVirtualThreads : r.n);
+    extern __shared__ __align__(16) unsigned long long scratch[];  // 3 x 1024 words: the statistics tree of CTA 0
+    resample_coop<kFusedThreads>(r, (int)blockIdx.x, (int)gridDim.x, scratch);
 }
 
 // ------------------------------------------------------------------------------------------------ K3b: gather
@@ -581,16 +581,12 @@ extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double flo
     if (n <= kFusedMax && !no_fuse) {
         int b = 0;
         while ((1ll << b) < n) ++b;
-        static bool attr_set = false;
-        if (!attr_set) {
-            CDW_CUDA(cudaFuncSetAttribute((const void*)fused_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kFusedMax)));
-            attr_set = true;
-        }
         ResampleArgs r = {};
         r.kind = kind; r.n = (int)n; r.s1 = 61 - b; r.threshold = floor_threshold; r.w = w; r.wmin_key = (unsigned long long*)wmin_key;
         r.seed = seed; r.stream_id = stream_id; r.stats = stats; r.cum_in = cum_in; r.cum_out = cum_out; r.anc = anc_out; r.uniforms_out = uniforms;
-        const size_t entries = n < kVirtualThreads ? (size_t)kVirtualThreads : (size_t)n;
-        fused_resample_kernel<<<1, kFusedThreads, sizeof(unsigned long long) * entries, st>>>(r);
+        r.cdf_spill = (unsigned long long*)cdf_out; r.ws = workspace;
+        CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+        fused_resample_kernel<<<kVirtualThreads / kFusedThreads, kFusedThreads, sizeof(unsigned long long) * 3 * kVirtualThreads, st>>>(r);
         CDW_CUDA(cudaGetLastError());
         return CDW_OK;
     }

@@ -20,6 +20,7 @@ Noise is keyed by the global particle id and the weights are reduced identically
 is bit-identical to the same anneal on one GPU (tests/multi_gpu_check.py asserts exactly that).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -118,7 +119,16 @@ class ShardedSMCEngine:
         self.W_loc = torch.zeros(Pl, dtype=torch.float64, device=d)
         self.inc_loc = torch.zeros(Pl, dtype=torch.float64, device=d)
         self.cum = torch.zeros(P, dtype=torch.float64, device=d)
-        self.anc = torch.arange(P, dtype=torch.int32, device=d)
+        # ancestors are double-buffered: iteration t gathers through anc_bufs[(t - 1) % 2] while its resampling, which overlaps
+        # the integration, already writes anc_bufs[t % 2]
+        self.anc_bufs = [torch.arange(P, dtype=torch.int32, device=d) for _ in range(2)]
+        self.anc_cur = 0
+        self.f_open = torch.zeros(Pl, A, 4, dtype=torch.float32, device=d)   # hand-over between the two launches of a split iteration
+        self.u_open = torch.zeros(Pl, dtype=torch.float64, device=d)
+        self._token = torch.zeros(1, dtype=torch.float32, device=d)
+        self._side = torch.cuda.Stream(device=d)
+        # split every MCMC iteration so that the weight exchange + resampling overlap the integration (step_overlapped)
+        self.overlap = os.environ.get("CDW_SHARDED_OVERLAP", "0") == "1"
         self.nan_flags = torch.zeros(Pl, dtype=torch.int32, device=d)
         self.wmin_key = torch.zeros(1, dtype=torch.int64, device=d)
         self.scratch_key = torch.zeros(1, dtype=torch.int64, device=d)
@@ -175,41 +185,88 @@ class ShardedSMCEngine:
             C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_cached")
         self.local("label").copy_(torch.arange(self.first, self.last, dtype=torch.int32, device=self.device))
         self.cum.zero_()
+        self.anc_cur = 0
         self.anc.copy_(torch.arange(self.P, dtype=torch.int32, device=self.device))
         self.stats.zero_()
         self.iteration = 0
         self.pending_gather = False
         dist.barrier(group=self.group)  # every rank's initial rows are in place before any peer read
 
-    def propagate(self, t):
-        self.iteration = t
-        c, n = self.cur, 1 - self.cur
+    @property
+    def anc(self):
+        """Ancestors still to be applied to the current rows (global ids)."""
+        return self.anc_bufs[self.anc_cur]
+
+    def _launch(self, t, phase_flag, c, n, anc, with_outputs, with_key):
         flags = _lib.CDW_FLAG_ULA if self.proposal == "ula" else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
-        prm = self.langevin.as_struct(flags)
-        self.wmin_key.fill_(-1)
-        cache = _lib.static_cache(None, None, self.local("fs", n), self.local("us", n), self.peer["fs"][c], self.peer["us"][c])
+        prm = self.langevin.as_struct(flags | phase_flag)
+        cache = _lib.static_cache(None, None, self.local("fs", n), self.local("us", n), self.peer["fs"][c], self.peer["us"][c], self.f_open, self.u_open)
         _lib.check(self.lib.cdw_smc_propagate_sharded_cached(
             self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]),
-            self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), self.P_loc, _lib.ptr(self.anc[self.first:self.last]),
+            self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), self.P_loc, _lib.ptr(anc[self.first:self.last]),
             _lib.ptr(self.cum[self.first:self.last]), _lib.ptr(self.lam[t]), C.byref(prm), C.c_uint64(self.seed),
-            C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc), _lib.ptr(self.W_loc), _lib.ptr(self.local("aux", n)),
-            _lib.ptr(self.local("label", n)), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), C.byref(cache), _lib.current_stream()),
-            "cdw_smc_propagate_sharded_cached")
+            C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc) if with_key else None,
+            _lib.ptr(self.W_loc) if with_key else None, _lib.ptr(self.local("aux", n)) if with_outputs else None,
+            _lib.ptr(self.local("label", n)) if with_outputs else None, _lib.ptr(self.nan_flags) if with_outputs else None,
+            _lib.ptr(self.wmin_key) if with_key else None, C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_sharded_cached")
+
+    def propagate(self, t):
+        """The whole propagate call of iteration t (gather over peer memory, weights, integration) as one launch."""
+        self.iteration = t
+        c, n = self.cur, 1 - self.cur
+        self.wmin_key.fill_(-1)
+        self._launch(t, 0, c, n, self.anc, True, True)
         self.cur = n
 
-    def finish_iteration(self, t):
-        # C1: one all-gather of the 8-byte weights; also the ordering point for the peer reads of the next iteration
+    def _exchange_and_resample(self, t, anc_out):
+        # C1: one all-gather of the 8-byte weights
         dist.all_gather_into_tensor(self.W, self.W_loc, group=self.group)
         # every rank reduces the SAME vector in the SAME order: global min, log-sum-exp, nESS, decision
         self.scratch_key.fill_(-1)
         _lib.check(self.lib.cdw_weight_update(_lib.ptr(self.W), None, None, None, self.P, None, _lib.ptr(self.W_copy), _lib.ptr(self.scratch_key),
                                              _lib.current_stream()), "cdw_weight_update")
         _lib.check(self.lib.cdw_smc_resample(self.kind, _lib.ptr(self.W), self.P, self.threshold, _lib.ptr(self.scratch_key), C.c_uint64(self.resample_seed),
-                                            C.c_uint64(t), _lib.ptr(self.stats[t]), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(self.anc), _lib.ptr(self.cdf),
+                                            C.c_uint64(t), _lib.ptr(self.stats[t]), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(anc_out), _lib.ptr(self.cdf),
                                             _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_smc_resample")
+
+    def finish_iteration(self, t):
+        """Weight exchange + global resampling after an unsplit propagate; the all-gather is also the ordering point for the
+        peer reads of the next iteration."""
+        self._exchange_and_resample(t, self.anc_bufs[1 - self.anc_cur])
+        self.anc_cur = 1 - self.anc_cur
+        self.pending_gather = True
+
+    def step_overlapped(self, t):
+        """Iteration t as two launches (CDW_FLAG_PHASE_OPEN / _REST): the weights are final after the opening evaluation, so the
+        all-gather of W and the global resampling run on a side stream WHILE this rank integrates; a one-element all-reduce
+        after the integration is the cross-rank ordering point for the next iteration's peer reads."""
+        self.iteration = t
+        c, n = self.cur, 1 - self.cur
+        main = torch.cuda.current_stream()
+        anc_in, anc_out = self.anc_bufs[self.anc_cur], self.anc_bufs[1 - self.anc_cur]
+        self.wmin_key.fill_(-1)
+        self._launch(t, _lib.CDW_FLAG_PHASE_OPEN, c, n, anc_in, False, True)
+        opened = torch.cuda.Event()
+        opened.record(main)
+        self._side.wait_event(opened)
+        with torch.cuda.stream(self._side):
+            self._exchange_and_resample(t, anc_out)
+        self._launch(t, _lib.CDW_FLAG_PHASE_REST, c, n, anc_in, True, False)
+        integrated = torch.cuda.Event()
+        integrated.record(main)
+        self._side.wait_event(integrated)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self._token, group=self.group)   # every rank's rows of iteration t are in place
+            joined = torch.cuda.Event()
+            joined.record(self._side)
+        main.wait_event(joined)
+        self.cur = n
+        self.anc_cur = 1 - self.anc_cur
         self.pending_gather = True
 
     def step(self, t):
+        if self.overlap and self.proposal != "ula" and self.langevin.n_steps > 0:
+            return self.step_overlapped(t)
         self.propagate(t)
         self.finish_iteration(t)
 
@@ -253,7 +310,7 @@ class ShardedSMCEngine:
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             for t in range(1, self.T):
                 self.step(t)
-        self._graph_final = (self.cur, self.pending_gather, self.iteration)
+        self._graph_final = (self.cur, self.pending_gather, self.iteration, self.anc_cur)
         self.graph = g
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
@@ -263,7 +320,7 @@ class ShardedSMCEngine:
         self.initialize(positions_local, velocities_local)
         if self.graph is not None:
             self.graph.replay()
-            self.cur, self.pending_gather, self.iteration = self._graph_final
+            self.cur, self.pending_gather, self.iteration, self.anc_cur = self._graph_final
             self.materialize()
             return self
         return self.run()

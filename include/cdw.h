@@ -120,6 +120,13 @@ typedef struct cdw_langevin_params {
  *   inc = u_t(x_t) + aux + proposal_work   (distribution_factories.py:98-131; troubleshooting/csmc.py:174-191).
  * Velocities are not used (vel_in / vel_out may be NULL); gamma is ignored. */
 #define CDW_FLAG_ULA 4u
+/* Split launches of one MCMC propagate call (used by the sharded loop to overlap the weight exchange and the resampling
+ * with the integration): PHASE_OPEN gathers the rows, runs the opening evaluation only and writes inc_out / w_out (and the
+ * running min) plus the hand-over buffers cdw_static_cache.force_open / u_open; PHASE_REST gathers the rows again, takes
+ * the opening forces and energy from those buffers and does everything else (integration, closing evaluation, outputs).
+ * OPEN followed by REST equals one unsplit call bit for bit.  Both need a cdw_static_cache with force_open / u_open. */
+#define CDW_FLAG_PHASE_OPEN 8u
+#define CDW_FLAG_PHASE_REST 16u
 
 #define CDW_RESAMPLE_MULTINOMIAL 0
 #define CDW_RESAMPLE_SYSTEMATIC 1
@@ -200,6 +207,8 @@ typedef struct cdw_static_cache {
     double* energy_out;
     const float* const* peer_force_in;   /* cdw_smc_propagate_sharded_cached only */
     const double* const* peer_energy_in;
+    float* force_open;                   /* CDW_FLAG_PHASE_OPEN (out) / CDW_FLAG_PHASE_REST (in): [P][A][4] and [P], local slots */
+    double* u_open;
 } cdw_static_cache;
 
 /* cdw_smc_propagate with a static-term cache (cache == NULL: identical to cdw_smc_propagate). */

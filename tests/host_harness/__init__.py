@@ -92,7 +92,8 @@ class HostSystem:
         o["v"] = o["vel"][..., :3].astype(np.float64)
         return o
 
-    def smc_propagate_cached(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, cache=None):
+    def smc_propagate_cached(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, cache=None,
+                             handover=None):
         """cdw_smc_propagate_cached on the host: `cache` = (fs rows (P, A, 4) float32, us (P,)) at the input rows, or None.
         Returns the usual outputs plus out["cache"] at the output rows."""
         pos = self.rows(x)
@@ -108,9 +109,11 @@ class HostSystem:
         fs_in = None if cache is None else np.ascontiguousarray(cache[0], dtype=np.float32)
         us_in = None if cache is None else np.ascontiguousarray(cache[1], dtype=np.float64)
         fs_out, us_out = np.zeros_like(pos), np.zeros(P)
+        f_open, u_open = handover if handover is not None else (np.zeros_like(pos), np.zeros(P))
+        o["handover"] = (f_open, u_open)
         lib().hh_smc_propagate_cached(self.handle, _p(pos), _p(vel), _p(o["pos"]), _p(o["vel"]), C.c_int64(P), _p(anc), _p(aux), _p(cum), _p(lam), C.byref(prm),
                                       C.c_uint64(seed), C.c_uint64(step0), C.c_int64(gid0), _p(o["inc"]), _p(o["w"]), _p(o["aux"]), _p(o["u_first"]),
-                                      _p(o["u_last"]), _p(o["proposal"]), _p(o["nan"]), _p(fs_in), _p(us_in), _p(fs_out), _p(us_out))
+                                      _p(o["u_last"]), _p(o["proposal"]), _p(o["nan"]), _p(fs_in), _p(us_in), _p(fs_out), _p(us_out), _p(f_open), _p(u_open))
         o["x"] = o["pos"][..., :3].astype(np.float64)
         o["v"] = o["vel"][..., :3].astype(np.float64)
         o["cache"] = (fs_out, us_out)

@@ -103,7 +103,7 @@ extern "C" int hh_smc_propagate_cached(const hh_system* s, const float* pos_in, 
                                        const int32_t* anc, const double* aux_in, const double* cum_in, const double* lambda,
                                        const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
                                        double* aux_out, double* u_first_out, double* u_last_out, double* proposal_out, int32_t* nan_flags,
-                                       const float* fs_in, const double* us_in, float* fs_out, double* us_out) {
+                                       const float* fs_in, const double* us_in, float* fs_out, double* us_out, float* f_open, double* u_open) {
     PropArgs a = {};
     a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out;
     a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.lambda = lambda;
@@ -114,6 +114,8 @@ extern "C" int hh_smc_propagate_cached(const hh_system* s, const float* pos_in, 
     if (a.flags & CDW_FLAG_ULA) { a.vel_in = nullptr; a.vel_out = nullptr; }
     a.fs_out = (float4*)fs_out; a.us_out = us_out;
     if (fs_in && a.n_steps > 0) { a.fs_in = (const float4*)fs_in; a.us_in = us_in; }
+    a.f_open = (float4*)f_open; a.u_open = u_open;
+    if (a.flags & CDW_FLAG_PHASE_OPEN) { a.pos_out = nullptr; a.vel_out = nullptr; }
     return run(s, a, true);
 }
 

@@ -92,3 +92,26 @@ def test_nan_guard_keeps_the_ancestors_cache():
     np.testing.assert_array_equal(out["x"][1], X[1])
     np.testing.assert_array_equal(out["cache"][0][1], seed_out["cache"][0][1])
     assert out["cache"][1][1] == seed_out["cache"][1][1] or (np.isnan(out["cache"][1][1]) and np.isnan(seed_out["cache"][1][1]))
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_split_launch_equals_one_launch(flags):
+    """CDW_FLAG_PHASE_OPEN followed by CDW_FLAG_PHASE_REST (the sharded loop's way to overlap the weight exchange with the
+    integration) gives bit for bit what the unsplit call gives."""
+    o, spec, hs = _pair(system_xml("fluorobenzene"))
+    X = cache_frames()[:6].astype(np.float64)
+    P = X.shape[0]
+    V = np.random.RandomState(2).normal(0, 0.2, X.shape).astype(np.float32).astype(np.float64)
+    lam0, lam1 = (spec.lambda_vector(relative_lambdas(q)) for q in (0.2, 0.3))
+    seed_out = hs.smc_propagate_cached(X, V, lam0, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    anc = np.array([1, 1, 0, 5, 4, 2])
+    kw = dict(anc=anc, aux=-seed_out["u_first"], cum=np.arange(P) * 0.1, cache=seed_out["cache"])
+    full = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=flags, **kw)
+    first = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=flags | _lib.CDW_FLAG_PHASE_OPEN, **kw)
+    np.testing.assert_array_equal(first["inc"], full["inc"])
+    np.testing.assert_array_equal(first["w"], full["w"])
+    rest = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=flags | _lib.CDW_FLAG_PHASE_REST, handover=first["handover"], **kw)
+    for k in ("x", "v", "aux", "u_last", "nan"):
+        np.testing.assert_array_equal(rest[k], full[k])
+    np.testing.assert_array_equal(rest["cache"][0], full["cache"][0])
+    np.testing.assert_array_equal(rest["cache"][1], full["cache"][1])
