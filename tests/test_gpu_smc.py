@@ -380,3 +380,24 @@ def test_one_launch_iteration_equals_two_launches(kind, P):
         assert len(eng.resampled_iterations()) >= 2
     for a, b in zip(*runs):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("P", [1, 2, 5, 33])
+def test_tiny_ensembles_run_through_the_one_launch_iteration(P):
+    """Edge sizes: fewer particles than one warp team / one CTA; ancestors stay in range, a single particle keeps weight 1."""
+    frames = cache_frames()
+    x0 = frames[np.random.RandomState(9).randint(0, len(frames), P)]
+    seq = ts.relative_alchemical_sequence(5)
+    eng = _engine(system_xml("fluorobenzene"), P, seq, seed=3, resample_seed=4, always_resample=True, record_history=True)
+    eng.anneal(x0)
+    for h in eng.ensemble.history:
+        anc = h["anc"].cpu().numpy()
+        assert anc.min() >= 0 and anc.max() < P
+        ref = weights.resample_step(h["W"].cpu().numpy() - h["inc"].cpu().numpy(), h["inc"].cpu().numpy(), np.zeros(P), np.arange(P),
+                                    uniforms=h["uniforms"].cpu().numpy(), kind="multinomial", always=True)
+        np.testing.assert_array_equal(anc, ref["ancestors"])
+    assert np.isfinite(eng.free_energy())
+    stats = eng.stats.cpu().numpy()
+    assert np.all(stats[1:, _lib.STAT_NESS] > 0) and np.all(stats[1:, _lib.STAT_NESS] <= 1 + 1e-12)
+    if P == 1:
+        np.testing.assert_allclose(stats[1:, _lib.STAT_NESS], 1.0, rtol=1e-12)
