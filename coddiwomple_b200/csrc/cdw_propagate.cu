@@ -247,6 +247,12 @@ extern "C" int cdw_system_register_protocol(cdw_system* sys, const double* lambd
     CDW_REQUIRE(sys->dev.n_lambda > 0, "the system has no global parameters");
     const Layout L = make_layout(sys->dev, true, kR, 1);
     CDW_REQUIRE(L.x <= 200 * 1024, "table image too large");
+    if (sys->proto_tables && sys->proto_lambda == lambda_rows && sys->proto_rows == n_rows && sys->proto_kT == kT && sys->proto_stride == L.x) {
+        // same protocol array again: rebuild the images in place (the pointers captured graphs hold stay valid)
+        build_tables_kernel<<<n_rows, 128, L.x, (cudaStream_t)stream>>>(sys->dev, lambda_rows, kT, sys->proto_tables, L.x);
+        CDW_CUDA(cudaGetLastError());
+        return CDW_OK;
+    }
     cudaFree(sys->proto_tables);
     sys->proto_tables = nullptr; sys->proto_lambda = nullptr; sys->proto_rows = 0;
     unsigned char* buf = nullptr;

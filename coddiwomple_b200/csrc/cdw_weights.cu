@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kBlock) weight_stats_kernel(const double* __re
             sum_e2 += ((volatile double*)ws.part_e2)[b];
         }
         unsigned long long T1 = ((volatile unsigned long long*)ws.hdr)[WS_T1];
+        ws.hdr[WS_T1] = 0; ws.hdr[WS_TICKET] = 0;  // leave the accumulators at rest: the next call needs no memset
         int bitlen = 64 - __clzll((long long)T1);
         int shift = 60 - bitlen;
         shift = shift < 0 ? 0 : shift;
@@ -310,14 +311,28 @@ __device__ __forceinline__ long long hier_search(unsigned long long target, cons
     return jlo;
 }
 
+// cdw_smc_resample draws its own uniforms (Philox, keyed by slot) inside the search kernels and lets them re-arm the
+// running-min key: no separate uniforms / fill launches.
+struct SearchGen {
+    int gen;                              // 0: read `uniforms`; 1: generate (and store to uniforms_out if not NULL)
+    unsigned long long seed, stream_id;
+    double* uniforms_out;
+    unsigned long long* rearm_key;        // set to ~0 by the kernel (may be NULL)
+};
+
+__device__ __forceinline__ void search_rearm(const SearchGen& g) {
+    if (g.rearm_key && blockIdx.x == 0 && threadIdx.x == 0) *g.rearm_key = ~0ull;
+}
+
 // Multinomial (unsorted uniforms): one slot per thread, hierarchical search.
 __global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* __restrict__ w, const double* __restrict__ uniforms,
                                                         long long n, const double* __restrict__ stats, WsView ws,
                                                         const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
-                                                        double* __restrict__ cum_out, int* __restrict__ anc) {
+                                                        double* __restrict__ cum_out, int* __restrict__ anc, SearchGen g) {
     __shared__ unsigned long long top[kTop];
     const bool resample = stats[CDW_STAT_RESAMPLE] != 0.0;
     const double mean = stats[CDW_STAT_MEAN];
+    search_rearm(g);
     if (!resample) {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
             if (anc) anc[i] = (int)i;
@@ -326,10 +341,16 @@ __global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* 
         return;
     }
     const unsigned long long total = ws.hdr[WS_TOTAL];
-    const double u0 = kind == CDW_RESAMPLE_SYSTEMATIC ? uniforms[0] : 0.0;
+    const double u0 = kind == CDW_RESAMPLE_SYSTEMATIC ? (g.gen ? philox_uniform53(g.seed, g.stream_id, 0) : uniforms[0]) : 0.0;
+    if (g.gen && g.uniforms_out && kind == CDW_RESAMPLE_SYSTEMATIC && blockIdx.x == 0 && threadIdx.x == 0) g.uniforms_out[0] = u0;
     const TopTable t = load_top(ws.coarse, n, top);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double u = kind == CDW_RESAMPLE_SYSTEMATIC ? __ddiv_rn(__dadd_rn((double)i, u0), (double)n) : uniforms[i];
+        double u;
+        if (kind == CDW_RESAMPLE_SYSTEMATIC) u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
+        else if (g.gen) {
+            u = philox_uniform53(g.seed, g.stream_id, i);
+            if (g.uniforms_out) g.uniforms_out[i] = u;
+        } else u = uniforms[i];
         anc[i] = (int)hier_search(fixed_target(u, total), cdf, ws.coarse, top, t, n);
         if (cum_out) {
             const double c = cum_in ? cum_in[i] : 0.0;
@@ -348,10 +369,11 @@ constexpr int kSysWindow = 3072;
 __global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double* __restrict__ w, const double* __restrict__ uniforms, long long n,
                                                                    const double* __restrict__ stats, WsView ws,
                                                                    const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
-                                                                   double* __restrict__ cum_out, int* __restrict__ anc) {
+                                                                   double* __restrict__ cum_out, int* __restrict__ anc, SearchGen g) {
     __shared__ unsigned long long top[kTop];
     __shared__ unsigned long long win[kSysWindow];
     __shared__ long long bounds[2];
+    search_rearm(g);
     if (stats[CDW_STAT_RESAMPLE] == 0.0) {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
             if (anc) anc[i] = (int)i;
@@ -361,7 +383,8 @@ __global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double*
     }
     const double mean = stats[CDW_STAT_MEAN];
     const unsigned long long total = ws.hdr[WS_TOTAL];
-    const double u0 = uniforms[0];
+    const double u0 = g.gen ? philox_uniform53(g.seed, g.stream_id, 0) : uniforms[0];
+    if (g.gen && g.uniforms_out && blockIdx.x == 0 && threadIdx.x == 0) g.uniforms_out[0] = u0;
     const TopTable t = load_top(ws.coarse, n, top);
     const long long n_chunks = (n + kSysSlots - 1) / kSysSlots;
     for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -518,13 +541,14 @@ extern "C" int cdw_weight_update(const double* u_new, const double* aux, const d
     return CDW_OK;
 }
 
-extern "C" int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
-                                void* workspace, size_t workspace_bytes, cdw_stream stream) {
+static int weight_stats_launch(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats, void* workspace,
+                               size_t workspace_bytes, cdw_stream stream, bool clear_header) {
     CDW_REQUIRE(w && wmin_key && stats && workspace && n > 0, "null argument or n == 0");
     CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
     CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
     WsView ws = ws_view(workspace, n);
-    CDW_CUDA(cudaMemsetAsync(ws.hdr, 0, sizeof(unsigned long long) * WS_HEADER_WORDS, (cudaStream_t)stream));
+    // every kernel that uses the header leaves it at rest (zero); a caller-facing call clears it anyway
+    if (clear_header) CDW_CUDA(cudaMemsetAsync(ws.hdr, 0, sizeof(unsigned long long) * WS_HEADER_WORDS, (cudaStream_t)stream));
     int b = 0;
     while ((1ll << b) < n) ++b;  // ceil(log2 n)
     int grid = blocks_for(n, kBlock * 4, sm_count() * 8);
@@ -534,12 +558,17 @@ extern "C" int cdw_weight_stats(const double* w, int64_t n, double floor_thresho
     return CDW_OK;
 }
 
-extern "C" int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats, const double* cum_in,
-                                    double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace, size_t workspace_bytes,
-                                    cdw_stream stream) {
+extern "C" int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
+                                void* workspace, size_t workspace_bytes, cdw_stream stream) {
+    return weight_stats_launch(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream, true);
+}
+
+static int resample_indices_launch(int kind, const double* w, const double* uniforms, int64_t n, const double* stats, const double* cum_in,
+                                   double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace, size_t workspace_bytes,
+                                   cdw_stream stream, SearchGen gen) {
     CDW_REQUIRE(w && stats && anc_out && cdf_out && workspace && n > 0, "null argument or n == 0");
     CDW_REQUIRE(kind == CDW_RESAMPLE_MULTINOMIAL || kind == CDW_RESAMPLE_SYSTEMATIC, "unknown resampler kind");
-    CDW_REQUIRE(uniforms, "uniforms are required");
+    CDW_REQUIRE(uniforms || gen.gen, "uniforms are required");
     CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
     CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
     WsView ws = ws_view(workspace, n);
@@ -561,13 +590,21 @@ extern "C" int cdw_resample_indices(int kind, const double* w, const double* uni
     CDW_DBG("cdf_tile_scan_kernel")
     if (kind == CDW_RESAMPLE_SYSTEMATIC) {
         int grid_s = blocks_for(n, kSysSlots, sm_count() * 8);
-        search_systematic_kernel<<<grid_s, kBlock, 0, st>>>(w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
+        search_systematic_kernel<<<grid_s, kBlock, 0, st>>>(w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out, gen);
     } else {
         int grid_s = blocks_for(n, kBlock * 4, sm_count() * 8);
-        search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out);
+        search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out, gen);
     }
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
+}
+
+extern "C" int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats, const double* cum_in,
+                                    double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace, size_t workspace_bytes,
+                                    cdw_stream stream) {
+    CDW_REQUIRE(uniforms, "uniforms are required");
+    SearchGen none = {};
+    return resample_indices_launch(kind, w, uniforms, n, stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream, none);
 }
 
 extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double floor_threshold, uint64_t* wmin_key, uint64_t seed, uint64_t stream_id,
@@ -590,13 +627,12 @@ extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double flo
         CDW_CUDA(cudaGetLastError());
         return CDW_OK;
     }
-    int rc = cdw_weight_stats(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream);
+    // multi-kernel form: statistics, three scan kernels, search (which also draws the uniforms and re-arms the key): 5 launches
+    int rc = weight_stats_launch(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream, false);
     if (rc) return rc;
-    rc = cdw_philox_uniforms(seed, stream_id, kind == CDW_RESAMPLE_MULTINOMIAL ? n : 1, uniforms, stream);
-    if (rc) return rc;
-    rc = cdw_resample_indices(kind, w, uniforms, n, stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream);
-    if (rc) return rc;
-    return cdw_fill_u64(wmin_key, ~0ull, 1, stream);
+    SearchGen gen = {};
+    gen.gen = 1; gen.seed = seed; gen.stream_id = stream_id; gen.uniforms_out = uniforms; gen.rearm_key = (unsigned long long*)wmin_key;
+    return resample_indices_launch(kind, w, uniforms, n, stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream, gen);
 }
 
 extern "C" int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,

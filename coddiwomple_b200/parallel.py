@@ -187,6 +187,7 @@ class ShardedSMCEngine:
         self.cum.zero_()
         self.anc_cur = 0
         self.anc.copy_(torch.arange(self.P, dtype=torch.int32, device=self.device))
+        self.scratch_key.fill_(-1)
         self.stats.zero_()
         self.iteration = 0
         self.pending_gather = False
@@ -208,13 +209,12 @@ class ShardedSMCEngine:
             C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc) if with_key else None,
             _lib.ptr(self.W_loc) if with_key else None, _lib.ptr(self.local("aux", n)) if with_outputs else None,
             _lib.ptr(self.local("label", n)) if with_outputs else None, _lib.ptr(self.nan_flags) if with_outputs else None,
-            _lib.ptr(self.wmin_key) if with_key else None, C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_sharded_cached")
+            None, C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_sharded_cached")
 
     def propagate(self, t):
         """The whole propagate call of iteration t (gather over peer memory, weights, integration) as one launch."""
         self.iteration = t
         c, n = self.cur, 1 - self.cur
-        self.wmin_key.fill_(-1)
         self._launch(t, 0, c, n, self.anc, True, True)
         self.cur = n
 
@@ -222,7 +222,7 @@ class ShardedSMCEngine:
         # C1: one all-gather of the 8-byte weights
         dist.all_gather_into_tensor(self.W, self.W_loc, group=self.group)
         # every rank reduces the SAME vector in the SAME order: global min, log-sum-exp, nESS, decision
-        self.scratch_key.fill_(-1)
+        # (scratch_key is armed once in initialize(); cdw_smc_resample re-arms it after every use)
         _lib.check(self.lib.cdw_weight_update(_lib.ptr(self.W), None, None, None, self.P, None, _lib.ptr(self.W_copy), _lib.ptr(self.scratch_key),
                                              _lib.current_stream()), "cdw_weight_update")
         _lib.check(self.lib.cdw_smc_resample(self.kind, _lib.ptr(self.W), self.P, self.threshold, _lib.ptr(self.scratch_key), C.c_uint64(self.resample_seed),
@@ -244,7 +244,6 @@ class ShardedSMCEngine:
         c, n = self.cur, 1 - self.cur
         main = torch.cuda.current_stream()
         anc_in, anc_out = self.anc_bufs[self.anc_cur], self.anc_bufs[1 - self.anc_cur]
-        self.wmin_key.fill_(-1)
         self._launch(t, _lib.CDW_FLAG_PHASE_OPEN, c, n, anc_in, False, True)
         opened = torch.cuda.Event()
         opened.record(main)

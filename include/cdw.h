@@ -157,7 +157,8 @@ CDW_API int cdw_system_destroy(cdw_system* sys);
  * thread block (what OpenMMPDFState.set_parameters + apply_to_context cost the reference P times per iteration,
  * openmm/states.py:89-103).  Results are bit-identical either way.  The array must stay unchanged until
  * cdw_system_clear_protocol or the next registration; registering is not thread-safe against concurrent launches on
- * the same handle.  Enqueues on `stream`. */
+ * the same handle; a registration with a different array frees the previous images (CUDA graphs captured with them must
+ * be re-captured).  Enqueues on `stream`. */
 CDW_API int cdw_system_register_protocol(cdw_system* sys, const double* lambda_rows, int32_t n_rows, double kT, cdw_stream stream);
 CDW_API int cdw_system_clear_protocol(cdw_system* sys);
 CDW_API int cdw_system_n_atoms(const cdw_system* sys);

@@ -36,6 +36,7 @@ def main():
         seq = ts.relative_alchemical_sequence(T)
         lang = LangevinParameters(timestep=0.0005) if proposal == "ula" else LangevinParameters()
         sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
+        sharded.overlap = kind == "systematic" and P == 4096   # one case through the opt-in split-launch loop (CDW_FLAG_PHASE_OPEN / _REST)
         sharded.anneal(x0[sharded.first:sharded.last])
         if os.environ.get("CDW_CHECK_GRAPH") and proposal == "baoab" and kind == "multinomial" and thr != 0.5:
             eager_cum = sharded.cum.clone()
@@ -56,7 +57,7 @@ def main():
             e = single.ensemble
             same = (torch.equal(torch.cat(pos_parts), e.pos[e.cur]) and torch.equal(torch.cat(vel_parts), e.vel[e.cur]) and
                     torch.equal(torch.cat(lab_parts), e.labels) and torch.equal(sharded.cum, e.cum) and torch.equal(sharded.stats, single.stats))
-            print(f"[multi_gpu_check] world={world} {proposal} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
+            print(f"[multi_gpu_check] world={world} {proposal} {kind} thr={thr} P={P}{' (split launches)' if sharded.overlap else ''}: sharded == single-GPU bitwise: {same}; "
                   f"resampled at {sharded.resampled_iterations()} FE={sharded.free_energy():.6f}", flush=True)
             ok &= bool(same) and len(sharded.resampled_iterations()) > 0 or (thr == 0.5 and bool(same))
         sharded.close()
