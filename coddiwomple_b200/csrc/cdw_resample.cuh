@@ -1,11 +1,11 @@
-// cdw_resample.cuh — one-CTA resampling (second half of K2 + K3a) as a device function, shared by
-//   * fused_resample_kernel (cdw_weights.cu): a 1024-thread CTA launched between two propagate kernels, and
-//   * the resample role of smc_propagate_kernel (cdw_propagate.cu): one extra 128-thread CTA of the SAME launch that waits
-//     until every replica's opening evaluation has produced its weight and then resamples while the other CTAs are
+// cdw_resample.cuh — resampling (second half of K2 + K3a) by a team of cooperating CTAs, as a device function shared by
+//   * fused_resample_kernel (cdw_weights.cu): 8 CTAs x 128 threads launched between two propagate kernels, and
+//   * the resample roles of smc_propagate_kernel (cdw_propagate.cu): 8 extra 128-thread CTAs of the SAME launch that wait
+//     until every replica's opening evaluation has produced its weight and then resample while the other CTAs are
 //     still integrating — an SMC iteration is then ONE kernel launch.
 // Both produce the same bits: log-sum-exp statistics are accumulated by 1024 VIRTUAL threads (element i belongs to
-// virtual thread i mod 1024, summed in index order) and combined by a fixed binary tree, whatever the real thread count;
-// everything after that is integer arithmetic (exact in any order).
+// virtual thread i mod 1024, summed in index order; the team's 1024 real threads are exactly those) and combined by a
+// fixed binary tree; everything after that is integer arithmetic (exact in any order).
 //
 // Reference semantics: nESS / vanilla_floor_threshold (coddiwomple/utils.py:41-72), Resampler.resample
 // (coddiwomple/resamplers.py:61-133), MultinomialResampler._resample (coddiwomple/resamplers.py:254-272).

@@ -285,8 +285,9 @@ CDW_API int cdw_resample_indices(int kind, const double* w, const double* unifor
 /* K2 (second half) + K3a in one call: everything between two propagate launches of the SMC loop
  * (openmm/coddiwomple.py:318).  Uniforms come from Philox (seed, stream_id): n draws for multinomial, one for systematic
  * (written to `uniforms` for inspection).  *wmin_key (the running min left by cdw_smc_propagate) is consumed and re-armed
- * to ~0.  For n <= 16384 this is a single one-CTA kernel with the integer cdf in shared memory; larger batches run
- * cdw_weight_stats + cdw_philox_uniforms + cdw_resample_indices.  Same ancestors either way. */
+ * to ~0.  For n <= 24576 this is ONE launch of 8 cooperating thread blocks (the routine cdw_smc_iteration runs inside the
+ * propagate launch); larger batches run statistics + three scan kernels + a search kernel that draws the uniforms itself
+ * (5 launches).  Same ancestors either way.  `workspace` must be zero when first used; the kernels leave it at rest. */
 CDW_API int cdw_smc_resample(int kind, const double* w, int64_t n, double floor_threshold, uint64_t* wmin_key, uint64_t seed,
                              uint64_t stream_id, double* stats, const double* cum_in, double* cum_out, int32_t* anc_out,
                              uint64_t* cdf_out, double* uniforms, void* workspace, size_t workspace_bytes, cdw_stream stream);
