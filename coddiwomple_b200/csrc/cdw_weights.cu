@@ -215,10 +215,75 @@ __global__ void __launch_bounds__(1024) cdf_scan_tiles_kernel(long long n, doubl
     }
 }
 
+// cdw_smc_resample draws its own uniforms (Philox, keyed by slot) inside the search kernels and lets them re-arm the
+// running-min key: no separate uniforms / fill launches.
+struct SearchGen {
+    int gen;                              // 0: read `uniforms`; 1: generate (and store to uniforms_out if not NULL)
+    unsigned long long seed, stream_id;
+    double* uniforms_out;
+    unsigned long long* rearm_key;        // set to ~0 by the kernel (may be NULL)
+};
+
+__device__ __forceinline__ void search_rearm(const SearchGen& g) {
+    if (g.rearm_key && blockIdx.x == 0 && threadIdx.x == 0) *g.rearm_key = ~0ull;
+}
+
+// Systematic resampling needs no search at all: its targets are sorted, so the tile scan that has cdf[j - 1] and cdf[j] in
+// registers can emit item j's slots directly, [first(cdf[j - 1]), first(cdf[j])) with first(c) = min{i : target_i >= c},
+// target_i = floor(((i + u0) / n) T).  first() is estimated in floating point and corrected with the exact forward map,
+// so the ancestors are bit-identical to the search form.  No second pass over the cdf.
+struct EmitArgs {
+    const double* uniforms;   // [1] u0 when gen.gen == 0
+    const double* cum_in; double* cum_out; int* anc;
+    SearchGen gen;
+};
+
+__device__ __forceinline__ unsigned long long systematic_target(long long i, double u0, long long n, unsigned long long total) {
+    return fixed_target(__ddiv_rn(__dadd_rn((double)i, u0), (double)n), total);
+}
+
+__device__ __forceinline__ long long first_slot(unsigned long long c, unsigned long long total, double u0, long long n, double n_over_total) {
+    if (c == 0) return 0;
+    long long i = (long long)ceil((double)c * n_over_total - u0);
+    i = i < 0 ? 0 : (i > n ? n : i);
+    while (i > 0 && systematic_target(i - 1, u0, n, total) >= c) --i;
+    while (i < n && systematic_target(i, u0, n, total) < c) ++i;
+    return i;
+}
+
+__device__ __forceinline__ void emit_slot(const EmitArgs& e, long long i, long long j, double mean) {
+    e.anc[i] = (int)j;
+    if (e.cum_out) {
+        const double c = e.cum_in ? e.cum_in[i] : 0.0;
+        e.cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
+    }
+}
+
+constexpr int kHeavyRange = 16;   // longer slot ranges (one ancestor copied many times) are written by the whole block
+constexpr int kHeavyList = 64;
+
+template <bool EMIT>
 __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __restrict__ w, long long n, const double* __restrict__ stats,
-                                                               WsView ws, unsigned long long* __restrict__ cdf) {
-    if (stats[CDW_STAT_RESAMPLE] == 0.0) return;
+                                                               WsView ws, unsigned long long* __restrict__ cdf, EmitArgs em) {
+    if (EMIT) search_rearm(em.gen);
+    if (stats[CDW_STAT_RESAMPLE] == 0.0) {
+        if (EMIT) {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+                em.anc[i] = (int)i;
+                if (em.cum_out) em.cum_out[i] = w[i];  // null update: cum += inc (resamplers.py:136-156)
+            }
+        }
+        return;
+    }
     __shared__ unsigned long long warp_tot[kBlock / 32];
+    __shared__ long long heavy[3 * kHeavyList];
+    __shared__ int n_heavy;
+    const unsigned long long total = EMIT ? ws.hdr[WS_TOTAL] : 0ull;
+    const double mean = stats[CDW_STAT_MEAN];
+    const double u0 = EMIT ? (em.gen.gen ? philox_uniform53(em.gen.seed, em.gen.stream_id, 0) : em.uniforms[0]) : 0.0;
+    const double n_over_total = EMIT ? (double)n / (double)total : 0.0;
+    if (EMIT && em.gen.gen && em.gen.uniforms_out && blockIdx.x == 0 && threadIdx.x == 0) em.gen.uniforms_out[0] = u0;
+    if (EMIT && threadIdx.x == 0) n_heavy = 0;
     const double wmin = stats[CDW_STAT_WMIN];
     const double scale = pow2((int)ws.hdr[WS_SHIFT]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,6 +324,28 @@ __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __r
             const unsigned long long i = (unsigned long long)(i0 + k);
             const bool ends = (k == kItems - 1 && ((i + 1) & (kGroup - 1)) == 0) || i + 1 == (unsigned long long)n;
             if (i < (unsigned long long)n && ends) ws.coarse[i >> kGroupLog2] = q[k] + off;
+        }
+        if (EMIT) {
+            long long lo = first_slot(off, total, u0, n, n_over_total);
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                const long long j = i0 + k;
+                const long long hi = j < n ? first_slot(q[k] + off, total, u0, n, n_over_total) : lo;
+                if (hi - lo > kHeavyRange) {
+                    const int slot = atomicAdd(&n_heavy, 1);
+                    if (slot < kHeavyList) { heavy[3 * slot] = j; heavy[3 * slot + 1] = lo; heavy[3 * slot + 2] = hi; }
+                    else for (long long i = lo; i < hi; ++i) emit_slot(em, i, j, mean);
+                } else {
+                    for (long long i = lo; i < hi; ++i) emit_slot(em, i, j, mean);
+                }
+                lo = hi;
+            }
+            __syncthreads();
+            const int nh = n_heavy < kHeavyList ? n_heavy : kHeavyList;
+            for (int h = 0; h < nh; ++h)
+                for (long long i = heavy[3 * h + 1] + threadIdx.x; i < heavy[3 * h + 2]; i += blockDim.x) emit_slot(em, i, heavy[3 * h], mean);
+            __syncthreads();
+            if (threadIdx.x == 0) n_heavy = 0;
         }
     }
 }
@@ -309,19 +396,6 @@ __device__ __forceinline__ long long hier_search(unsigned long long target, cons
         if (__ldg(cdf + mid) > target) jhi = mid; else jlo = mid + 1;
     }
     return jlo;
-}
-
-// cdw_smc_resample draws its own uniforms (Philox, keyed by slot) inside the search kernels and lets them re-arm the
-// running-min key: no separate uniforms / fill launches.
-struct SearchGen {
-    int gen;                              // 0: read `uniforms`; 1: generate (and store to uniforms_out if not NULL)
-    unsigned long long seed, stream_id;
-    double* uniforms_out;
-    unsigned long long* rearm_key;        // set to ~0 by the kernel (may be NULL)
-};
-
-__device__ __forceinline__ void search_rearm(const SearchGen& g) {
-    if (g.rearm_key && blockIdx.x == 0 && threadIdx.x == 0) *g.rearm_key = ~0ull;
 }
 
 // Multinomial (unsorted uniforms): one slot per thread, hierarchical search.
@@ -586,7 +660,15 @@ static int resample_indices_launch(int kind, const double* w, const double* unif
     CDW_DBG("cdf_tile_sums_kernel")
     cdf_scan_tiles_kernel<<<1, 1024, 0, st>>>(n, (double*)stats, ws);
     CDW_DBG("cdf_scan_tiles_kernel")
-    cdf_tile_scan_kernel<<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out);
+    static const bool sys_search = getenv("CDW_SYSTEMATIC_SEARCH") != nullptr;   // A/B: the windowed search form
+    if (kind == CDW_RESAMPLE_SYSTEMATIC && !sys_search) {
+        EmitArgs em = {};
+        em.uniforms = uniforms; em.cum_in = cum_in; em.cum_out = cum_out; em.anc = anc_out; em.gen = gen;
+        cdf_tile_scan_kernel<true><<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out, em);
+        CDW_CUDA(cudaGetLastError());
+        return CDW_OK;
+    }
+    cdf_tile_scan_kernel<false><<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out, EmitArgs{});
     CDW_DBG("cdf_tile_scan_kernel")
     if (kind == CDW_RESAMPLE_SYSTEMATIC) {
         int grid_s = blocks_for(n, kSysSlots, sm_count() * 8);
