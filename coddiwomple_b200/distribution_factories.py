@@ -1,84 +1,89 @@
 """Distribution Factory module — `DistributionFactory`, `TargetFactory`, `ProposalFactory` with the reference's
-interface (coddiwomple/distribution_factories.py:16-252)."""
+interface (coddiwomple/distribution_factories.py:16-252): a factory owns a `PDFState` and the sequence of parameter sets
+it is annealed through; the target factory turns a particle into an incremental work, the proposal factory moves it."""
 import logging
 
 _logger = logging.getLogger("distribution_factories")
 
 
-class DistributionFactory():
-    """Manage a PDFState."""
+def _same_kind(candidate, sequence, what):
+    have, want = type(candidate), type(sequence[0])
+    if have is not want:
+        raise AssertionError(f"{what}: got {have.__name__}, the sequence holds {want.__name__}")
+
+
+class DistributionFactory:
+    """A `pdf_state` plus the list of parameter sets that index its members (`parameter_sequence[t]`)."""
 
     def __init__(self, pdf_state, parameter_sequence, **kwargs):
-        self.pdf_state = pdf_state
-        self.parameter_sequence = parameter_sequence
+        self.pdf_state, self.parameter_sequence = pdf_state, parameter_sequence
 
     def update_pdf(self, sequence_index):
-        parameters = self.parameter_sequence[sequence_index]
-        self.pdf_state.set_parameters(parameters)
+        """Point the pdf_state at member `sequence_index` of the sequence."""
+        self.pdf_state.set_parameters(self.parameter_sequence[sequence_index])
 
     def update_parameter_sequence(self, new_parameters):
-        new_parameters_type, parameter_sequence_type = type(new_parameters), type(self.parameter_sequence[0])
-        assert new_parameters_type == parameter_sequence_type, f"the new_parameters type ({new_parameters_type}) is not the same as the parameter sequence element type ({parameter_sequence_type})"
+        """Append one more member (on-the-fly protocols)."""
+        _same_kind(new_parameters, self.parameter_sequence, "update_parameter_sequence")
         self.parameter_sequence.append(new_parameters)
 
 
 class TargetFactory(DistributionFactory):
-    """Manage Target probability distributions."""
+    """Target distributions: incremental works and the termination test."""
 
     def __init__(self, pdf_state, parameter_sequence, termination_parameters=None, **kwargs):
         super().__init__(pdf_state, parameter_sequence)
-        if termination_parameters is None:
-            self.termination_parameters = self.parameter_sequence[-1]
-        else:
-            termination_parameters_type, parameter_type = type(termination_parameters), type(self.parameter_sequence[0])
-            assert termination_parameters_type == parameter_type, f"The termination parameters type ({termination_parameters_type}) do not match the sequence parameters type ({parameter_type})"
-            self.termination_parameters = termination_parameters
+        if termination_parameters is not None:
+            _same_kind(termination_parameters, self.parameter_sequence, "termination_parameters")
+        self.termination_parameters = self.parameter_sequence[-1] if termination_parameters is None else termination_parameters
 
     def compute_incremental_work(self, particle, neglect_proposal_work=False, **kwargs):
-        """work_(inc,t) = u_t(x) + auxiliary_work (+ last proposal work).  The flag is inverted in the reference
-        (distribution_factories.py:128: `neglect_proposal_work=True` ADDS the proposal work); reproduced deliberately."""
-        iteration = particle.iteration
-        self.update_pdf(iteration)
-        u_t = self.pdf_state.reduced_potential(particle.state)
-        state_work = u_t + particle.auxiliary_work
-        proposal_work = particle.get_last_proposal_work() if neglect_proposal_work else 0.
-        return state_work + proposal_work
+        """u_t(x) + auxiliary_work, where auxiliary_work = -u_{t-1}(x_{t-1}) is carried by the particle.
+
+        The flag reads backwards in the reference (distribution_factories.py:128 ADDS the last proposal work when
+        `neglect_proposal_work` is true); that behaviour is kept on purpose so that callers see the same numbers."""
+        self.update_pdf(particle.iteration)
+        work = self.pdf_state.reduced_potential(particle.state) + particle.auxiliary_work
+        if neglect_proposal_work:
+            work += particle.get_last_proposal_work()
+        return work
 
     def terminate(self, particle):
-        current_particle_parameters = self.parameter_sequence[particle.iteration]
-        return True if all(current_particle_parameters[key] == self.termination_parameters[key] for key in current_particle_parameters.keys()) else False
+        """True once the particle's current parameter set equals the termination set, key by key."""
+        now = self.parameter_sequence[particle.iteration]
+        return all(now[k] == self.termination_parameters[k] for k in now)
 
 
 class ProposalFactory(DistributionFactory):
-    """Manage Proposal probability distributions"""
+    """Proposal distributions: equips the first sample and applies the propagator."""
 
     def __init__(self, parameter_sequence, propagator, **kwargs):
-        super(ProposalFactory, self).__init__(propagator.pdf_state, parameter_sequence)
+        super().__init__(propagator.pdf_state, parameter_sequence)
         self._propagator = propagator
 
     def equip_initial_sample(self, particle, initial_particle_state, generation_pdf=None, **kwargs):
-        """1. update particle state 2. update proposal work 3. auxiliary_work = -u_0(x_0); returns -log(weight_0)."""
-        assert particle.state is None, f"the particle state is not None; it looks like the particle has already been Initialized"
-        if generation_pdf is None:
-            self.update_pdf(0)
-            generation_pdf = self.pdf_state
-        # (the reference's else-branch references an undefined name, distribution_factories.py:206; the argument is honoured here)
-        state_reduced_potential = self.pdf_state.reduced_potential(initial_particle_state)
-        generation_reduced_potential = generation_pdf.reduced_potential(initial_particle_state)
-        initial_work = state_reduced_potential - generation_reduced_potential
+        """Give a fresh particle its state, a zero proposal work and auxiliary_work = -u_0(x_0); returns the initial work
+        u_0(x_0) - u_gen(x_0) (zero when the sample was drawn from the first target itself).
+        (The reference's branch for an explicit `generation_pdf` uses an undefined name, distribution_factories.py:206;
+        here the argument simply is the generating distribution.)"""
+        if particle.state is not None:
+            raise AssertionError("equip_initial_sample: this particle already has a state")
+        self.update_pdf(0)
+        u_target = self.pdf_state.reduced_potential(initial_particle_state)
+        u_generation = u_target if generation_pdf is None else generation_pdf.reduced_potential(initial_particle_state)
         particle.update_state(initial_particle_state)
-        particle.update_proposal_work(0.)
-        particle.update_auxiliary_work(-state_reduced_potential)
-        return initial_work
+        particle.update_proposal_work(0.0)
+        particle.update_auxiliary_work(-u_target)
+        return u_target - u_generation
 
     def propagate(self, particle, num_applications=1, **kwargs):
-        iteration = particle.iteration
-        self.update_pdf(iteration)
-        proposal_work = 0.
-        particle_state = particle.state
-        for i in range(num_applications):
-            particle_state, work = self._propagator.apply(particle_state, **kwargs)
-            proposal_work += work
-        particle.update_state(particle_state)
-        particle.update_proposal_work(proposal_work)
-        return particle, proposal_work
+        """Apply the propagator `num_applications` times under the particle's current parameter set; the summed proposal
+        work is stored in the particle and returned with it."""
+        self.update_pdf(particle.iteration)
+        state, total = particle.state, 0.0
+        for _ in range(num_applications):
+            state, work = self._propagator.apply(state, **kwargs)
+            total += work
+        particle.update_state(state)
+        particle.update_proposal_work(total)
+        return particle, total

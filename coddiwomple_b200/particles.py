@@ -8,89 +8,69 @@ lazy `Particle` views so that code written against the reference — `[p.cumulat
 unless it is asked for.
 """
 import copy
+import operator
 
 import numpy as np
 
 
-class Particle(object):
-    """Holds ancestry, proposal works, state, incremental and cumulative works of one particle."""
+class Particle:
+    """Host-side record of one particle: lineage, works and (optionally) a trace of its states.
+
+    Public surface = the reference's (`coddiwomple/particles.py:11-177`): the `update_*` / `zero_*` mutators and the
+    read-only properties generated below.  Storage is a handful of slots; there is nothing here to accelerate.
+    """
+
+    __slots__ = ("_w", "_dw", "_pw", "_x", "_line", "_trace", "_aux", "_t")
 
     def __init__(self, index, record_states=False, iteration=0, **kwargs):
-        self._cumulative_work = 0.
-        self._incremental_works = []
-        self._proposal_works = []
-        self._state = None
-        self._ancestry = [index]
-        self._record_states = record_states
-        self._state_history = [] if record_states else None
-        self._auxiliary_work = 0.
-        self._iteration = iteration
+        self._w, self._aux, self._t = 0.0, 0.0, iteration
+        self._dw, self._pw = [], []
+        self._x = None
+        self._line = [index]
+        self._trace = [] if record_states else None   # None: states are not recorded
+
+    # ---- works
+    def update_work(self, incremental_work):
+        self._dw.append(incremental_work)
+        self._w += incremental_work
 
     def update_auxiliary_work(self, incremental_work):
-        self._auxiliary_work += incremental_work
+        self._aux += incremental_work
 
     def zero_auxiliary_work(self):
-        self._auxiliary_work = 0.
-
-    def update_work(self, incremental_work):
-        self._cumulative_work += incremental_work
-        self._incremental_works.append(incremental_work)
-
-    def get_last_proposal_work(self):
-        return self._proposal_works[-1]
+        self._aux = 0.0
 
     def update_proposal_work(self, proposal_work):
-        self._proposal_works.append(proposal_work)
+        self._pw.append(proposal_work)
 
     def update_proposal_work_in_place(self, proposal_work):
-        self._proposal_works[-1] = proposal_work
+        self._pw[-1] = proposal_work
 
+    def get_last_proposal_work(self):
+        return self._pw[-1]
+
+    # ---- lineage / state / clock
     def update_ancestry(self, index):
-        self._ancestry.append(index)
+        self._line.append(index)
 
     def update_state(self, state, amend_state_history=False, state_history_index=-1):
-        # the reference calls copy.deepcopy here without importing copy (particles.py:138,140); imported above
-        if self._record_states:
+        if self._trace is not None:
+            snapshot = copy.deepcopy(state)
             if amend_state_history:
-                self._state_history[state_history_index] = copy.deepcopy(state)
+                self._trace[state_history_index] = snapshot
             else:
-                self._state_history.append(copy.deepcopy(state))
-        self._state = state
+                self._trace.append(snapshot)
+        self._x = state
 
     def update_iteration(self, increment=1):
-        self._iteration += increment
+        self._t += increment
 
-    @property
-    def cumulative_work(self):
-        return self._cumulative_work
 
-    @property
-    def incremental_works(self):
-        return self._incremental_works
-
-    @property
-    def proposal_works(self):
-        return self._proposal_works
-
-    @property
-    def state(self):
-        return self._state
-
-    @property
-    def ancestry(self):
-        return self._ancestry
-
-    @property
-    def auxiliary_work(self):
-        return self._auxiliary_work
-
-    @property
-    def state_history(self):
-        return self._state_history
-
-    @property
-    def iteration(self):
-        return self._iteration
+# read-only views under the reference's property names
+for _name, _slot in (("cumulative_work", "_w"), ("incremental_works", "_dw"), ("proposal_works", "_pw"), ("state", "_x"), ("ancestry", "_line"),
+                     ("auxiliary_work", "_aux"), ("state_history", "_trace"), ("iteration", "_t")):
+    setattr(Particle, _name, property(operator.attrgetter(_slot)))
+del _name, _slot
 
 
 class ParticleList:
@@ -126,17 +106,17 @@ class ParticleList:
         if i < 0:
             i += len(self)
         p = Particle(index=int(self.ensemble.gid0 + i), iteration=self.ensemble.iteration)
-        p._cumulative_work = float(h["cum"][i])
-        p._auxiliary_work = float(h["aux"][i])
+        p._w = float(h["cum"][i])
+        p._aux = float(h["aux"][i])
         if self._histories is not None:
             cums = self._histories["cum"][:, i]
-            p._incremental_works = list(np.diff(np.concatenate([[0.0], cums])))
-            p._ancestry = [int(self.ensemble.gid0 + i)] + [int(l) for l in self._histories["labels"][:, i]]
+            p._dw = list(np.diff(np.concatenate([[0.0], cums])))
+            p._line = [int(self.ensemble.gid0 + i)] + [int(l) for l in self._histories["labels"][:, i]]
         else:
-            p._ancestry = [int(self.ensemble.gid0 + i), int(h["label"][i])]
-        p._proposal_works = [0.] * (self.ensemble.iteration + 1)
+            p._line = [int(self.ensemble.gid0 + i), int(h["label"][i])]
+        p._pw = [0.] * (self.ensemble.iteration + 1)
         if self._state_factory is not None:
-            p._state = self._state_factory(h["pos"][i], h["vel"][i])
+            p._x = self._state_factory(h["pos"][i], h["vel"][i])
         return p
 
     def __iter__(self):

@@ -45,33 +45,35 @@ class Resampler():
 
     # ------------------------------------------------------------------ public API
     def resample(self, particles, incremental_works, observable=None, threshold=None, update_particle_indices=True, **kwargs):
+        """Decide (observable + threshold, or always when either is None) and, if so, resample; otherwise every particle
+        just accumulates its incremental work (coddiwomple/resamplers.py:61-133)."""
         if isinstance(particles, ParticleList):
             return self._resample_device(particles, incremental_works, observable, threshold, **kwargs)
-        if observable is None or threshold is None:
-            resample_bool = True
-        else:
-            _observable_value = observable(particles, incremental_works, **kwargs)
-            resample_bool = threshold(_observable_value, **kwargs)
-        if resample_bool:
-            previous_cumulative_works = np.array([particle.cumulative_work for particle in particles])
-            updated_cumulative_works = previous_cumulative_works + np.asarray(incremental_works, dtype=np.float64)
-            _, stats, _ = kernels.weight_stats(updated_cumulative_works, always=True)
-            mean_cumulative_work = float(stats[_lib.STAT_MEAN].item())  # -logsumexp(-W) + log N (resamplers.py:107)
-            resampled_indices = self._resample(cumulative_works=updated_cumulative_works, num_resamples=len(updated_cumulative_works), **kwargs)
-            copy_particle_auxiliaries = [particle.auxiliary_work for particle in particles]
-            copy_particle_states = [particle.state for particle in particles]
-            copy_particle_indices = [particle.ancestry[-1] for particle in particles]
-            iterations = [particle.iteration for particle in particles]
-            assert all(_iter == iterations[0] for _iter in iterations), f"the particles are desynchronized"
-            self._resampling_logger.append(iterations[0])
-            for current_particle_index, resampling_particle_index in enumerate(resampled_indices):
-                self._update_particle(particles[current_particle_index],
-                                      from_particle_auxiliary_work=copy_particle_auxiliaries[resampling_particle_index],
-                                      from_particle_state=copy_particle_states[resampling_particle_index],
-                                      from_particle_index=copy_particle_indices[resampling_particle_index],
-                                      cumulative_work=mean_cumulative_work)
-        else:
-            [self._null_update_particle(particle, incremental_work, **kwargs) for particle, incremental_work in zip(particles, incremental_works)]
+        wanted = True
+        if observable is not None and threshold is not None:
+            wanted = threshold(observable(particles, incremental_works, **kwargs), **kwargs)
+        if not wanted:
+            for particle, work in zip(particles, incremental_works):
+                self._null_update_particle(particle, work, **kwargs)
+            return
+        self._host_resample(particles, np.asarray(incremental_works, dtype=np.float64), **kwargs)
+
+    def _host_resample(self, particles, incremental_works, **kwargs):
+        """Python `Particle` objects: the works go to the GPU, ancestors and the normaliser -logsumexp(-W) + log N
+        (resamplers.py:107) come back from the K2/K3 kernels, and each particle is rewritten from a snapshot of its ancestor."""
+        clock = {p.iteration for p in particles}
+        if len(clock) != 1:
+            raise AssertionError(f"the particles are desynchronized (iterations {sorted(clock)})")
+        works = np.fromiter((p.cumulative_work for p in particles), dtype=np.float64, count=len(particles)) + incremental_works
+        _, stats, _ = kernels.weight_stats(works, always=True)
+        normaliser = float(stats[_lib.STAT_MEAN].item())
+        ancestors = self._resample(cumulative_works=works, num_resamples=len(works), **kwargs)
+        snapshot = [(p.auxiliary_work, p.state, p.ancestry[-1]) for p in particles]   # taken before anything is overwritten
+        self._resampling_logger.append(clock.pop())
+        for particle, a in zip(particles, ancestors):
+            aux, state, label = snapshot[int(a)]
+            self._update_particle(particle, from_particle_auxiliary_work=aux, from_particle_state=state, from_particle_index=label,
+                                  cumulative_work=normaliser)
 
     def _resample_device(self, particles, incremental_works, observable, threshold, floor_threshold=0.5, **kwargs):
         import torch
@@ -99,18 +101,21 @@ class Resampler():
         return stats
 
     def _null_update_particle(self, particle, incremental_work, **kwargs):
-        particle.update_state(particle.state)
+        """No resampling: the particle keeps its state and lineage and accumulates the work (resamplers.py:136-156)."""
         particle.update_work(incremental_work)
+        particle.update_state(particle.state)
         particle.update_ancestry(particle.ancestry[-1])
 
     def _update_particle(self, particle_to_update, from_particle_auxiliary_work, from_particle_state, from_particle_index, cumulative_work,
                          amend_state_history=True, **kwargs):
-        particle_to_update.zero_auxiliary_work()
-        particle_to_update.update_auxiliary_work(from_particle_auxiliary_work)
-        particle_to_update.update_state(copy.deepcopy(from_particle_state), amend_state_history=amend_state_history)
-        modified_incremental_work = cumulative_work - particle_to_update.cumulative_work
-        particle_to_update.update_work(modified_incremental_work)
-        particle_to_update.update_ancestry(from_particle_index)
+        """Overwrite a particle with (a copy of) its ancestor; its cumulative work becomes the ensemble normaliser, i.e. the
+        incremental work recorded is (normaliser - previous cumulative work) (resamplers.py:159-199)."""
+        target = particle_to_update
+        target.update_work(cumulative_work - target.cumulative_work)
+        target.zero_auxiliary_work()
+        target.update_auxiliary_work(from_particle_auxiliary_work)
+        target.update_ancestry(from_particle_index)
+        target.update_state(copy.deepcopy(from_particle_state), amend_state_history=amend_state_history)
 
     def _resample(self, cumulative_works, num_resamples, **kwargs):
         """Dummy _resample method; does NOT resample (coddiwomple/resamplers.py:202-216)."""

@@ -8,9 +8,9 @@ import numpy as np
 
 
 def add_method(object, function):
-    """Bind a function to an object instance (coddiwomple/utils.py:8-19)."""
-    from functools import partial
-    setattr(object, function.__name__, partial(function, object))
+    """Attach `function` to one instance under its own name, with the instance as first argument (coddiwomple/utils.py:8-19)."""
+    import functools
+    setattr(object, function.__name__, functools.partial(function, object))
 
 
 def dummy_function():
@@ -30,11 +30,10 @@ def nESS(particles, incremental_works=None, **kwargs):
     if isinstance(particles, ParticleList):
         cum = particles.ensemble.cum
     else:
-        cum = np.array([particle.cumulative_work for particle in particles], dtype=np.float64)
+        cum = np.fromiter((p.cumulative_work for p in particles), dtype=np.float64)
     return device_ness(cum, incremental_works)
 
 
 def vanilla_floor_threshold(_observable, floor_threshold=0.5, **kwargs):
-    """simple floor threshold: resample iff observable <= floor (coddiwomple/utils.py:67-72)."""
-    returnable = False if _observable > floor_threshold else True
-    return returnable
+    """Resample iff the observable has dropped to the floor or below (coddiwomple/utils.py:67-72)."""
+    return not (_observable > floor_threshold)
