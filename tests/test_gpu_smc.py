@@ -216,7 +216,8 @@ def test_Resampler_on_python_particles_matches_the_reference(case):
     P = c["P"]
     particles = [Particle(index=i) for i in range(P)]
     for p, cw, a in zip(particles, c["cumulative_works_in"], c["auxiliary_works_in"]):
-        p._cumulative_work, p._auxiliary_work = cw, a
+        p.update_work(cw)
+        p.update_auxiliary_work(a)
         p.update_state(("state", p.ancestry[0]))
     assert nESS(particles, np.array(c["incremental_works"])) == pytest.approx(c["nESS"], rel=1e-12)
     np.random.seed(1000 + c["seed"])
