@@ -105,3 +105,31 @@ def ancestors(works, uniforms, kind="multinomial", u0=None):
     if kind == "systematic":
         uniforms = systematic_uniforms(u0 if u0 is not None else uniforms[0], len(works))
     return ancestors_fixed(works, uniforms)
+
+
+def canonical_statistics(works):
+    """(sum e, sum e^2) of e_i = det_exp(min W - W_i) in the order the one-launch resampling team uses
+    (coddiwomple_b200/csrc/cdw_resample.cuh): 1024 virtual threads, element i belongs to virtual thread i mod 1024 and is
+    added in index order; the 1024 partials are combined by the fixed binary tree p[k] += p[k + s], s = 512 .. 1.
+    With det_exp bit-identical on CPU and GPU this makes sum e bit-reproducible (the device accumulates e^2 with a fused
+    multiply-add and uses its own log, so sum e^2, nESS and the normaliser agree to ~1e-15, not bitwise).
+    Returns (wmin, sum_e, sum_e2, nESS, mean) with mean = wmin - log(sum_e) + log(N) (resamplers.py:107, utils.py:41-64)."""
+    w = np.asarray(works, dtype=np.float64)
+    n = w.size
+    wmin = w.min()
+    e = det_exp(wmin - w)
+    V = 1024
+    pe, pe2 = np.zeros(V), np.zeros(V)
+    for start in range(0, n, V):          # row r of the (n / 1024, 1024) layout is added to the partials in index order
+        chunk = e[start:start + V]
+        pe[:chunk.size] += chunk
+        pe2[:chunk.size] += chunk * chunk
+    s = V // 2
+    while s > 0:
+        pe[:s] += pe[s:2 * s]
+        pe2[:s] += pe2[s:2 * s]
+        s //= 2
+    sum_e, sum_e2 = float(pe[0]), float(pe2[0])
+    ness = (sum_e * sum_e) / (float(n) * sum_e2)
+    mean = wmin - np.log(sum_e) + np.log(float(n))
+    return float(wmin), sum_e, sum_e2, float(ness), float(mean)

@@ -242,3 +242,35 @@ def test_K2_large_reduction_accuracy(gpu):
     assert s[_lib.STAT_WMIN] == W.min()
     s2 = kernels.weight_stats(W, floor_threshold=0.5)[1].cpu().numpy()
     np.testing.assert_array_equal(s, s2)   # run-to-run deterministic reduction
+
+
+@pytest.mark.parametrize("n,kind", [(1, 0), (7, 1), (1000, 0), (10000, 0), (10000, 1), (24576, 0)])
+def test_cooperative_resample_statistics_follow_the_canonical_order(gpu, n, kind):
+    """cdw_smc_resample (8 cooperating CTAs, the routine cdw_smc_iteration runs inside the propagate launch): the
+    log-sum-exp statistics follow oracle.resampling.canonical_statistics — the plain sum bit for bit (det_exp and the
+    1024-virtual-thread order are fully specified), the rest to 1e-13 — and the ancestors equal the oracle's."""
+    import ctypes as C
+    from coddiwomple_b200 import kernels
+    lib = _lib.load()
+    W_host = np.random.RandomState(n).normal(0.0, 1.5, n)
+    W = torch.as_tensor(W_host).cuda()
+    ws = kernels.WeightWorkspace(n)
+    ws.wmin_key.fill_(-1)
+    Wc = torch.empty_like(W)
+    _lib.check(lib.cdw_weight_update(_lib.ptr(W), None, None, None, n, None, _lib.ptr(Wc), _lib.ptr(ws.wmin_key), _lib.current_stream()))
+    cum = torch.zeros_like(W)
+    anc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    u = torch.zeros(n, dtype=torch.float64, device="cuda")
+    _lib.check(lib.cdw_smc_resample(kind, _lib.ptr(W), n, -1.0, _lib.ptr(ws.wmin_key), C.c_uint64(11), C.c_uint64(3), _lib.ptr(ws.stats), _lib.ptr(cum),
+                                    _lib.ptr(cum), _lib.ptr(anc), _lib.ptr(ws.cdf), _lib.ptr(u), _lib.ptr(ws.buf), ws.bytes, _lib.current_stream()))
+    s = ws.stats.cpu().numpy()
+    wmin, sum_e, sum_e2, ness, mean = resampling.canonical_statistics(W_host)
+    assert s[_lib.STAT_WMIN] == wmin and s[_lib.STAT_SUM_E] == sum_e
+    assert s[_lib.STAT_SUM_E2] == pytest.approx(sum_e2, rel=1e-13) and s[_lib.STAT_NESS] == pytest.approx(ness, rel=1e-13)
+    assert s[_lib.STAT_MEAN] == pytest.approx(mean, rel=1e-13, abs=1e-13)
+    uni = u.cpu().numpy()
+    ref = resampling.ancestors(W_host, uni if kind == 0 else None, kind="multinomial" if kind == 0 else "systematic", u0=None if kind == 0 else uni[0])
+    np.testing.assert_array_equal(anc.cpu().numpy(), ref)
+    np.testing.assert_allclose(cum.cpu().numpy(), np.full(n, s[_lib.STAT_MEAN]), rtol=1e-15, atol=1e-15)
+    assert int(ws.wmin_key.item()) == -1                     # re-armed
+    assert int(ws.buf[4].item()) == 0 and int(ws.buf[5].item()) == 0   # team counters back at rest

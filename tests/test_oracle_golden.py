@@ -130,3 +130,16 @@ def test_normals_moments():
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
     z2 = rng.normals(3, np.arange(20000), 5, 4, rng.KIND_MAXWELL_BOLTZMANN)
     assert abs(np.corrcoef(z.ravel(), z2.ravel())[0, 1]) < 0.02  # streams are independent
+
+
+@pytest.mark.parametrize("n", [1, 5, 1023, 1024, 1025, 10000])
+def test_canonical_statistics_equal_the_plain_definitions(n):
+    """The fixed summation order of the resampling team (oracle.resampling.canonical_statistics) is just an order:
+    nESS and the normaliser equal the textbook / reference forms (coddiwomple/utils.py:41-64, resamplers.py:107)."""
+    from oracle import resampling, weights
+    W = np.random.RandomState(n).normal(0.0, 2.0, n)
+    wmin, sum_e, sum_e2, ness, mean = resampling.canonical_statistics(W)
+    assert wmin == W.min()
+    assert ness == pytest.approx(weights.nESS(W), rel=1e-12)
+    assert mean == pytest.approx(-(np.logaddexp.reduce(-W) - np.log(n)), rel=1e-12, abs=1e-12)
+    assert sum_e == pytest.approx(np.exp(wmin - W).sum(), rel=1e-13)
