@@ -14,7 +14,8 @@
 // a TEAM of T lanes per replica: the T lanes split the term lists, atoms and constraint clusters of their replica
 // round-robin, each accumulates forces into its own fp32 copy (summed after the evaluation; still no atomics), and
 // energies are combined with log2(T) shuffles.  T = 1 is the pure lane-per-replica case (and the host harness);
-// the launcher picks T from the batch size and the shared-memory footprint so that the SMs stay full.
+// the launcher picks T from the system (atom count, shared-memory footprint), never from the batch size, so that
+// results do not depend on how a batch is sharded.
 //
 // Layout: the CTA stages the lambda-resolved term tables once (shared by all its threads); every per-replica
 // array (x, v, f, r0) is stored [element][thread] in shared memory, so a warp touching element k of its 32 replicas

@@ -1,14 +1,17 @@
 // cdw_propagate.cu — K1 (batched reduced potential) and K4 (fused SMC propagate: gather-on-load, energy+force,
-// incremental work, BAOAB + SHAKE/RATTLE + Philox, closing energy) for sm_100a.
+// incremental work, BAOAB + SHAKE/RATTLE + Philox, closing energy; optionally the whole SMC iteration with an in-launch
+// resampling team) for sm_100a.
 //
-// Mapping: one THREAD per replica, persistent CTAs looping over batches of blockDim replicas.  The
-// per-replica algorithm lives in cdw_lane.cuh (shared with the host test harness); this file is the kernel shells and
-// the C ABI.
-//   * prologue (once per CTA): the lambda vector is resolved into "effective" term records in shared memory;
-//   * a batch of rows is loaded by the whole CTA as coalesced float4 and transposed into [element][thread] shared
-//     arrays, where the state stays on chip for all substeps; every lane of a warp then evaluates the same term of 32
-//     different replicas (warp-uniform parameter broadcasts, no atomics, no inter-lane traffic);
-//   * constraints: exact k x k velocity projection and Gauss-Seidel SHAKE per cluster, per thread.
+// Mapping: a TEAM of T lanes per replica (T = 4 for 13-22 atom systems), 32 replica columns per CTA.  The
+// per-replica algorithm lives in cdw_lane.cuh (shared with the host test harness); this file is the kernel shells, the
+// launch logic and the C ABI.
+//   * prologue (once per CTA): the lambda-resolved "effective" term records arrive in shared memory, either by one TMA bulk
+//     copy of a prebuilt image (registered protocols) or built in place;
+//   * a batch of rows is gathered by the whole CTA (4-byte cp.async straight into [component][replica] shared arrays; row
+//     index = ancestor), where the state stays on chip for all substeps; every lane of a warp evaluates the same term of
+//     different replicas or, inside a team, the next term of the same replica (no atomics, per-lane fp32 force copies);
+//   * constraints: exact k x k velocity projection and Gauss-Seidel SHAKE per cluster;
+//   * cdw_smc_iteration: the last 8 CTAs of the launch are the resampling team (cdw_resample.cuh).
 #include <stdlib.h>
 
 #include "cdw_common.h"
