@@ -261,7 +261,7 @@ class ParticleEnsemble:
 
     def iterate(self, lam_row, langevin, seed, stats_row, kind, floor_threshold, resample_seed, stream_id, randomize_velocities=False, ula=False):
         """One whole SMC iteration in one call (include/cdw.h: cdw_smc_iteration): propagate_and_weigh + resample_fused.
-        For MCMC moves on a batch that fits the GPU at once this is a single kernel launch in which one extra thread block
+        For MCMC moves on a batch that fits the GPU at once this is a single kernel launch in which an extra team of thread blocks
         resamples while the others are still integrating."""
         self.iteration += 1
         flags = _lib.CDW_FLAG_ULA if ula else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0)
@@ -402,7 +402,7 @@ class SMCEngine:
         self.run()
 
     def capture(self):
-        """Capture `equip initial sample + T-1 iterations + final gather` (2 T launches) into one CUDA graph.
+        """Capture `equip initial sample + T-1 iterations + final gather` (T + 1 launches for MCMC moves: one per iteration) into one CUDA graph.
         The loop has no host decision (the resampling test runs on the device), so the whole anneal replays as a
         single graph launch; positions are (re)staged with load() before each replay."""
         e = self.ensemble
