@@ -88,3 +88,32 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
+    """Error behaviour of the C ABI (include/cdw.h): a negative return code and a thread-local message, never an abort;
+    argument validation comes before any CUDA call, so it is testable on a box without a GPU."""
+    lib = _lib.load()
+    prm = _lib.LangevinParams(0.002, 1.0, 2.494, 1e-6, 1, 0)
+    none = None
+    calls = {
+        "cdw_reduced_potential": (none, none, 4, none, 0.4, none, none),
+        "cdw_smc_propagate": (none,) * 5 + (4,) + (none,) * 5 + (ctypes.byref(prm), 0, 0, 0) + (none,) * 11,
+        "cdw_smc_propagate_cached": (none,) * 5 + (4,) + (none,) * 5 + (ctypes.byref(prm), 0, 0, 0) + (none,) * 12,
+        "cdw_smc_iteration": (none,) * 5 + (4,) + (none,) * 5 + (ctypes.byref(prm), 0, 0, 0) + (none,) * 7 + (0, 0.5, 0, 0) + (none,) * 5 + (0, none),
+        "cdw_smc_resample": (0, none, 4, 0.5, none, 0, 0) + (none,) * 7 + (0, none),
+        "cdw_weight_stats": (none, 4, 0.5, none, none, none, 0, none),
+        "cdw_resample_indices": (0, none, none, 4, none, none, none, none, none, none, 0, none),
+        "cdw_gather_particles": (none,) * 9 + (4, 3, none),
+        "cdw_system_register_protocol": (none, none, 3, 2.494, none),
+        "cdw_system_create": (none, none),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc < 0, name
+        assert lib.cdw_last_error(), name
+    # well-formed but empty batches are fine and do nothing (n == 0 returns before the null checks)
+    assert lib.cdw_smc_propagate(*((none,) * 5 + (0,) + (none,) * 5 + (ctypes.byref(prm), 0, 0, 0) + (none,) * 11)) < 0   # still needs sys
+    assert lib.cdw_system_destroy(None) == 0
+    with pytest.raises(_lib.CdwError):
+        _lib.check(lib.cdw_weight_stats(none, 4, 0.5, none, none, none, 0, none), "cdw_weight_stats")
