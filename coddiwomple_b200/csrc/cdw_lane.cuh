@@ -39,8 +39,16 @@
 #else
 #define CDW_CTA_THREADS(tid, nt) for (int tid = 0, nt = 1; tid < 1; ++tid)
 #define CDW_LDG(p) (*(p))
+#if defined(CDW_HOST_TEAMS)
+// host harness with teams: the T lanes of a replica are T host threads; the harness supplies a barrier and an exchange
+void cdw_host_team_sync();
+double cdw_host_shfl_xor(double v, int tl, int o);
+#define CDW_TEAM_SYNC(M) cdw_host_team_sync()
+#define CDW_SHFL_XOR(M, v, o) cdw_host_shfl_xor((v), (M).tl, (o))
+#else
 #define CDW_TEAM_SYNC(M) ((void)0)
 #define CDW_SHFL_XOR(M, v, o) (v)
+#endif
 #endif
 #if !defined(__CUDACC__)
 struct alignas(16) float4 {
@@ -753,6 +761,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                     const int bi = CDW_BASE(T.cons_atoms[2 * q]), bj = CDW_BASE(T.cons_atoms[2 * q + 1]), bq = CDW_BASE(q);
                     M.r0[bq] = M.x[bi] - M.x[bj]; M.r0[bq + kR] = M.x[bi + kR] - M.x[bj + kR]; M.r0[bq + 2 * kR] = M.x[bi + 2 * kR] - M.x[bj + 2 * kR];
                 }
+                CDW_TEAM_SYNC(M);  // every constraint vector is taken before any lane moves an atom
                 for (int at = tl; at < A; at += T_) {
                     const int b = CDW_BASE(at);
                     const double tau = 0.5 * a.kT * a.dt * a.dt * T.inv_m[at];

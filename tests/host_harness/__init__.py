@@ -16,7 +16,7 @@ def build():
     src = os.path.join(HERE, "harness.cpp")
     deps = [src] + [os.path.join(ROOT, "coddiwomple_b200", "csrc", f) for f in ("cdw_math.cuh", "cdw_lane.cuh", "cdw_pack.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", SO, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-o", SO, src])
     return SO
 
 
@@ -28,11 +28,18 @@ def lib():
     if _h is None:
         _h = C.CDLL(build())
         _h.hh_last_error.restype = C.c_char_p
+        if os.environ.get("CDW_HH_TEAM"):   # run a whole test file through the team emulation
+            _h.hh_set_team(int(os.environ["CDW_HH_TEAM"]))
     return _h
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def set_team(T):
+    """Lanes per replica for the propagate entry points (1 = one lane per replica; > 1 = host threads emulating a warp team)."""
+    lib().hh_set_team(int(T))
 
 
 class HostSystem:

@@ -5,8 +5,13 @@
 // no CPU fallback.
 #include <stdlib.h>
 
+#include <barrier>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
+
+#define CDW_HOST_TEAMS 1
 
 #include "../../coddiwomple_b200/csrc/cdw_pack.h"
 #include "../../coddiwomple_b200/csrc/cdw_lane.cuh"
@@ -47,7 +52,58 @@ extern "C" int hh_system_info(const hh_system* s, int* n_slots, int* n_clusters,
     return 0;
 }
 
+// ---- team emulation: the T lanes of one replica run as T host threads; CDW_TEAM_SYNC is a real barrier and the xor
+// shuffle goes through a small exchange buffer (write, barrier, read partner, barrier), so the host executes the same
+// team algorithm (term partition, per-lane force copies, reductions) as a warp does.
+static thread_local std::barrier<>* g_team_barrier = nullptr;
+static thread_local double* g_team_exchange = nullptr;
+static int g_team = 1;
+
+void cdw_host_team_sync() {
+    if (g_team_barrier) g_team_barrier->arrive_and_wait();
+}
+double cdw_host_shfl_xor(double v, int tl, int o) {
+    if (!g_team_barrier) return v;
+    g_team_exchange[tl] = v;
+    g_team_barrier->arrive_and_wait();
+    const double r = g_team_exchange[tl ^ o];
+    g_team_barrier->arrive_and_wait();
+    return r;
+}
+
+extern "C" void hh_set_team(int T) { g_team = T < 1 ? 1 : T; }
+
+static int run_team(const hh_system* s, PropArgs& a) {
+    const int T_ = g_team;
+    const Layout L = make_layout(s->dev, true, 1, T_);
+    std::vector<unsigned char> smem(L.total + 64, 0);
+    unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));
+    const Tables T = table_pointers(L, base);
+    build_tables(s->dev, T, a.lambda, a.kT, true);
+    unsigned long long mn = ~0ull;
+    for (long long p = 0; p < a.n; ++p) {
+        cta_load_rows(s->dev, a, base, L, 0, p, 1, true);
+        std::barrier<> bar(T_);
+        std::vector<double> exchange(T_, 0.0);
+        std::vector<unsigned long long> keys(T_, ~0ull);
+        std::vector<std::thread> lanes;
+        for (int tl = 0; tl < T_; ++tl)
+            lanes.emplace_back([&, tl]() {
+                g_team_barrier = &bar; g_team_exchange = exchange.data();
+                const LaneMem M = lane_pointers(L, base, T_, tl);
+                keys[tl] = lane_step(s->dev, T, M, a, p);
+                g_team_barrier = nullptr; g_team_exchange = nullptr;
+            });
+        for (auto& t : lanes) t.join();
+        mn = keys[0] < mn ? keys[0] : mn;
+        cta_store_rows(s->dev, a, base, L, 0, p, 1);
+    }
+    if (a.wmin_key && mn < *a.wmin_key) *a.wmin_key = mn;
+    return 0;
+}
+
 static int run(const hh_system* s, PropArgs& a, bool forces) {
+    if (forces && g_team > 1) return run_team(s, a);
     const Layout L = make_layout(s->dev, forces, 1, 1);
     std::vector<unsigned char> smem(L.total + 64, 0);
     unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));

@@ -1,0 +1,110 @@
+"""The TEAM form of the device code on the host: the T lanes of a replica run as T host threads (real barriers, an
+exchange buffer for the xor shuffles — tests/host_harness/harness.cpp), so the term partition, the per-lane force copies,
+their reduction, the cluster round-robin and the team sums that a warp executes on the GPU are checked here, without one."""
+import numpy as np
+import pytest
+
+from coddiwomple_b200 import _lib, testsystems as ts
+from coddiwomple_b200.system import spec_from_xml
+from oracle import langevin, ula
+from oracle.potential import XmlSystemOracle, kT_kj_per_mol
+from tests import host_harness as hh
+from tests.helpers import cache_frames, hybrid_positions, relative_lambdas, system_xml
+
+kT = kT_kj_per_mol()
+
+
+@pytest.fixture(autouse=True)
+def _one_lane_afterwards():
+    yield
+    hh.set_team(1)
+
+
+def _setup(name, P=4):
+    xml = system_xml(name) if name != "ala" else ts.alanine_dipeptide_shaped_xml()[0]
+    o, spec = XmlSystemOracle(xml), spec_from_xml(xml)
+    if name == "fluorobenzene":
+        X = cache_frames()[:P].astype(np.float64)
+    elif name == "ala":
+        X = ts.alanine_dipeptide_shaped_ensemble(P, seed=1).astype(np.float32).astype(np.float64)
+    else:
+        X = np.repeat(hybrid_positions(name)[None], P, 0).astype(np.float32).astype(np.float64)
+    return o, spec, hh.HostSystem(spec), X
+
+
+@pytest.mark.parametrize("name,T", [("fluorobenzene", 2), ("fluorobenzene", 4), ("ethylbenzene", 4), ("ala", 4), ("ala", 8)])
+def test_team_baoab_matches_oracle(name, T):
+    o, spec, hs, X = _setup(name)
+    P = X.shape[0]
+    lam = relative_lambdas(0.3)
+    V = np.random.RandomState(1).normal(0, 0.3, X.shape).astype(np.float32).astype(np.float64)
+    langevin._rattle_v(X, V, 1.0 / o.masses, o.constraints, 1e-6)
+    V = V.astype(np.float32).astype(np.float64)
+    ref = langevin.baoab(lambda xx: o.energy_forces(xx, lam), X, V, o.masses, o.constraints, 0.002, 1.0, kT, 2, seed=7, gids=np.arange(5, 5 + P), step0=11,
+                         track_works=True)
+    hh.set_team(T)
+    out = hs.smc_propagate(X, V, spec.lambda_vector(lam), 0.002, 1.0, kT, 2, seed=7, step0=11, gid0=5, flags=2, aux=np.full(P, 0.25), cum=np.full(P, 1.5))
+    assert np.abs(out["x"] - ref["x"]).max() < 2e-7
+    assert np.abs(out["v"] - ref["v"]).max() < 2e-5
+    np.testing.assert_allclose(out["u_first"], ref["u_first"] / kT, rtol=1e-12)
+    np.testing.assert_allclose(out["u_last"], ref["u_last"] / kT, atol=2e-4)
+    np.testing.assert_allclose(out["inc"], ref["u_first"] / kT + 0.25, rtol=1e-12)
+    np.testing.assert_allclose(out["shadow"], ref["shadow_work"] / kT, atol=3e-4)
+    np.testing.assert_allclose(out["proposal"], ref["proposal_work"] / kT, atol=2e-5)
+    for (i, j, d) in o.constraints:
+        assert np.abs(np.linalg.norm(out["x"][:, i] - out["x"][:, j], axis=-1) / d - 1).max() < 3e-6
+
+
+@pytest.mark.parametrize("T", [4])
+def test_team_static_cache_and_split_launch(T):
+    """Cached iterations (static + dynamic passes, cache rows through the ancestor) and the OPEN / REST split with a team."""
+    o, spec, hs, X = _setup("fluorobenzene", P=6)
+    P = X.shape[0]
+    V = np.zeros_like(X)
+    lam0, lam1 = (spec.lambda_vector(relative_lambdas(q)) for q in (0.2, 0.3))
+    hh.set_team(T)
+    seed_out = hs.smc_propagate_cached(X, V, lam0, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    anc = np.array([2, 2, 0, 5, 4, 4])
+    kw = dict(anc=anc, aux=-seed_out["u_first"], cum=np.zeros(P), cache=seed_out["cache"])
+    cached = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1, **kw)
+    plain = hs.smc_propagate(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1, anc=anc, aux=-seed_out["u_first"], cum=np.zeros(P))
+    for k, tol in (("x", 2e-7), ("v", 2e-5), ("u_first", 1e-10), ("u_last", 2e-4), ("inc", 1e-9)):
+        assert np.abs(cached[k] - plain[k]).max() <= tol, k
+    first = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1 | _lib.CDW_FLAG_PHASE_OPEN, **kw)
+    rest = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1 | _lib.CDW_FLAG_PHASE_REST, handover=first["handover"], **kw)
+    np.testing.assert_array_equal(first["w"], cached["w"])
+    for k in ("x", "v", "aux", "u_last"):
+        np.testing.assert_array_equal(rest[k], cached[k])
+    np.testing.assert_array_equal(rest["cache"][0], cached["cache"][0])
+    # the oracle, too
+    ref = langevin.baoab(lambda xx: o.energy_forces(xx, relative_lambdas(0.3)), X[anc], V[anc], o.masses, o.constraints, 0.002, 1.0, kT, 1, seed=7,
+                         gids=np.arange(P), step0=1, randomize_velocities=True)
+    assert np.abs(cached["x"] - ref["x"]).max() < 2e-7
+
+
+def test_team_ula_matches_oracle():
+    o, spec, hs, X = _setup("fluorobenzene", P=5)
+    P = X.shape[0]
+    lam = relative_lambdas(0.3)
+    ref = ula.ula(lambda xx: o.energy_forces(xx, lam), X, o.masses, o.constraints, 0.0005, kT, 2, seed=7, gids=np.arange(5, 5 + P), step0=11)
+    hh.set_team(4)
+    out = hs.smc_propagate(X, None, spec.lambda_vector(lam), 0.0005, 0.0, kT, 2, seed=7, step0=11, gid0=5, flags=_lib.CDW_FLAG_ULA, aux=np.full(P, 0.25),
+                           cum=np.full(P, 1.5))
+    assert np.abs(out["x"] - ref["x"]).max() < 2e-7
+    np.testing.assert_allclose(out["proposal"], ref["proposal_work"], atol=2e-4)
+    np.testing.assert_allclose(out["inc"], out["u_last"] + 0.25 + out["proposal"], rtol=1e-12)
+
+
+def test_team_sizes_agree_with_each_other():
+    """Only the summation order changes with the team size: one fp32 ulp in the coordinates, 1e-14 in the energies."""
+    o, spec, hs, X = _setup("ala", P=3)
+    V = np.zeros_like(X)
+    lam = spec.lambda_vector(relative_lambdas(0.4))
+    outs = {}
+    for T in (1, 2, 4, 8):
+        hh.set_team(T)
+        outs[T] = hs.smc_propagate(X, V, lam, 0.002, 1.0, kT, 1, seed=3, step0=2, flags=1, aux=np.zeros(3), cum=np.zeros(3))
+    for T in (2, 4, 8):
+        assert np.abs(outs[T]["x"] - outs[1]["x"]).max() < 2e-7
+        np.testing.assert_allclose(outs[T]["u_first"], outs[1]["u_first"], rtol=1e-13)
+        np.testing.assert_allclose(outs[T]["u_last"], outs[1]["u_last"], atol=2e-4)
