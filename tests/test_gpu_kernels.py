@@ -274,3 +274,34 @@ def test_cooperative_resample_statistics_follow_the_canonical_order(gpu, n, kind
     np.testing.assert_allclose(cum.cpu().numpy(), np.full(n, s[_lib.STAT_MEAN]), rtol=1e-15, atol=1e-15)
     assert int(ws.wmin_key.item()) == -1                     # re-armed
     assert int(ws.buf[4].item()) == 0 and int(ws.buf[5].item()) == 0   # team counters back at rest
+
+
+@pytest.mark.parametrize("n,kind", [(50000, 0), (50000, 1), (100003, 0)])
+def test_multi_kernel_resample_draws_its_own_uniforms(gpu, n, kind):
+    """cdw_smc_resample above 24 576 particles (statistics + scan + a search / emit kernel that draws the Philox uniforms
+    itself and re-arms the key): the uniforms are the documented counter-based stream and the ancestors are the oracle's."""
+    import ctypes as C
+    from coddiwomple_b200 import kernels
+    lib = _lib.load()
+    W_host = np.random.RandomState(n + kind).normal(0.0, 1.5, n)
+    W = torch.as_tensor(W_host).cuda()
+    ws = kernels.WeightWorkspace(n)
+    ws.wmin_key.fill_(-1)
+    Wc = torch.empty_like(W)
+    _lib.check(lib.cdw_weight_update(_lib.ptr(W), None, None, None, n, None, _lib.ptr(Wc), _lib.ptr(ws.wmin_key), _lib.current_stream()))
+    cum = torch.zeros_like(W)
+    anc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    u = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for rep in range(2):   # twice on the same workspace: the kernels leave it at rest
+        _lib.check(lib.cdw_smc_resample(kind, _lib.ptr(W), n, -1.0, _lib.ptr(ws.wmin_key), C.c_uint64(11), C.c_uint64(3 + rep), _lib.ptr(ws.stats),
+                                        _lib.ptr(cum), _lib.ptr(cum), _lib.ptr(anc), _lib.ptr(ws.cdf), _lib.ptr(u), _lib.ptr(ws.buf), ws.bytes,
+                                        _lib.current_stream()))
+        assert int(ws.wmin_key.item()) == -1
+        _lib.check(lib.cdw_weight_update(_lib.ptr(W), None, None, None, n, None, _lib.ptr(Wc), _lib.ptr(ws.wmin_key), _lib.current_stream()))
+        uni = u.cpu().numpy()
+        n_u = n if kind == 0 else 1
+        np.testing.assert_array_equal(uni[:n_u], rng.uniforms53(11, n_u, stream=3 + rep))
+        ref = resampling.ancestors(W_host, uni if kind == 0 else None, kind="multinomial" if kind == 0 else "systematic", u0=None if kind == 0 else uni[0])
+        np.testing.assert_array_equal(anc.cpu().numpy(), ref)
+    s = ws.stats.cpu().numpy()
+    assert s[_lib.STAT_NESS] == pytest.approx(weights.nESS(W_host), rel=1e-12)
