@@ -182,3 +182,20 @@ def test_ordered_key_is_monotone():
     hh.lib().hh_ordered_key(x.ctypes.data_as(C.c_void_p), C.c_int64(len(x)), key.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p))
     assert np.all(np.diff(key.astype(object)) >= 0)
     np.testing.assert_array_equal(back, x)
+
+
+def test_harmonic_oscillator_equilibrium_statistics_on_the_host():
+    """G6 on the build box (coddiwomple/tests/test_openmm.py:192-221 re-expressed): BAOAB on the 3-d harmonic oscillator samples
+    <u> = 3/2 with std sqrt(3/2); the accumulated shadow work stays small and the heat is an O(1)-per-step quantity."""
+    xml = ts.harmonic_oscillator_xml()
+    o, spec, hs = _pair(xml)
+    prm = ts.harmonic_oscillator_parameters()
+    P = 1500
+    X = np.zeros((P, 1, 3))
+    lam = spec.lambda_vector(ts.harmonic_parameter_sequence(2)[0])
+    out = hs.smc_propagate(X, None, lam, prm["timestep"], prm["collision_rate"], kT, 400, seed=11, step0=0, flags=3)
+    u = o.reduced_potential(out["x"], ts.harmonic_parameter_sequence(2)[0])
+    assert abs(u.mean() - 1.5) < 6 * np.sqrt(1.5 / P) + 0.02          # dt = period / 20 biases <u> by ~1 %
+    assert abs(u.std() - np.sqrt(1.5)) < 0.1
+    assert np.all(np.isfinite(out["shadow"])) and abs(out["shadow"].mean()) < 0.2
+    assert not out["nan"].any()
