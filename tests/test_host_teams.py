@@ -108,3 +108,36 @@ def test_team_sizes_agree_with_each_other():
         assert np.abs(outs[T]["x"] - outs[1]["x"]).max() < 2e-7
         np.testing.assert_allclose(outs[T]["u_first"], outs[1]["u_first"], rtol=1e-13)
         np.testing.assert_allclose(outs[T]["u_last"], outs[1]["u_last"], atol=2e-4)
+
+
+def test_whole_anneal_on_the_host_tracks_the_oracle():
+    """The full loop semantics without a GPU: device lane code (team of 4, static-term cache carried from iteration to
+    iteration, gather through the ancestors) + the oracle's resampling step, against oracle.smc.anneal on the same seeds."""
+    from oracle import rng, smc as oracle_smc, weights
+    o, spec, hs, _ = _setup("fluorobenzene", P=1)
+    P = 48
+    frames = cache_frames()
+    x0 = frames[np.random.RandomState(1).randint(0, len(frames), P)].astype(np.float64)
+    seq = ts.relative_alchemical_sequence(6)
+    trace = []
+    ref = oracle_smc.anneal(o, x0, seq, seed=5, resample_seed=6, trace=trace, floor_threshold=0.9)
+    hh.set_team(4)
+    X, V = x0.copy(), np.zeros_like(x0)
+    seed_out = hs.smc_propagate_cached(X, V, spec.lambda_vector(seq[0]), 0.002, 1.0, kT, 0, seed=5, step0=0)
+    aux, cum, cache, anc = -seed_out["u_first"], np.zeros(P), seed_out["cache"], None
+    labels = np.arange(P)
+    for t in range(1, len(seq)):
+        out = hs.smc_propagate_cached(X, V, spec.lambda_vector(seq[t]), 0.002, 1.0, kT, 1, seed=5, step0=t, flags=1 if t == 1 else 0, anc=anc,
+                                      aux=aux, cum=cum, cache=cache)
+        if anc is not None:
+            labels = labels[anc]
+        step = weights.resample_step(cum, out["inc"], out["aux"], labels, uniforms=rng.uniforms53(6, P, stream=t), kind="multinomial", floor_threshold=0.9)
+        if t == 1:
+            np.testing.assert_allclose(out["inc"], trace[0]["inc"], rtol=1e-10)
+            np.testing.assert_array_equal(step["ancestors"], trace[0]["ancestors"])
+        X, V, aux, cache = out["x"], out["v"], out["aux"], out["cache"]
+        cum, anc = step["cum"], (step["ancestors"] if step["resampled"] else None)
+        # aux travels with the particle: resample_step already returned it gathered; the rows are gathered by the next call
+        aux = out["aux"]
+    fe = weights.free_energy(cum)
+    assert abs(fe - ref["free_energy"]) < 0.1, (fe, ref["free_energy"])
