@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcdw_b200.so")
 SOURCES = ["cdw_system.cu", "cdw_propagate.cu", "cdw_weights.cu"]
-HEADERS = ["cdw_common.h", "cdw_math.cuh", "cdw_lane.cuh", "cdw_pack.h", os.path.join("..", "..", "include", "cdw.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "cdw.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-ffp-contract=off"]
 

@@ -214,8 +214,10 @@ static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t 
     // the opening evaluation) and room for the statistics scratch in the CTA's shared memory
     static const bool no_inline = getenv("CDW_NO_INLINE_RESAMPLE") != nullptr;
     const int roles = kVirtualThreads / (small ? 128 : 256);
+    // (the resample role assumes blockDim == the kernel's MAXT: teams of 1 or 2 lanes launch 32- / 64-thread CTAs and take the
+    // separate cdw_smc_resample launch instead)
     const bool fuse = a.rs.enabled && forces && !no_inline && !(a.flags & CDW_FLAG_ULA) && need + roles <= cap && a.n < (1ll << 30) &&
-                      L.total >= sizeof(unsigned long long) * 3 * kVirtualThreads;
+                      nthr == (small ? 128 : 256) && L.total >= sizeof(unsigned long long) * 3 * kVirtualThreads;
     a.rs.enabled = fuse ? 1 : 0;
     if (fuse) { grid = (int)need + roles; a.rs.n_main = (unsigned)need; }
     if (forces && small && dense)

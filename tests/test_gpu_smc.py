@@ -71,6 +71,31 @@ def test_first_iterations_track_the_oracle_anneal():
     assert abs(eng.free_energy() - out["free_energy"]) < 0.05
 
 
+def test_config2_system_tracks_the_oracle_anneal():
+    """The 22-atom AlanineDipeptideVacuum-shaped system of BASELINE configs[1] (team of 4 lanes, static-term cache on):
+    the GPU anneal and oracle.smc.anneal (order of openmm/coddiwomple.py:312-331) run on the same particles with the
+    same Philox counters: first-iteration incremental works at 1e-10, first ancestors bit-exact, second-iteration works
+    at the fp32-coordinate level, and free energies equal within statistical error at matched P."""
+    xml, _ = ts.alanine_dipeptide_shaped_xml()
+    P = 384
+    x0 = ts.alanine_dipeptide_shaped_ensemble(P, seed=7)
+    seq = ts.relative_alchemical_sequence(16)
+    o = XmlSystemOracle(xml)
+    for kind in ("multinomial", "systematic"):
+        eng = _engine(xml, P, seq, seed=5, resample_seed=6, resampler=kind, record_history=True)
+        eng.anneal(x0)
+        trace = []
+        out = oracle_smc.anneal(o, x0, seq, seed=5, resample_seed=6, resampler=kind, trace=trace)
+        h = eng.ensemble.history
+        np.testing.assert_allclose(h[0]["inc"].cpu().numpy(), trace[0]["inc"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_array_equal(h[0]["anc"].cpu().numpy(), trace[0]["ancestors"])
+        if not trace[0]["resampled"]:
+            np.testing.assert_allclose(h[1]["inc"].cpu().numpy(), trace[1]["inc"], atol=2e-4)
+        # the statistical error of the estimate at this P is ~0.1 kT; both runs share particles, noise and uniforms
+        assert abs(eng.free_energy() - out["free_energy"]) < 0.1, (eng.free_energy(), out["free_energy"])
+        assert int(eng.ensemble.nan_flags.sum()) == 0
+
+
 def test_harmonic_oscillator_free_energy_is_one_kT():
     """G6: x0 0 -> 2 sigma, U0 0 -> 1 kT gives Delta F = 1 kT exactly (coddiwomple/tests/utils.py:63-67); config 1."""
     from coddiwomple_b200.engine import LangevinParameters
@@ -384,6 +409,31 @@ def test_one_launch_iteration_equals_two_launches(kind, P):
         assert len(eng.resampled_iterations()) >= 2
     for a, b in zip(*runs):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("team", [1, 2, 8])
+def test_in_launch_resampling_with_other_team_sizes(team, tmp_path):
+    """CDW_TEAM = 1, 2 (32- / 64-thread CTAs: the in-launch resampling role is not available, cdw_smc_iteration must fall back
+    to the separate launch) and 8 (256-thread CTAs, four role CTAs): statistics, ancestors and state equal the run that never
+    resamples in-launch (CDW_NO_INLINE_RESAMPLE), bit for bit."""
+    import os
+    import subprocess
+    import sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "team_probe.py")
+    outs = []
+    for no_inline in (False, True):
+        env = dict(os.environ, CDW_TEAM=str(team))
+        env.pop("CDW_NO_INLINE_RESAMPLE", None)
+        if no_inline:
+            env["CDW_NO_INLINE_RESAMPLE"] = "1"
+        out = str(tmp_path / f"team{team}_{int(no_inline)}.npz")
+        subprocess.run([sys.executable, probe, out], env=env, check=True, timeout=600)
+        outs.append(np.load(out))
+    for k in outs[0].files:
+        np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
+    stats = outs[0]["stats"]
+    assert stats[1:, _lib.STAT_RESAMPLE].sum() >= 2 and np.all(stats[1:, _lib.STAT_NESS] > 0)
+    assert outs[0]["anc"].min() >= 0 and outs[0]["anc"].max() < 3000
 
 
 @pytest.mark.parametrize("P", [1, 2, 5, 33])

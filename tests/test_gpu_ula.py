@@ -47,12 +47,14 @@ def _propagate(xml, X, lam, dt, n_steps, seed, step0, gid0, aux, cum):
     return out
 
 
-@pytest.mark.parametrize("name,n_steps,P", [("fluorobenzene", 1, 100), ("fluorobenzene", 3, 37), ("ethylbenzene", 2, 64)])
+@pytest.mark.parametrize("name,n_steps,P", [("fluorobenzene", 1, 100), ("fluorobenzene", 3, 37), ("ethylbenzene", 2, 64), ("ala", 1, 64), ("ala", 4, 33)])
 def test_kernel_matches_oracle(name, n_steps, P):
-    xml = system_xml(name)
+    xml = ts.alanine_dipeptide_shaped_xml()[0] if name == "ala" else system_xml(name)
     o = XmlSystemOracle(xml)
     if name == "fluorobenzene":
         X = cache_frames()[np.random.RandomState(0).randint(0, 151, P)].astype(np.float64)
+    elif name == "ala":
+        X = ts.alanine_dipeptide_shaped_ensemble(P).astype(np.float64)
     else:
         X = np.repeat(hybrid_positions(name)[None], P, 0).astype(np.float32).astype(np.float64)
     lam = relative_lambdas(0.3)
