@@ -11,8 +11,6 @@ LIB_PATH = os.environ.get("CDW_LIB") or os.path.join(HERE, "libcdw_b200.so")  # 
 CDW_FLAG_RANDOMIZE_VELOCITIES = 1
 CDW_FLAG_TRACK_WORKS = 2
 CDW_FLAG_ULA = 4
-CDW_FLAG_PHASE_OPEN = 8
-CDW_FLAG_PHASE_REST = 16
 CDW_RESAMPLE_MULTINOMIAL = 0
 CDW_RESAMPLE_SYSTEMATIC = 1
 STAT_WMIN, STAT_SUM_E, STAT_SUM_E2, STAT_NESS, STAT_MEAN, STAT_RESAMPLE, STAT_TOTAL, STAT_NNAN = range(8)
@@ -47,16 +45,15 @@ class LangevinParams(C.Structure):
 class StaticCache(C.Structure):
     """struct cdw_static_cache (include/cdw.h): static-term forces / energies at the input and output rows."""
     _fields_ = [("force_in", C.c_void_p), ("energy_in", C.c_void_p), ("force_out", C.c_void_p), ("energy_out", C.c_void_p),
-                ("peer_force_in", C.c_void_p), ("peer_energy_in", C.c_void_p), ("force_open", C.c_void_p), ("u_open", C.c_void_p)]
+                ("peer_force_in", C.c_void_p), ("peer_energy_in", C.c_void_p)]
 
 
 def _addr(t):
     return None if t is None else (t.data_ptr() if hasattr(t, "data_ptr") else int(t))
 
 
-def static_cache(force_in, energy_in, force_out, energy_out, peer_force_in=None, peer_energy_in=None, force_open=None, u_open=None):
-    return StaticCache(_addr(force_in), _addr(energy_in), _addr(force_out), _addr(energy_out), _addr(peer_force_in), _addr(peer_energy_in),
-                       _addr(force_open), _addr(u_open))
+def static_cache(force_in, energy_in, force_out, energy_out, peer_force_in=None, peer_energy_in=None):
+    return StaticCache(_addr(force_in), _addr(energy_in), _addr(force_out), _addr(energy_out), _addr(peer_force_in), _addr(peer_energy_in))
 
 
 def make_desc(spec):
@@ -109,9 +106,10 @@ _SIGNATURES = {
                                     C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cdw_smc_propagate_cached": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64,
                                            C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), _P]),
-    "cdw_smc_iteration": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64, C.c_int64,
-                                    _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), C.c_int, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P,
-                                    C.c_size_t, _P]),
+    "cdw_smc_lookahead": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64, C.c_uint64, C.c_int64,
+                                    _P, _P, _P, _P, _P]),
+    "cdw_smc_lookahead_sharded": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams),
+                                            C.c_uint64, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P]),
     "cdw_smc_propagate_sharded_cached": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams),
                                                    C.c_uint64, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P, C.POINTER(StaticCache), _P]),
     "cdw_smc_propagate_sharded": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(LangevinParams), C.c_uint64,
@@ -122,8 +120,11 @@ _SIGNATURES = {
     "cdw_weight_stats": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, _P, C.c_size_t, _P]),
     "cdw_resample_indices": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "cdw_smc_resample": (C.c_int, [C.c_int, _P, C.c_int64, C.c_double, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "cdw_smc_weigh_resample": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_double, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "cdw_gather_particles": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "cdw_gather_particles_peer": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "cdw_record_lineage": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
+    "cdw_peer_barrier": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "cdw_fill_u64": (C.c_int, [_P, C.c_uint64, C.c_int64, _P]),
     "cdw_philox_uniforms": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, _P, _P]),
     "cdw_ipc_get_handle": (C.c_int, [_P, _P]),

@@ -31,6 +31,11 @@
 #pragma once
 #include "cdw_math.cuh"
 
+#if defined(__CUDACC__)
+#define CDW_NOINLINE_HD __host__ __device__ __noinline__
+#else
+#define CDW_NOINLINE_HD
+#endif
 #if defined(__CUDA_ARCH__)
 #define CDW_CTA_THREADS(tid, nt) for (int tid = (int)threadIdx.x, nt = (int)blockDim.x, _cdw_once = 1; _cdw_once; _cdw_once = 0, __syncthreads())
 #define CDW_LDG(p) __ldg(p)
@@ -118,15 +123,9 @@ struct Tables {  // pointers into the CTA-shared tables
     int* cl_start; int* cons_atoms; double* cons_d2; int* cl_coef_start; double* cl_coef;
 };
 
-struct CtaSignal {  // shared memory, one per CTA
-    unsigned long long min_key;  // running min of the order-preserving keys of this CTA's weights
-    unsigned int warps_done, n_warps;
-};
-
 struct LaneMem {  // this thread's view of its replica's columns
     float* x; float* v; float* f; float* r0;
     long long* src; int* bad;
-    struct CtaSignal* sig;  // in-launch resampling: where this CTA collects "my weights are final" (NULL otherwise)
     int rid;           // this replica's column (0 .. kR-1)
     int T, tl, sw;     // team size, lane within the team, bank rotation (32 / T, 0 on the host)
     unsigned mask;     // lanes of this warp whose replica is valid
@@ -148,7 +147,6 @@ CDW_HD LaneMem lane_pointers(const Layout& L, unsigned char* smem, int T, int ti
     M.src = (long long*)(smem + L.src); M.bad = (int*)(smem + L.bad);
     M.T = T; M.rid = tid / T; M.tl = tid - M.rid * T; M.sw = kR > 1 ? 32 / T : 0;
     M.mask = 0xffffffffu;
-    M.sig = nullptr;
     return M;
 }
 
@@ -164,7 +162,7 @@ CDW_HD double team_sum(const LaneMem& M, double v) {
 
 // ------------------------------------------------------------------------------------------------ prologue (once per CTA)
 // Resolve the lambda vector into effective term records: the per-replica code never touches lambda again.
-CDW_HD void build_tables(const SysDev& s, const Tables& T, const double* lam_g, double kT, bool forces) {
+CDW_NOINLINE_HD inline void build_tables(const SysDev& s, const Tables& T, const double* lam_g, double kT, bool forces) {
     CDW_CTA_THREADS(tid, nt) {
         for (int q = tid; q < s.n_lambda; q += nt) T.lam[q] = lam_g[q];
     }
@@ -394,6 +392,15 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M, in
     return e;
 }
 
+// One out-of-line copy for callers with several call sites (the look-ahead kernel evaluates in part A and in part B): the body is
+// ~1.5 k SASS instructions, and the instruction cache is what an SM with four resident CTAs of this kernel runs out of first.
+// (-DCDW_ENERGY_INLINE builds the fully inlined variant for A/B timing.)
+#if defined(CDW_ENERGY_INLINE)
+CDW_HD double lane_energy_forces(const SysDev& s, const Tables& T, const LaneMem& M, int part) { return lane_energy<true>(s, T, M, part); }
+#else
+CDW_NOINLINE_HD inline double lane_energy_forces(const SysDev& s, const Tables& T, const LaneMem& M, int part) { return lane_energy<true>(s, T, M, part); }
+#endif
+
 // ------------------------------------------------------------------------------------------------ constraints
 // SHAKE: Gauss-Seidel sweeps per cluster until every distance is inside OpenMM's (1 +- tol)^2 window.  The
 // displacement is applied to x and, divided by the drift time, to v ("v += (x - x1)/(dt/2)", integrators.py:310).
@@ -544,10 +551,11 @@ struct PropArgs {
     // then they are evaluated) and at the OUTPUT rows.  Indexed like pos_in / pos_out (input through the ancestor).
     const float4* fs_in; const double* us_in; float4* fs_out; double* us_out;
     const float4* const* peer_fs; const double* const* peer_us;
-    // split launches (CDW_FLAG_PHASE_OPEN / CDW_FLAG_PHASE_REST): the opening evaluation's total forces and energy, handed from
-    // the first launch to the second through HBM, indexed by the LOCAL slot (they are already gathered)
-    float4* f_open; double* u_open;
-    ResampleArgs rs;  // rs.enabled: the last CTA of the launch resamples as soon as every weight is final (cdw_smc_iteration)
+    // look-ahead iteration (cdw_smc_lookahead, smc_lookahead_kernel): fs_in / peer_fs rows hold the TOTAL forces F(x_{t-1}; lambda_t) of the
+    // input rows, fs_out receives F(x_t; lambda_{t+1}); lambda_next / tables_next describe lambda_{t+1} (NULL on the last iteration) and
+    // inc_next_out[p] = u_{t+1}(x_t) - u_t(x_t), the incremental work of the NEXT iteration (distribution_factories.py:124-129)
+    const double* lambda_next; const unsigned char* tables_next; double* inc_next_out;
+    int have_next;  // part B runs (lambda_next may still be NULL for a system without global parameters)
 };
 
 // where row `src` (a global particle id when the run is sharded) lives
@@ -588,8 +596,7 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
     // wait_all before the CTA barrier.
     CDW_CTA_THREADS(tid, nt) {
         float* Fc = (float*)(smem + L.f);
-        const bool rest = with_v && (a.flags & CDW_FLAG_PHASE_REST) != 0;   // the opening evaluation's forces come from the first launch
-        const bool with_f = with_v && a.fs_in != nullptr && !rest;
+        const bool with_f = with_v && a.fs_in != nullptr;
         for (int idx = tid; idx < count * A; idx += nt) {
             const int r = idx / A, at = idx - r * A;
             const long long src = with_v ? SRC[r] : p0 + r;
@@ -599,8 +606,7 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
                 if (a.vel_in) cdw_copy3(V, b, (const float*)(row_ptr(a, a.vel_in, a.peer_vel, src, A) + at));
                 else { V[b] = 0.f; V[b + kR] = 0.f; V[b + 2 * kR] = 0.f; }
             }
-            if (with_f) cdw_copy3(Fc, b, (const float*)(row_ptr(a, a.fs_in, a.peer_fs, src, A) + at));  // static forces of the ancestor's coordinates -> copy 0
-            if (rest) cdw_copy3(Fc, b, (const float*)(a.f_open + (p0 + r) * A + at));
+            if (with_f) cdw_copy3(Fc, b, (const float*)(row_ptr(a, a.fs_in, a.peer_fs, src, A) + at));  // cached forces of the ancestor's coordinates -> copy 0
         }
         cdw_copy_wait();
     }
@@ -637,26 +643,41 @@ CDW_HD void cta_store_rows(const SysDev& s, const PropArgs& a, unsigned char* sm
     }
 }
 
-// In-launch resampling: a warp whose weights are final records their min in the CTA's CtaSignal; the last warp of the
-// CTA folds it into the global running min and bumps the launch-wide counter the resample CTA is waiting on.
-CDW_HD void lane_signal_weights(const LaneMem& M, const PropArgs& a, unsigned long long key) {
-#if defined(__CUDA_ARCH__)
-    if (!M.sig) return;
-    __threadfence();  // this lane's inc_out / w_out stores, before the counter moves
-    if (key != ~0ull) atomicMin(&M.sig->min_key, key);
-    __syncwarp(M.mask);
-    if ((threadIdx.x & 31) == 0) {  // valid lanes are a prefix of the warp: lane 0 is in every non-empty warp
-        const unsigned int before = atomicAdd(&M.sig->warps_done, 1u);
-        if (before + 1 == M.sig->n_warps) {
-            __threadfence();
-            atomicMin(a.wmin_key, atomicMin(&M.sig->min_key, ~0ull));
-            __threadfence();
-            atomicAdd(a.rs.done, 1u);
-        }
+// ------------------------------------------------------------------------------------------------ integrator sub-steps
+// V : v += h f / m                                                  (integrators.py:317-336)
+CDW_HD void lane_kick(const SysDev& s, const Tables& T, const LaneMem& M, double h) {
+    CDW_UNPACK(M);
+    for (int at = tl; at < s.n_atoms; at += T_) {
+        const int b = CDW_BASE(at);
+        st3(M.v, b, ld3(M.v, b) + (h * T.inv_m[at]) * ld3(M.f, b));
     }
-#else
-    (void)M; (void)a; (void)key;
-#endif
+}
+// R : x += h v ; SHAKE ; v += (x - x1) / h                          (integrators.py:297-315)
+CDW_HD void lane_drift(const SysDev& s, const Tables& T, const LaneMem& M, double h, double tol) {
+    CDW_UNPACK(M);
+    for (int q = tl; q < s.n_cons; q += T_) {  // constraint vectors before the drift (fp32 differences)
+        const int bi = CDW_BASE(T.cons_atoms[2 * q]), bj = CDW_BASE(T.cons_atoms[2 * q + 1]), bq = CDW_BASE(q);
+        M.r0[bq] = M.x[bi] - M.x[bj]; M.r0[bq + kR] = M.x[bi + kR] - M.x[bj + kR]; M.r0[bq + 2 * kR] = M.x[bi + 2 * kR] - M.x[bj + 2 * kR];
+    }
+    CDW_TEAM_SYNC(M);
+    for (int at = tl; at < s.n_atoms; at += T_) {
+        const int b = CDW_BASE(at);
+        st3(M.x, b, ld3(M.x, b) + h * ld3(M.v, b));
+    }
+    CDW_TEAM_SYNC(M);
+    if (s.n_cons) lane_shake(s, T, M, tol, 1.0 / h);
+}
+// O : v = cv v + cn sqrt(kT/m) xi, xi = Philox(seed; gid, step, atom, kind)   (integrators.py:338-350; cv = 0, cn = 1: Maxwell-Boltzmann)
+CDW_HD void lane_noise(const SysDev& s, const Tables& T, const LaneMem& M, double cv, double cn, unsigned long long seed, unsigned long long gid,
+                       uint32_t step, uint32_t kind) {
+    CDW_UNPACK(M);
+    for (int at = tl; at < s.n_atoms; at += T_) {
+        double z0, z1, z2;
+        normals3(seed, gid, step, (uint32_t)at, kind, z0, z1, z2);
+        const int b = CDW_BASE(at);
+        const double sg = cn * T.sig_v[at];
+        st3(M.v, b, cv * ld3(M.v, b) + sg * mk3(z0, z1, z2));
+    }
 }
 
 // K4 body (+ first half of K2) for the replica already staged in this team's column.
@@ -700,15 +721,10 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         if (a.label_in) label = a.label_in[src];
     }
     if (cached_open) Us = a.peer_pos ? a.peer_us[src / a.n_per_rank][src % a.n_per_rank] : a.us_in[src];
-    // split launches: PHASE_OPEN stops after the opening evaluation (weights, total forces and energy out); PHASE_REST
-    // resumes behind it with those forces preloaded in force copy 0
-    const bool phase_open = (a.flags & CDW_FLAG_PHASE_OPEN) != 0, phase_rest = (a.flags & CDW_FLAG_PHASE_REST) != 0;
-    const int n_ops = phase_open ? n_open : n_open + n_body * a.n_steps;
-    if (phase_rest) U = u_first = a.u_open[p];
+    const int n_ops = n_open + n_body * a.n_steps;
     // op -1 (only with RANDOMIZE): Context.setVelocitiesToTemperature (propagators.py:137-138)
-    for (int op = (!ula && !phase_open && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0; op < n_ops; ++op) {
+    for (int op = (!ula && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0; op < n_ops; ++op) {
         int kind, slot = 0, st = 0, part = PART_ALL;
-        if (phase_rest && op >= 0 && op < n_open) continue;
         if (op < 0) kind = OP_MB;
         else if (op < n_open) {
             kind = OP_E;
@@ -737,15 +753,13 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
             if (op < n_open) {
                 u_first = U;
                 if (!ula) {
-                    // MCMC move: work_inc = u_t(x_{t-1}) - u_{t-1}(x_{t-1}) (distribution_factories.py:98-131) is final as soon as the
-                    // opening evaluation is: publish W now, so that the resampling can overlap the integration
+                    // MCMC move: work_inc = u_t(x_{t-1}) - u_{t-1}(x_{t-1}) (distribution_factories.py:98-131)
                     inc = u_first * inv_kT + aux;
                     w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
                     if (tl == 0) {
                         if (a.inc_out) a.inc_out[p] = inc;
                         if (a.w_out) a.w_out[p] = w;
                     }
-                    lane_signal_weights(M, a, tl == 0 ? ordered_key(w) : ~0ull);
                 }
             } else if (track) shadow += pending + U;  // closes the second R of the step: (KE + U_new) - (KE_old + U_mid)
             continue;
@@ -788,33 +802,11 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
             continue;
         }
         const double ke_before = track ? lane_kinetic(s, T, M) : 0.0;
-        if (kind == OP_V) {
-            for (int at = tl; at < A; at += T_) {
-                const int b = CDW_BASE(at);
-                st3(M.v, b, ld3(M.v, b) + (h * T.inv_m[at]) * ld3(M.f, b));
-            }
-        } else if (kind == OP_R) {
-            for (int q = tl; q < s.n_cons; q += T_) {  // constraint vectors before the drift (fp32 differences)
-                const int bi = CDW_BASE(T.cons_atoms[2 * q]), bj = CDW_BASE(T.cons_atoms[2 * q + 1]), bq = CDW_BASE(q);
-                M.r0[bq] = M.x[bi] - M.x[bj]; M.r0[bq + kR] = M.x[bi + kR] - M.x[bj + kR]; M.r0[bq + 2 * kR] = M.x[bi + 2 * kR] - M.x[bj + 2 * kR];
-            }
-            CDW_TEAM_SYNC(M);
-            for (int at = tl; at < A; at += T_) {
-                const int b = CDW_BASE(at);
-                st3(M.x, b, ld3(M.x, b) + h * ld3(M.v, b));
-            }
-            CDW_TEAM_SYNC(M);
-            if (s.n_cons) lane_shake(s, T, M, a.tol, 1.0 / h);
-        } else {  // OP_O / OP_MB: fresh Gaussian noise, counter = (seed; gid, step, atom, kind)
+        if (kind == OP_V) lane_kick(s, T, M, h);
+        else if (kind == OP_R) lane_drift(s, T, M, h, a.tol);
+        else {  // OP_O / OP_MB: fresh Gaussian noise, counter = (seed; gid, step, atom, kind)
             const bool mb = kind == OP_MB;
-            const double cv = mb ? 0.0 : ca, cn = mb ? 1.0 : cb;
-            for (int at = tl; at < A; at += T_) {
-                double z0, z1, z2;
-                normals3(a.seed, gid, (uint32_t)(a.step0 + st), (uint32_t)at, mb ? CDW_KIND_MAXWELL_BOLTZMANN : CDW_KIND_O_STEP, z0, z1, z2);
-                const int b = CDW_BASE(at);
-                const double sg = cn * T.sig_v[at];
-                st3(M.v, b, cv * ld3(M.v, b) + sg * mk3(z0, z1, z2));
-            }
+            lane_noise(s, T, M, mb ? 0.0 : ca, mb ? 1.0 : cb, a.seed, gid, (uint32_t)(a.step0 + st), mb ? CDW_KIND_MAXWELL_BOLTZMANN : CDW_KIND_O_STEP);
         }
         CDW_TEAM_SYNC(M);
         if (s.n_cons) lane_rattle(s, T, M, a.tol);
@@ -828,14 +820,6 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                 U = U_mid;
             } else pending = ke_after - (ke_before + U);                         // second R: U here is U_mid; closed by the next E
         }
-    }
-    if (phase_open) {  // hand the opening evaluation over to the PHASE_REST launch
-        for (int at = tl; at < A; at += T_) {
-            const int b = CDW_BASE(at);
-            a.f_open[p * A + at] = make_float4(M.f[b], M.f[b + kR], M.f[b + 2 * kR], 0.f);
-        }
-        if (tl == 0) a.u_open[p] = u_first;
-        return ordered_key(w);
     }
     const double u_last = U;
     const double fin = ula ? u_last + proposal : u_last;
@@ -865,6 +849,152 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
         }
     }
     return ordered_key(w);
+}
+
+// ------------------------------------------------------------------------------------------------ look-ahead iteration
+// One SMC iteration with the weights of the NEXT iteration as a by-product (cdw_smc_lookahead).  For an MCMC move the incremental
+// work of iteration t + 1 is u_{t+1}(x_t) - u_t(x_t) (distribution_factories.py:124-129 with the aux mechanism of
+// openmm/coddiwomple.py:326-327): both energies are taken at the coordinates this launch ends with, so the launch that makes x_t
+// can also deliver it, and the resampling of iteration t + 1 then runs BESIDE the launch of iteration t + 1 instead of between two
+// launches.  The evaluation that used to open launch t + 1 (forces at lambda_{t+1}) closes launch t instead; the forces travel
+// with the particle (one float4 row, gathered through the same ancestor index as x and v).
+//
+//   part A (tables of lambda_t):      [MB] (V R O R Es Ed V)^n   Es / Ed = static / dynamic terms; Es leaves its forces in fs_out[p]
+//   part B (tables of lambda_{t+1}):  Ed' on top of the static forces  ->  fs_out[p] = F(x_t; lambda_{t+1}),  inc_next
+//
+// A move that ends in a non-finite energy is reverted (propagators.py:166-186): the team reloads its input row and evaluates the
+// energies there, so that aux and inc_next are those of the state that is kept.  The redo is decided per WARP (every team of the
+// warp repeats the closing evaluation, which is idempotent for the teams that were fine) so that the team barriers stay uniform.
+struct AheadState {
+    double U_keep, Us;  // u_t at the coordinates that are kept (kJ/mol), and its static part
+    int bad;
+};
+
+CDW_HD void lane_restore_row(const SysDev& s, const LaneMem& M, const PropArgs& a, long long src) {
+    CDW_UNPACK(M);
+    for (int at = tl; at < s.n_atoms; at += T_) {
+        const int b = CDW_BASE(at);
+        const float4 q = row_ptr(a, a.pos_in, a.peer_pos, src, s.n_atoms)[at];
+        M.x[b] = q.x; M.x[b + kR] = q.y; M.x[b + 2 * kR] = q.z;
+        if (a.vel_in) {
+            const float4 w = row_ptr(a, a.vel_in, a.peer_vel, src, s.n_atoms)[at];
+            M.v[b] = w.x; M.v[b + kR] = w.y; M.v[b + 2 * kR] = w.z;
+        }
+    }
+    CDW_TEAM_SYNC(M);
+}
+
+CDW_HD AheadState lane_ahead_main(const SysDev& s, const Tables& T, const LaneMem& M, const PropArgs& a, long long p) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms;
+    const unsigned long long gid = (unsigned long long)(a.gid0 + p);
+    const double h = 0.5 * a.dt;
+    const double ca = exp(-a.gamma * a.dt), cb = sqrt(1.0 - exp(-2.0 * a.gamma * a.dt));
+    enum { OP_V = 0, OP_R = 1, OP_O = 2, OP_ES = 3, OP_ED = 4, OP_MB = 5 };
+    const int n_ops = a.n_steps > 0 ? 7 * a.n_steps : 2;   // (V R O R Es Ed V)^n, or Es Ed alone (the call that equips the initial sample)
+    double U = 0.0, Us = 0.0;
+    bool reverted = false;
+    int was_bad = 0;
+    int op = (a.n_steps > 0 && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) ? -1 : 0;
+    for (;;) {
+        for (; op < n_ops; ++op) {
+            int kind, st = 0;
+            if (op < 0) kind = OP_MB;
+            else if (a.n_steps == 0) kind = op == 0 ? OP_ES : OP_ED;
+            else {
+                const int slot = op % 7;
+                st = op / 7;
+                kind = slot == 0 || slot == 6 ? OP_V : (slot == 1 || slot == 3 ? OP_R : (slot == 2 ? OP_O : (slot == 4 ? OP_ES : OP_ED)));
+            }
+            if (kind == OP_ES || kind == OP_ED) {
+                const double e = lane_energy_forces(s, T, M, kind == OP_ES ? PART_STATIC : PART_DYNAMIC);
+                if (kind == OP_ED) { U = Us + e; continue; }
+                Us = e;
+                if (st == a.n_steps - 1 || a.n_steps == 0) {  // static forces (force copy 0 right now) at the final coordinates: part B starts from them
+                    for (int at = tl; at < A; at += T_) {
+                        const int b = CDW_BASE(at);
+                        a.fs_out[p * A + at] = make_float4(M.f[b], M.f[b + kR], M.f[b + 2 * kR], 0.f);
+                    }
+                }
+                continue;
+            }
+            if (reverted) continue;  // the redo only repeats the closing evaluation
+            if (kind == OP_V) lane_kick(s, T, M, h);
+            else if (kind == OP_R) lane_drift(s, T, M, h, a.tol);
+            else {
+                const bool mb = kind == OP_MB;
+                lane_noise(s, T, M, mb ? 0.0 : ca, mb ? 1.0 : cb, a.seed, gid, (uint32_t)(a.step0 + st), mb ? CDW_KIND_MAXWELL_BOLTZMANN : CDW_KIND_O_STEP);
+            }
+            CDW_TEAM_SYNC(M);
+            if (s.n_cons) lane_rattle(s, T, M, a.tol);
+        }
+        const bool bad = a.n_steps > 0 && !reverted && !(U - U == 0.0);  // NaN or inf
+#if defined(__CUDA_ARCH__)
+        const bool redo = __any_sync(M.mask, bad) != 0;
+#else
+        const bool redo = bad;
+#endif
+        if (bad) {  // (uniform within the team: the team sum leaves the same bits in every lane)
+            was_bad = 1;
+            lane_restore_row(s, M, a, M.src[rid]);
+        }
+        if (!redo) break;
+        reverted = true;
+        op = n_ops - 3;  // Es Ed (V skipped)
+    }
+    AheadState S;
+    S.U_keep = U; S.Us = Us; S.bad = was_bad;
+    return S;
+}
+
+// part B: the dynamic terms at lambda_{t+1} on top of the static forces saved by part A.
+CDW_HD void lane_ahead_next(const SysDev& s, const Tables& T, const LaneMem& M, const PropArgs& a, long long p, const AheadState& S, bool have_next) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms;
+    const double inv_kT = 1.0 / a.kT;
+    const double aux_next = -S.U_keep * inv_kT;  // -u_t(x_t) (openmm/coddiwomple.py:326-327)
+    if (have_next) {
+        for (int at = tl; at < A; at += T_) {  // (each lane reads back the rows it wrote itself)
+            const int b = CDW_BASE(at);
+            const float4 q = a.fs_out[p * A + at];
+            M.f[b] = q.x; M.f[b + kR] = q.y; M.f[b + 2 * kR] = q.z;
+        }
+        const double e = lane_energy_forces(s, T, M, PART_DYNAMIC);
+        for (int at = tl; at < A; at += T_) {
+            const int b = CDW_BASE(at);
+            a.fs_out[p * A + at] = make_float4(M.f[b], M.f[b + kR], M.f[b + 2 * kR], 0.f);
+        }
+        if (tl == 0 && a.inc_next_out) a.inc_next_out[p] = (S.Us + e) * inv_kT + aux_next;  // distribution_factories.py:124-129
+    }
+    if (tl == 0) {
+        if (a.aux_out) a.aux_out[p] = aux_next;
+        if (a.u_last_out) a.u_last_out[p] = S.U_keep * inv_kT;
+        if (a.nan_flags) a.nan_flags[p] = S.bad;
+        if (a.label_out) {
+            const long long src = M.src[rid];
+            int label = (int)src;
+            if (a.peer_pos) {
+                const long long r = src / a.n_per_rank, l = src - r * a.n_per_rank;
+                if (a.peer_label) label = a.peer_label[r][l];
+            } else if (a.label_in) label = a.label_in[src];
+            a.label_out[p] = label;
+        }
+    }
+}
+
+// coalesced store of the rows of a look-ahead launch (reverted replicas were restored on chip: no special case)
+CDW_HD void cta_store_rows_ahead(const SysDev& s, const PropArgs& a, unsigned char* smem, const Layout& L, int sw, long long p0, int count) {
+    const int A = s.n_atoms;
+    const float* X = (const float*)(smem + L.x);
+    const float* V = (const float*)(smem + L.v);
+    CDW_CTA_THREADS(tid, nt) {
+        for (int idx = tid; idx < count * A; idx += nt) {
+            const int r = idx / A, at = idx - r * A;
+            const int b = CDW_BASE_R(at, r);
+            if (a.pos_out) a.pos_out[(p0 + r) * A + at] = make_float4(X[b], X[b + kR], X[b + 2 * kR], 0.f);
+            if (a.vel_out) a.vel_out[(p0 + r) * A + at] = make_float4(V[b], V[b + kR], V[b + 2 * kR], 0.f);
+        }
+    }
 }
 
 }  // namespace cdw

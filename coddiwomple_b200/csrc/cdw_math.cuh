@@ -355,23 +355,4 @@ struct SysDev {
 };
 
 
-// arguments of the one-CTA resampling (cdw_resample.cuh)
-struct ResampleArgs {
-    int enabled;             // resample role present in this launch
-    int kind, n, s1;         // CDW_RESAMPLE_*, particles, first-pass quantisation exponent (61 - ceil(log2 n))
-    double threshold;        // resample iff nESS <= threshold (< 0: always)
-    const double* w;         // [n] cumulative works after the incremental update
-    unsigned long long* wmin_key;
-    unsigned long long seed, stream_id;
-    double* stats;           // [8] (CDW_STAT_*)
-    const double* cum_in; double* cum_out;
-    int* anc;                // [n] out
-    double* uniforms_out;    // [n] (multinomial) / [1] (systematic), may be NULL
-    unsigned long long* cdf_spill;  // [n] global: the cdf (slice-local inclusive prefixes)
-    void* ws;                // weight workspace (cdw_weight_workspace_bytes): scratch of the cooperating CTAs
-    unsigned int* done;      // in-launch use: CTAs whose weights are final
-    unsigned int n_main;     // ... out of this many
-};
-
-
 }  // namespace cdw

@@ -1,6 +1,6 @@
 // cdw_propagate.cu — K1 (batched reduced potential) and K4 (fused SMC propagate: gather-on-load, energy+force,
-// incremental work, BAOAB + SHAKE/RATTLE + Philox, closing energy; optionally the whole SMC iteration with an in-launch
-// resampling team) for sm_100a.
+// incremental work, BAOAB + SHAKE/RATTLE + Philox, closing energy) and the look-ahead iteration (the same, with the evaluation
+// that opens iteration t + 1 moved to the end of launch t: the next weights are a by-product) for sm_100a.
 //
 // Mapping: a TEAM of T lanes per replica (T = 4 for 13-22 atom systems), 32 replica columns per CTA.  The
 // per-replica algorithm lives in cdw_lane.cuh (shared with the host test harness); this file is the kernel shells, the
@@ -11,12 +11,11 @@
 //     index = ancestor), where the state stays on chip for all substeps; every lane of a warp evaluates the same term of
 //     different replicas or, inside a team, the next term of the same replica (no atomics, per-lane fp32 force copies);
 //   * constraints: exact k x k velocity projection and Gauss-Seidel SHAKE per cluster;
-//   * cdw_smc_iteration: the last 8 CTAs of the launch are the resampling team (cdw_resample.cuh).
+//   * smc_lookahead_kernel: a second table image (lambda_{t+1}) replaces the first one on chip before the trailing evaluation.
 #include <stdlib.h>
 
 #include "cdw_common.h"
 #include "cdw_lane.cuh"
-#include "cdw_resample.cuh"
 
 namespace cdw {
 
@@ -62,20 +61,27 @@ __global__ void __launch_bounds__(128) build_tables_kernel(SysDev s, const doubl
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void bulk_load_tables(unsigned char* smem, const unsigned char* src, unsigned bytes, unsigned long long* bar) {
+// One elected thread announces `bytes` and starts the bulk copy.  The barrier is initialised once per CTA (init_table_barrier +
+// __syncthreads); every copy is the next phase of the same barrier (wait_tables takes the phase parity).
+__device__ __forceinline__ void init_table_barrier(unsigned long long* bar) {
     const unsigned b = smem_addr(bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void bulk_load_tables(unsigned char* smem, const unsigned char* src, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = smem_addr(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads/writes of the image area are ordered before the async-proxy writes
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem)), "l"(src), "r"(bytes), "r"(b)
                  : "memory");
 }
 
-__device__ __forceinline__ void wait_tables(unsigned long long* bar) {
+__device__ __forceinline__ void wait_tables(unsigned long long* bar, unsigned parity) {
     const unsigned b = smem_addr(bar);
     unsigned ok = 0;
     while (!ok) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(b) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
     }
 }
 
@@ -89,44 +95,28 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long cta_min[MAXT / 32];
     __shared__ __align__(8) unsigned long long table_bar;
-    __shared__ CtaSignal cta_sig;
     const int T_ = sh.T, sw = 32 / T_;
     const Layout L = make_layout(s, true, kR, T_);
-    constexpr int kRoles = kVirtualThreads / MAXT;  // resample team: kRoles CTAs x MAXT threads = the 1024 virtual threads
-    if (a.rs.enabled && blockIdx.x >= gridDim.x - kRoles) {
-        // resample roles (cdw_smc_iteration): wait until every main CTA has published its weights (they are final right after
-        // the opening evaluation), then do the whole second half of the SMC iteration while the others integrate.  All
-        // CTAs of the launch are co-resident (checked by the host), so the wait cannot starve anyone.
-        if (threadIdx.x == 0) {
-            while (atomicAdd(a.rs.done, 0u) < a.rs.n_main) __nanosleep(200);
-            __threadfence();
-        }
-        __syncthreads();
-        resample_coop<MAXT>(a.rs, (int)(blockIdx.x - (gridDim.x - kRoles)), kRoles, (unsigned long long*)smem);
-        return;
-    }
-    const int n_main = (int)gridDim.x - (a.rs.enabled ? kRoles : 0);
     const Tables T = table_pointers(L, smem);
     bool tables_in_flight = false;
     if (a.tables) {
-        if (threadIdx.x == 0) bulk_load_tables(smem, a.tables, (unsigned)L.x, &table_bar);
+        if (threadIdx.x == 0) {
+            init_table_barrier(&table_bar);
+            bulk_load_tables(smem, a.tables, (unsigned)L.x, &table_bar);
+        }
         tables_in_flight = true;
         __syncthreads();  // the barrier is initialised before anyone polls it
     } else {
         build_tables(s, T, a.lambda, a.kT, true);
     }
     LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
-    if (a.rs.enabled) M.sig = &cta_sig;
     unsigned long long my_min = ~0ull;
-    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)n_main * kR) {
+    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
         const long long left = a.n - p0;
         const int count = left < kR ? (int)left : kR;
-        if (a.rs.enabled && threadIdx.x == 0) {  // published to the CTA by the barrier inside cta_load_rows
-            cta_sig.min_key = ~0ull; cta_sig.warps_done = 0u; cta_sig.n_warps = (unsigned)((count * T_ + 31) / 32);
-        }
         cta_load_rows(s, a, smem, L, sw, p0, count, true);
         if (tables_in_flight) {
-            wait_tables(&table_bar);
+            wait_tables(&table_bar, 0);
             tables_in_flight = false;
         }
         const bool valid = M.rid < count;
@@ -146,10 +136,56 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     }
     if ((threadIdx.x & 31) == 0) cta_min[threadIdx.x >> 5] = my_min;
     __syncthreads();
-    if (a.wmin_key && !a.rs.enabled && !(a.flags & CDW_FLAG_PHASE_REST) && threadIdx.x == 0) {  // (with the resample role the min was published with the weights)
+    if (a.wmin_key && threadIdx.x == 0) {
         unsigned long long m = cta_min[0];
         for (int w = 1; w < ((int)blockDim.x + 31) / 32; ++w) m = cta_min[w] < m ? cta_min[w] : m;
         if (m != ~0ull) atomicMin(a.wmin_key, m);
+    }
+}
+
+// The look-ahead iteration (cdw_lane.cuh: lane_ahead_main / lane_ahead_next).  One CTA per batch of 32 replicas (no persistent loop:
+// CTAs retire continuously, so a small kernel on another stream — the resampling of this very iteration — finds room beside it).
+// The table image of lambda_t arrives by TMA while the rows are gathered; after part A the image of lambda_{t+1} replaces it.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) smc_lookahead_kernel(SysDev s, PropArgs a, Shape sh) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long table_bar;
+    const int T_ = sh.T, sw = 32 / T_;
+    const Layout L = make_layout(s, true, kR, T_);
+    const Tables T = table_pointers(L, smem);
+    LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
+    const bool have_next = a.have_next != 0;
+    unsigned parity = 0;
+    if (threadIdx.x == 0) init_table_barrier(&table_bar);
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
+        const long long left = a.n - p0;
+        const int count = left < kR ? (int)left : kR;
+        if (a.tables) {
+            if (threadIdx.x == 0) bulk_load_tables(smem, a.tables, (unsigned)L.x, &table_bar);
+        } else {
+            build_tables(s, T, a.lambda, a.kT, true);
+        }
+        cta_load_rows(s, a, smem, L, sw, p0, count, true);
+        if (a.tables) { wait_tables(&table_bar, parity & 1u); ++parity; }
+        const bool valid = M.rid < count;
+        M.mask = __ballot_sync(0xffffffffu, valid);
+        AheadState S;
+        S.U_keep = 0.0; S.Us = 0.0; S.bad = 0;
+        if (valid) S = lane_ahead_main(s, T, M, a, p0 + M.rid);
+        __syncthreads();  // nobody reads the tables of lambda_t any more
+        if (have_next) {
+            if (a.tables_next) {
+                if (threadIdx.x == 0) bulk_load_tables(smem, a.tables_next, (unsigned)L.x, &table_bar);
+                wait_tables(&table_bar, parity & 1u);
+                ++parity;
+            } else {
+                build_tables(s, T, a.lambda_next, a.kT, true);
+            }
+        }
+        if (valid) lane_ahead_next(s, T, M, a, p0 + M.rid, S, have_next);
+        __syncthreads();
+        cta_store_rows_ahead(s, a, smem, L, sw, p0, count);
     }
 }
 
@@ -183,9 +219,15 @@ static const unsigned char* registered_tables(const cdw_system* sys, const doubl
     return sys->proto_tables + (size_t)row * sys->proto_stride;
 }
 
-static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t st) {
+enum LaunchKind { LAUNCH_ENERGY = 0, LAUNCH_PROPAGATE = 1, LAUNCH_LOOKAHEAD = 2 };
+
+static int launch(const cdw_system* sys, PropArgs& a, LaunchKind kind, cudaStream_t st) {
     static const bool no_tables = getenv("CDW_NO_PREBUILT_TABLES") != nullptr;
-    if (forces && !no_tables) a.tables = registered_tables(sys, a.lambda, a.kT);
+    const bool forces = kind != LAUNCH_ENERGY, ahead = kind == LAUNCH_LOOKAHEAD;
+    if (forces && !no_tables) {
+        a.tables = registered_tables(sys, a.lambda, a.kT);
+        if (ahead && a.lambda_next) a.tables_next = registered_tables(sys, a.lambda_next, a.kT);
+    }
     int devid = 0, sms = 148;
     cudaGetDevice(&devid);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
@@ -198,8 +240,10 @@ static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t 
     // and the batch is large enough to use it (measured: 13-atom system, 10^5 replicas: 333 us vs 375 us)
     const bool dense = small && L.total * 4 <= 227 * 1024 && (a.n + kR - 1) / kR >= (long long)sms * 4;
     const void* k = !forces ? (const void*)reduced_potential_kernel
-                            : (!small ? (const void*)smc_propagate_kernel<256, 2>
-                                      : (dense ? (const void*)smc_propagate_kernel<128, 4> : (const void*)smc_propagate_kernel<128, CDW_MINBLOCKS_SMALL>));
+                  : ahead ? (!small ? (const void*)smc_lookahead_kernel<256, 2>
+                                    : (dense ? (const void*)smc_lookahead_kernel<128, 4> : (const void*)smc_lookahead_kernel<128, CDW_MINBLOCKS_SMALL>))
+                          : (!small ? (const void*)smc_propagate_kernel<256, 2>
+                                    : (dense ? (const void*)smc_propagate_kernel<128, 4> : (const void*)smc_propagate_kernel<128, CDW_MINBLOCKS_SMALL>));
     if (L.total > 227 * 1024) {
         set_error("system needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
         return CDW_EUNSUPPORTED;
@@ -209,26 +253,11 @@ static int launch(const cdw_system* sys, PropArgs& a, bool forces, cudaStream_t 
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, nthr, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
     const long long need = (a.n + sh.R - 1) / sh.R, cap = (long long)sms * per_sm;
-    int grid = (int)(need < cap ? need : cap);
-    // in-launch resampling needs every CTA co-resident (the resample CTA waits for the others), MCMC weights (final after
-    // the opening evaluation) and room for the statistics scratch in the CTA's shared memory
-    static const bool no_inline = getenv("CDW_NO_INLINE_RESAMPLE") != nullptr;
-    const int roles = kVirtualThreads / (small ? 128 : 256);
-    // (the resample role assumes blockDim == the kernel's MAXT: teams of 1 or 2 lanes launch 32- / 64-thread CTAs and take the
-    // separate cdw_smc_resample launch instead)
-    const bool fuse = a.rs.enabled && forces && !no_inline && !(a.flags & CDW_FLAG_ULA) && need + roles <= cap && a.n < (1ll << 30) &&
-                      nthr == (small ? 128 : 256) && L.total >= sizeof(unsigned long long) * 3 * kVirtualThreads;
-    a.rs.enabled = fuse ? 1 : 0;
-    if (fuse) { grid = (int)need + roles; a.rs.n_main = (unsigned)need; }
-    if (forces && small && dense)
-        smc_propagate_kernel<128, 4><<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
-    else if (forces && small)
-        smc_propagate_kernel<128, CDW_MINBLOCKS_SMALL><<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
-    else if (forces)
-        smc_propagate_kernel<256, 2><<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
-    else
-        reduced_potential_kernel<<<grid, nthr, L.total, st>>>(sys->dev, a, sh);
-    CDW_CUDA(cudaGetLastError());
+    // the look-ahead kernel runs one CTA per batch (CTAs retire continuously: the resampling kernel of the same iteration, on another
+    // stream, finds room beside it); the others are persistent
+    int grid = (int)(ahead ? (need < (1ll << 30) ? need : (1ll << 30)) : (need < cap ? need : cap));
+    void* args[] = {(void*)&sys->dev, (void*)&a, (void*)&sh};
+    CDW_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(nthr), args, L.total, st));
     return CDW_OK;
 }
 
@@ -244,7 +273,7 @@ extern "C" int cdw_reduced_potential(const cdw_system* sys, const float* pos, in
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     PropArgs a = {};
     a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.beta = beta; a.energy_out = u_out;
-    return launch(sys, a, false, (cudaStream_t)stream);
+    return launch(sys, a, LAUNCH_ENERGY, (cudaStream_t)stream);
 }
 
 extern "C" int cdw_system_register_protocol(cdw_system* sys, const double* lambda_rows, int32_t n_rows, double kT, cdw_stream stream) {
@@ -290,26 +319,17 @@ extern "C" int cdw_energy_forces(const cdw_system* sys, const float* pos, int64_
     PropArgs a = {};
     a.pos_in = (const float4*)pos; a.n = n; a.lambda = lambda; a.kT = 1.0; a.dt = 0.0; a.n_steps = 0; a.tol = 1e-6;
     a.energy_out = energy_out; a.force_out = (float4*)force_out;
-    return launch(sys, a, true, (cudaStream_t)stream);
+    return launch(sys, a, LAUNCH_PROPAGATE, (cudaStream_t)stream);
 }
 
 static int apply_cache(PropArgs& a, const cdw_static_cache* c, bool sharded, bool gather) {
-    if (!c) {
-        CDW_REQUIRE(!(a.flags & (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST)), "split launches need a cdw_static_cache");
-        return CDW_OK;
-    }
+    if (!c) return CDW_OK;
     CDW_REQUIRE(c->force_out && c->energy_out, "cdw_static_cache: force_out and energy_out are required");
     CDW_REQUIRE(!(a.flags & CDW_FLAG_TRACK_WORKS), "cdw_static_cache cannot be combined with CDW_FLAG_TRACK_WORKS");
     const bool have_in = sharded ? (c->peer_force_in && c->peer_energy_in) : (c->force_in && c->energy_in);
     CDW_REQUIRE(have_in || a.n_steps == 0, "cdw_static_cache: seed the cache with an n_steps = 0 call before stepping");
     CDW_REQUIRE(!(gather && have_in && !sharded && c->force_in == c->force_out), "cdw_static_cache: gather-on-load needs distinct in/out rows");
     a.fs_out = (float4*)c->force_out; a.us_out = c->energy_out;
-    if (a.flags & (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST)) {
-        CDW_REQUIRE(c->force_open && c->u_open, "cdw_static_cache: split launches need force_open and u_open");
-        CDW_REQUIRE(!(a.flags & CDW_FLAG_ULA) && a.n_steps > 0 && have_in, "split launches: MCMC moves with n_steps > 0 and a seeded cache only");
-        CDW_REQUIRE((a.flags & (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST)) != (CDW_FLAG_PHASE_OPEN | CDW_FLAG_PHASE_REST), "choose one phase");
-        a.f_open = (float4*)c->force_open; a.u_open = c->u_open;
-    }
     if (have_in && a.n_steps > 0) {
         if (sharded) { a.peer_fs = (const float4* const*)c->peer_force_in; a.peer_us = c->peer_energy_in; a.fs_in = (const float4*)1; a.us_in = (const double*)1; }
         else { a.fs_in = (const float4*)c->force_in; a.us_in = c->energy_in; }
@@ -351,47 +371,59 @@ extern "C" int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
     if (int rc = apply_cache(a, cache, false, anc != nullptr)) return rc;
-    return launch(sys, a, true, (cudaStream_t)stream);
+    return launch(sys, a, LAUNCH_PROPAGATE, (cudaStream_t)stream);
 }
 
-extern "C" int cdw_smc_iteration(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out, int64_t n,
-                                 const int32_t* anc_in, const double* aux_in, double* cum, const int32_t* label_in, const double* lambda,
-                                 const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
-                                 double* aux_out, int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache, int kind,
-                                 double floor_threshold, uint64_t resample_seed, uint64_t stream_id, double* stats, int32_t* anc_out, uint64_t* cdf,
-                                 double* uniforms, void* workspace, size_t workspace_bytes, cdw_stream stream) {
-    CDW_REQUIRE(sys && prm && n > 0, "null argument or n == 0");
-    CDW_REQUIRE(pos_in && pos_out && cum && w_out && wmin_key && stats && anc_out && cdf && uniforms && workspace, "null argument");
-    CDW_REQUIRE(kind == CDW_RESAMPLE_MULTINOMIAL || kind == CDW_RESAMPLE_SYSTEMATIC, "unknown resampler kind");
-    CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
-    CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+// ---- the look-ahead iteration
+static int lookahead_common(const cdw_system* sys, PropArgs& a, const cdw_langevin_params* prm, const double* lambda, const double* lambda_next,
+                            uint64_t seed, uint64_t step0, int64_t gid0, float* pos_out, float* vel_out, float* force_out, double* inc_next_out,
+                            double* aux_out, int32_t* label_out, int32_t* nan_flags, cudaStream_t st) {
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
-    CDW_REQUIRE(!(anc_in && (pos_in == pos_out || (vel_in && vel_in == vel_out))), "gather-on-load needs distinct in/out buffers");
-    const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;
-    CDW_REQUIRE(ula || vel_in || (prm->flags & CDW_FLAG_RANDOMIZE_VELOCITIES) || prm->n_steps == 0, "velocities required unless they are randomized");
-    CDW_REQUIRE(ula || prm->n_steps == 0 || vel_out, "vel_out is required when positions are written");
-    CDW_REQUIRE(!(prm->flags & CDW_FLAG_TRACK_WORKS), "cdw_smc_iteration does not track shadow / proposal works: use cdw_smc_propagate");
-    PropArgs a = {};
-    a.pos_in = (const float4*)pos_in; a.vel_in = ula ? nullptr : (const float4*)vel_in; a.pos_out = (float4*)pos_out;
-    a.vel_out = ula ? nullptr : (float4*)vel_out;
-    a.n = n; a.anc = anc_in; a.aux_in = aux_in; a.cum_in = cum; a.label_in = label_in; a.lambda = lambda;
+    CDW_REQUIRE(!(prm->flags & ~CDW_FLAG_RANDOMIZE_VELOCITIES), "cdw_smc_lookahead: BAOAB moves only (flags other than CDW_FLAG_RANDOMIZE_VELOCITIES are not supported)");
+    CDW_REQUIRE(force_out, "force_out is required");
+    CDW_REQUIRE(prm->n_steps == 0 || (pos_out && vel_out), "pos_out and vel_out are required when n_steps > 0");
+    CDW_REQUIRE(!inc_next_out || lambda_next || sys->dev.n_lambda == 0, "lambda_next is required with inc_next_out");
+    a.lambda = lambda; a.lambda_next = lambda_next; a.have_next = inc_next_out != nullptr;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
-    a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
-    if (int rc = apply_cache(a, cache, false, anc_in != nullptr)) return rc;
-    int b = 0;
-    while ((1ll << b) < n) ++b;
-    ResampleArgs& r = a.rs;
-    r.enabled = 1;  // a request: launch() keeps it only if the whole grid is co-resident
-    r.kind = kind; r.n = (int)n; r.s1 = 61 - b; r.threshold = floor_threshold; r.w = w_out; r.wmin_key = (unsigned long long*)wmin_key;
-    r.seed = resample_seed; r.stream_id = stream_id; r.stats = stats; r.cum_in = cum; r.cum_out = cum; r.anc = anc_out; r.uniforms_out = uniforms;
-    r.cdf_spill = (unsigned long long*)cdf; r.ws = workspace;
-    r.done = (unsigned int*)workspace + 2 * 4;  // header word 4 of the weight workspace (zero at rest)
-    if (int rc = launch(sys, a, true, (cudaStream_t)stream)) return rc;
-    if (a.rs.enabled) return CDW_OK;
-    return cdw_smc_resample(kind, w_out, n, floor_threshold, wmin_key, resample_seed, stream_id, stats, cum, cum, anc_out, cdf, uniforms, workspace,
-                            workspace_bytes, stream);
+    a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out; a.fs_out = (float4*)force_out;
+    a.inc_next_out = inc_next_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags;
+    return launch(sys, a, LAUNCH_LOOKAHEAD, st);
+}
+
+extern "C" int cdw_smc_lookahead(const cdw_system* sys, const float* pos_in, const float* vel_in, const float* force_in, float* pos_out, float* vel_out,
+                                 float* force_out, int64_t n, const int32_t* anc, const int32_t* label_in, const double* lambda, const double* lambda_next,
+                                 const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_next_out, double* aux_out,
+                                 int32_t* label_out, int32_t* nan_flags, cdw_stream stream) {
+    CDW_REQUIRE(sys && prm && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    CDW_REQUIRE(pos_in, "null argument");
+    CDW_REQUIRE(prm->n_steps == 0 || (force_in && (vel_in || (prm->flags & CDW_FLAG_RANDOMIZE_VELOCITIES))), "force_in (and velocities, unless they are randomized) are required when n_steps > 0");
+    CDW_REQUIRE(!(anc && (pos_in == pos_out || (vel_in && vel_in == vel_out) || (force_in && force_in == force_out))), "gather-on-load needs distinct in/out buffers");
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.fs_in = prm->n_steps > 0 ? (const float4*)force_in : nullptr;
+    a.n = n; a.anc = anc; a.label_in = label_in;
+    return lookahead_common(sys, a, prm, lambda, lambda_next, seed, step0, gid0, pos_out, vel_out, force_out, inc_next_out, aux_out, label_out, nan_flags,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int cdw_smc_lookahead_sharded(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel, const float* const* peer_force,
+                                         const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, float* pos_out, float* vel_out,
+                                         float* force_out, int64_t n, const int32_t* anc, const double* lambda, const double* lambda_next,
+                                         const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_next_out,
+                                         double* aux_out, int32_t* label_out, int32_t* nan_flags, cdw_stream stream) {
+    CDW_REQUIRE(sys && prm && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    CDW_REQUIRE(peer_pos && peer_vel && peer_force && anc && n_ranks > 0 && n_per_rank > 0, "null argument");
+    CDW_REQUIRE(prm->n_steps > 0, "the sharded look-ahead iteration needs n_steps > 0 (equip the initial sample with cdw_smc_lookahead)");
+    PropArgs a = {};
+    a.peer_pos = (const float4* const*)peer_pos; a.peer_vel = (const float4* const*)peer_vel; a.peer_fs = (const float4* const*)peer_force;
+    a.peer_label = peer_label; a.n_per_rank = n_per_rank;
+    a.vel_in = (const float4*)1; a.fs_in = (const float4*)1;  // they exist (read through the peer tables); the local pointers are never dereferenced
+    a.n = n; a.anc = anc;
+    return lookahead_common(sys, a, prm, lambda, lambda_next, seed, step0, gid0, pos_out, vel_out, force_out, inc_next_out, aux_out, label_out, nan_flags,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int cdw_smc_propagate_sharded(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel, const double* const* peer_aux,
@@ -411,21 +443,20 @@ extern "C" int cdw_smc_propagate_sharded_cached(const cdw_system* sys, const flo
     CDW_REQUIRE(sys && prm && n >= 0, "null argument");
     if (n == 0) return CDW_OK;
     const bool ula = (prm->flags & CDW_FLAG_ULA) != 0;
-    const bool open_only = (prm->flags & CDW_FLAG_PHASE_OPEN) != 0;  // the opening launch of a split call writes no rows
-    CDW_REQUIRE(peer_pos && anc && n_ranks > 0 && n_per_rank > 0 && (open_only || (pos_out && (ula || (peer_vel && vel_out)))), "null argument");
+    CDW_REQUIRE(peer_pos && anc && n_ranks > 0 && n_per_rank > 0 && pos_out && (ula || (peer_vel && vel_out)), "null argument");
     CDW_REQUIRE(!(ula && (prm->flags & CDW_FLAG_TRACK_WORKS)), "CDW_FLAG_TRACK_WORKS does not apply to the Euler-Maruyama proposal");
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     PropArgs a = {};
     a.peer_pos = (const float4* const*)peer_pos; a.peer_vel = (const float4* const*)peer_vel; a.peer_aux = peer_aux; a.peer_label = peer_label;
     a.n_per_rank = n_per_rank;
-    a.vel_in = ula || open_only ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
-    a.pos_out = open_only ? nullptr : (float4*)pos_out; a.vel_out = ula || open_only ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
+    a.vel_in = ula ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
+    a.pos_out = (float4*)pos_out; a.vel_out = ula ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
     if (int rc = apply_cache(a, cache, true, true)) return rc;
-    return launch(sys, a, true, (cudaStream_t)stream);
+    return launch(sys, a, LAUNCH_PROPAGATE, (cudaStream_t)stream);
 }
 
 extern "C" int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n, const double* lambda, const cdw_langevin_params* prm,

@@ -1,55 +1,69 @@
-// cdw_weights.cu — K2 (incremental work / log-weight update, log-sum-exp + ESS reduction), K3a (integer cdf scan +
-// vectorised search for multinomial / systematic resampling), K3b (coalesced particle gather) for sm_100a.
+// cdw_weights.cu — K2 (incremental work / log-weight update, log-sum-exp + ESS reduction), K3a (integer cdf scan, direct
+// emission of systematic ancestors, guide-table lookup for multinomial ancestors), K3b (coalesced particle gather) for sm_100a.
 //
 // Reference semantics: TargetFactory.compute_incremental_work (coddiwomple/distribution_factories.py:124-129),
 // nESS / vanilla_floor_threshold (coddiwomple/utils.py:41-72), Resampler.resample (coddiwomple/resamplers.py:61-133),
 // MultinomialResampler._resample (coddiwomple/resamplers.py:254-272).
 //
-// Exactness: ancestors come from an INTEGER cdf (weights quantised with det_exp + rint, uint64 prefix sum, integer
-// search), so they are independent of summation order, block schedule and GPU count, and equal oracle/resampling.py
-// bit for bit.
+// Exactness: EVERYTHING after the exponential is integer arithmetic, hence exactly associative — results do
+// not depend on grid size, block schedule, summation order or GPU count, and equal oracle/resampling.py bit for bit:
+//   * e_i = det_exp(min W - W_i) is evaluated ONCE per particle (correctly rounded mul/add/rint only: same bits on CPU and GPU) and
+//     kept as q_i = rint(e_i 2^62) (uint64);
+//   * sum e and sum e^2 (nESS, the normaliser) are 128-bit integer sums of q_i and rint(e_i^2 2^62);
+//   * the cdf is the uint64 prefix sum of q_i >> k (rounded), k chosen from the exact sum so that 2^59 <= total < 2^61;
+//   * ancestors are searched in integers (floor(u total) in 128-bit arithmetic).
+//
+// Passes over n particles (HBM bytes per particle):
+//   weight_update / weight_compose   W = cum + inc, running min                          R 16-20  W 8-16
+//   weight_stats                     q, the two integer sums; last block: statistics      R 8      W 8
+//   cdf_tile_sums                    per-tile sums of q >> k; last block scans them       R 8
+//   cdf_tile_scan<EMIT>              cdf; systematic ancestors or the multinomial guide   R 8      W 8 + 4
+//   lookup (multinomial only)        bucket -> guide -> <= a few cdf probes               R 8 + ~64 (random sectors)  W 4
 #include <stdlib.h>
+#include <string.h>
 
 #include "cdw_common.h"
-#include "cdw_resample.cuh"
 
 namespace cdw {
 
 constexpr int kBlock = 256;
 constexpr int kItems = 8;
 constexpr int kTile = kBlock * kItems;
-constexpr int kMaxStatBlocks = 2048;
 
-// workspace header (uint64 words)
-enum { WS_TICKET = 0, WS_T1 = 1, WS_SHIFT = 2, WS_TOTAL = 3, WS_HEADER_WORDS = 8 };
+// workspace header (uint64 words); every kernel that uses an accumulator leaves it at zero
+enum { WS_TICKET = 0, WS_S1_LO = 1, WS_S1_HI = 2, WS_S2_LO = 3, WS_S2_HI = 4, WS_SHIFT = 5, WS_TOTAL = 6, WS_TICKET2 = 7, WS_HEADER_WORDS = 8 };
 
 struct WsView {
     unsigned long long* hdr;
-    double* part_e;
-    double* part_e2;
     unsigned long long* tile_sum;
     unsigned long long* tile_off;
-    unsigned long long* coarse;  // cdf sampled at the end of every group of kGroup entries: coarse[g] = cdf[min(n, kGroup (g + 1)) - 1]
+    unsigned long long* q;   // [n] rint(e_i 2^62)
+    int* guide;              // [n] multinomial: guide[b] = first j with cdf[j] > floor((b / n) total)
 };
 
-constexpr int kGroup = 32, kGroupLog2 = 5;  // coarse table = n/4 bytes: L2-resident up to ~4e8 particles
-__host__ __device__ inline long long n_groups_for(long long n) { return (n + kGroup - 1) / kGroup; }
-
 __host__ __device__ inline long long n_tiles_for(long long n) { return (n + kTile - 1) / kTile; }
+
+__host__ __device__ inline size_t align16u(size_t v) { return (v + 15) & ~(size_t)15; }
 
 __host__ __device__ inline WsView ws_view(void* ws, long long n) {
     WsView v;
     unsigned char* b = (unsigned char*)ws;
     v.hdr = (unsigned long long*)b; b += sizeof(unsigned long long) * WS_HEADER_WORDS;
-    v.part_e = (double*)b; b += sizeof(double) * kMaxStatBlocks;
-    v.part_e2 = (double*)b; b += sizeof(double) * kMaxStatBlocks;
-    v.tile_sum = (unsigned long long*)b; b += sizeof(unsigned long long) * n_tiles_for(n);
-    v.tile_off = (unsigned long long*)b; b += sizeof(unsigned long long) * (n_tiles_for(n) + 1);
-    b = (unsigned char*)(((size_t)b + 15) & ~(size_t)15);  // the coarse table is written with 16-byte stores
-    v.coarse = (unsigned long long*)b;
+    v.tile_sum = (unsigned long long*)b; b += align16u(sizeof(unsigned long long) * n_tiles_for(n));
+    v.tile_off = (unsigned long long*)b; b += align16u(sizeof(unsigned long long) * (n_tiles_for(n) + 1));
+    v.q = (unsigned long long*)b; b += align16u(sizeof(unsigned long long) * n);
+    v.guide = (int*)b;
     return v;
 }
 
+__device__ __forceinline__ double philox_uniform53(unsigned long long seed, unsigned long long stream_id, long long i) {
+    u4 c;
+    const long long pair = i >> 1;
+    c.x = (uint32_t)pair; c.y = (uint32_t)((unsigned long long)pair >> 32); c.z = (uint32_t)stream_id; c.w = 0x5EEDu;
+    const u4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const unsigned long long bits = (i & 1) ? ((((unsigned long long)r.z << 32) | r.w) >> 11) : ((((unsigned long long)r.x << 32) | r.y) >> 11);
+    return (double)bits * 1.1102230246251565e-16;
+}
 
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce(T v, Op op, T* sh /*[kBlock/32]*/) {
@@ -63,6 +77,55 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T* sh /*[kBlock/32]*/) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = op(r, sh[w]);
     return r;  // same value in every thread, combined in a fixed order
 }
+
+// ------------------------------------------------------------------------------------------------ 128-bit unsigned sums
+struct u128 {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ void add128(u128& a, unsigned long long v) {
+    a.lo += v;
+    a.hi += a.lo < v ? 1ull : 0ull;
+}
+__device__ __forceinline__ void add128(u128& a, const u128& b) {
+    a.lo += b.lo;
+    a.hi += b.hi + (a.lo < b.lo ? 1ull : 0ull);
+}
+__device__ __forceinline__ u128 block_sum128(u128 v, unsigned long long* sh /*[2 * kBlock/32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u128 t;
+        t.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+        t.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+        add128(v, t);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { sh[2 * warp] = v.lo; sh[2 * warp + 1] = v.hi; }
+    __syncthreads();
+    u128 r;
+    r.lo = sh[0]; r.hi = sh[1];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        u128 t;
+        t.lo = sh[2 * w]; t.hi = sh[2 * w + 1];
+        add128(r, t);
+    }
+    return r;
+}
+// integers commute: any number of blocks may add their partial sums in any order
+__device__ __forceinline__ void atomic_add128(unsigned long long* lo, unsigned long long* hi, const u128& v) {
+    const unsigned long long old = atomicAdd(lo, v.lo);
+    const unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
+    if (v.hi + carry) atomicAdd(hi, v.hi + carry);
+}
+// (hi 2^64 + lo) 2^-62 with two correctly rounded conversions, one add and an exact scaling (oracle/resampling.py:u128_to_double)
+__device__ __forceinline__ double u128_to_double_2m62(const u128& v) {
+    return __dmul_rn(__dadd_rn(__dmul_rn(__ull2double_rn(v.hi), 18446744073709551616.0), __ull2double_rn(v.lo)), 2.168404344971008868e-19);
+}
+// bit length of a 128-bit integer
+__device__ __forceinline__ int bitlen128(const u128& v) { return v.hi ? 128 - __clzll((long long)v.hi) : 64 - __clzll((long long)v.lo); }
+
+// q >> k rounded half up (k = 0: q itself)
+__device__ __forceinline__ unsigned long long shift_round(unsigned long long q, int k) { return k ? ((q >> (k - 1)) + 1ull) >> 1 : q; }
 
 // ------------------------------------------------------------------------------------------------ K2 pass 1
 __global__ void __launch_bounds__(kBlock) weight_update_kernel(const double* __restrict__ u_new, const double* __restrict__ aux,
@@ -84,49 +147,73 @@ __global__ void __launch_bounds__(kBlock) weight_update_kernel(const double* __r
     if (threadIdx.x == 0 && wmin_key && m != ~0ull) atomicMin(wmin_key, m);
 }
 
+// The look-ahead loop (cdw_smc_lookahead): the incremental work of slot i was computed one launch earlier, at the slot its state
+// then lived in: W[i] = cum[i] + inc_src[anc_prev[i]]  (Resampler.resample's `cumulative_work + incremental_work`, resamplers.py:99-100).
+__global__ void __launch_bounds__(kBlock) weight_compose_kernel(const double* __restrict__ inc_src, const int* __restrict__ anc_prev,
+                                                                const double* __restrict__ cum, long long n, double* __restrict__ inc_out,
+                                                                double* __restrict__ w_out, unsigned long long* wmin_key) {
+    __shared__ unsigned long long sh[kBlock / 32];
+    unsigned long long m = ~0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double inc = inc_src[anc_prev ? (long long)anc_prev[i] : i];
+        const double w = (cum ? cum[i] : 0.0) + inc;
+        if (inc_out) inc_out[i] = inc;
+        w_out[i] = w;
+        const unsigned long long k = ordered_key(w);
+        m = k < m ? k : m;
+    }
+    m = block_reduce(m, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, sh);
+    if (threadIdx.x == 0 && m != ~0ull) atomicMin(wmin_key, m);
+}
+
 // ------------------------------------------------------------------------------------------------ K2 pass 2
+// One exponential per particle; everything it feeds is kept as integers.  `rearm` (may be NULL): the running-min key is reset to
+// ~0 by the last block (every block has read it by then), so that the next iteration's weight pass can fold into it again.
 __global__ void __launch_bounds__(kBlock) weight_stats_kernel(const double* __restrict__ w, long long n, double threshold,
                                                               const unsigned long long* __restrict__ wmin_key, double* stats, WsView ws,
-                                                              int s1) {
-    __shared__ double shd[kBlock / 32];
-    __shared__ unsigned long long shu[kBlock / 32];
+                                                              unsigned long long* rearm) {
+    __shared__ unsigned long long sh[2 * (kBlock / 32)];
     __shared__ bool is_last;
-    const double wmin = ordered_key_inverse(*wmin_key);
-    const double scale1 = pow2(s1);
-    double se = 0.0, se2 = 0.0;
-    unsigned long long t1 = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        double e = det_exp(CDW_ADD(wmin, -w[i]));
-        se += e;
-        se2 += e * e;
-        t1 += __double2ull_rn(CDW_MUL(e, scale1));
+    const double wmin = ordered_key_inverse(*(const volatile unsigned long long*)wmin_key);
+    const double two62 = 4611686018427387904.0;
+    u128 s1 = {0ull, 0ull}, s2 = {0ull, 0ull};
+    const long long n2 = n >> 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = __ldg((const double2*)w + i);
+        const double ea = det_exp(CDW_ADD(wmin, -v.x)), eb = det_exp(CDW_ADD(wmin, -v.y));
+        const unsigned long long qa = __double2ull_rn(CDW_MUL(ea, two62)), qb = __double2ull_rn(CDW_MUL(eb, two62));
+        ((ulonglong2*)ws.q)[i] = make_ulonglong2(qa, qb);
+        add128(s1, qa); add128(s1, qb);
+        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(ea, ea), two62)));
+        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(eb, eb), two62)));
     }
-    se = block_reduce(se, [](double a, double b) { return a + b; }, shd);
-    se2 = block_reduce(se2, [](double a, double b) { return a + b; }, shd);
-    t1 = block_reduce(t1, [](unsigned long long a, unsigned long long b) { return a + b; }, shu);
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double e = det_exp(CDW_ADD(wmin, -w[n - 1]));
+        const unsigned long long q = __double2ull_rn(CDW_MUL(e, two62));
+        ws.q[n - 1] = q;
+        add128(s1, q);
+        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(e, e), two62)));
+    }
+    s1 = block_sum128(s1, sh);
+    s2 = block_sum128(s2, sh);
     if (threadIdx.x == 0) {
-        ws.part_e[blockIdx.x] = se;
-        ws.part_e2[blockIdx.x] = se2;
-        atomicAdd(&ws.hdr[WS_T1], t1);
+        atomic_add128(&ws.hdr[WS_S1_LO], &ws.hdr[WS_S1_HI], s1);
+        atomic_add128(&ws.hdr[WS_S2_LO], &ws.hdr[WS_S2_HI], s2);
         __threadfence();
-        unsigned long long ticket = atomicAdd(&ws.hdr[WS_TICKET], 1ull);
+        const unsigned long long ticket = atomicAdd(&ws.hdr[WS_TICKET], 1ull);
         is_last = ticket == (unsigned long long)gridDim.x - 1;
     }
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
         __threadfence();
-        double sum_e = 0.0, sum_e2 = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) {  // fixed order: run-to-run deterministic
-            sum_e += ((volatile double*)ws.part_e)[b];
-            sum_e2 += ((volatile double*)ws.part_e2)[b];
-        }
-        unsigned long long T1 = ((volatile unsigned long long*)ws.hdr)[WS_T1];
-        ws.hdr[WS_T1] = 0; ws.hdr[WS_TICKET] = 0;  // leave the accumulators at rest: the next call needs no memset
-        int bitlen = 64 - __clzll((long long)T1);
-        int shift = 60 - bitlen;
-        shift = shift < 0 ? 0 : shift;
-        ws.hdr[WS_SHIFT] = (unsigned long long)(s1 + shift);
-        double ness = (sum_e * sum_e) / ((double)n * sum_e2);
+        volatile unsigned long long* h = ws.hdr;
+        u128 S1, S2;
+        S1.lo = h[WS_S1_LO]; S1.hi = h[WS_S1_HI]; S2.lo = h[WS_S2_LO]; S2.hi = h[WS_S2_HI];
+        h[WS_S1_LO] = 0; h[WS_S1_HI] = 0; h[WS_S2_LO] = 0; h[WS_S2_HI] = 0; h[WS_TICKET] = 0;  // at rest for the next call: no memset needed
+        const int b = bitlen128(S1);
+        h[WS_SHIFT] = (unsigned long long)(b > 60 ? b - 60 : 0);   // total = sum (q >> k, rounded) then has 59..61 bits
+        const double sum_e = u128_to_double_2m62(S1), sum_e2 = u128_to_double_2m62(S2);
+        const double ness = (sum_e * sum_e) / ((double)n * sum_e2);
         stats[CDW_STAT_WMIN] = wmin;
         stats[CDW_STAT_SUM_E] = sum_e;
         stats[CDW_STAT_SUM_E2] = sum_e2;
@@ -135,125 +222,127 @@ __global__ void __launch_bounds__(kBlock) weight_stats_kernel(const double* __re
         stats[CDW_STAT_RESAMPLE] = (threshold < 0.0 || ness <= threshold) ? 1.0 : 0.0;
         stats[CDW_STAT_TOTAL] = 0.0;
         stats[CDW_STAT_NNAN] = 0.0;
+        if (rearm) *rearm = ~0ull;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ K3a: integer cdf
-__device__ __forceinline__ void load_tile_q(const double* __restrict__ w, long long n, long long base, double wmin, double scale,
-                                            unsigned long long (&q)[kItems]) {
+__device__ __forceinline__ void load_tile_q(const unsigned long long* __restrict__ q_in, long long n, long long base, int k, unsigned long long (&q)[kItems]) {
     const long long i0 = base + (long long)threadIdx.x * kItems;
     if (i0 + kItems <= n) {
-        const double2* p = (const double2*)(w + i0);  // i0 is a multiple of 8 -> 64-byte aligned
+        const ulonglong2* p = (const ulonglong2*)(q_in + i0);  // i0 is a multiple of 8 -> 64-byte aligned
 #pragma unroll
-        for (int k = 0; k < kItems / 2; ++k) {
-            double2 v = __ldg(p + k);
-            q[2 * k] = quantise(v.x, wmin, scale);
-            q[2 * k + 1] = quantise(v.y, wmin, scale);
+        for (int j = 0; j < kItems / 2; ++j) {
+            const ulonglong2 v = __ldcg(p + j);
+            q[2 * j] = shift_round(v.x, k);
+            q[2 * j + 1] = shift_round(v.y, k);
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) q[k] = (i0 + k < n) ? quantise(w[i0 + k], wmin, scale) : 0ull;
+        for (int j = 0; j < kItems; ++j) q[j] = (i0 + j < n) ? shift_round(__ldcg(q_in + i0 + j), k) : 0ull;
     }
 }
 
-__global__ void __launch_bounds__(kBlock) cdf_tile_sums_kernel(const double* __restrict__ w, long long n, const double* __restrict__ stats,
-                                                               WsView ws) {
+// per-tile sums; the last block to finish scans them (exclusive offsets + grand total)
+__global__ void __launch_bounds__(kBlock) cdf_tile_sums_kernel(long long n, double* stats, WsView ws) {
     if (stats[CDW_STAT_RESAMPLE] == 0.0) return;
     __shared__ unsigned long long sh[kBlock / 32];
-    const double wmin = stats[CDW_STAT_WMIN];
-    const double scale = pow2((int)ws.hdr[WS_SHIFT]);
-    for (long long tile = blockIdx.x; tile < n_tiles_for(n); tile += gridDim.x) {
+    __shared__ unsigned long long carry_sh;
+    __shared__ bool is_last;
+    const int k = (int)ws.hdr[WS_SHIFT];
+    const long long nt = n_tiles_for(n);
+    for (long long tile = blockIdx.x; tile < nt; tile += gridDim.x) {
         unsigned long long q[kItems];
-        load_tile_q(w, n, tile * kTile, wmin, scale, q);
+        load_tile_q(ws.q, n, tile * kTile, k, q);
         unsigned long long s = 0;
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) s += q[k];
+        for (int j = 0; j < kItems; ++j) s += q[j];
         s = block_reduce(s, [](unsigned long long a, unsigned long long b) { return a + b; }, sh);
         if (threadIdx.x == 0) ws.tile_sum[tile] = s;
     }
-}
-
-__global__ void __launch_bounds__(1024) cdf_scan_tiles_kernel(long long n, double* stats, WsView ws) {
-    if (stats[CDW_STAT_RESAMPLE] == 0.0) return;
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry_sh;
-    const long long nt = n_tiles_for(n);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_sh = 0;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(&ws.hdr[WS_TICKET2], 1ull);
+        is_last = ticket == (unsigned long long)gridDim.x - 1;
+        carry_sh = 0;
+    }
     __syncthreads();
-    for (long long base = 0; base < nt; base += 1024) {
-        long long i = base + threadIdx.x;
-        unsigned long long v = i < nt ? ws.tile_sum[i] : 0ull;
-        unsigned long long incl = v;
+    if (!is_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < nt; base += kTile) {   // kItems consecutive tile sums per thread
+        unsigned long long v[kItems], run = 0;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            const long long i = base + (long long)threadIdx.x * kItems + j;
+            v[j] = i < nt ? __ldcg(ws.tile_sum + i) : 0ull;
+            run += v[j];
+        }
+        unsigned long long incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long t = warp_tot[lane], s = t;
+        if (lane == 31) sh[warp] = incl;
+        __syncthreads();
+        unsigned long long off = carry_sh + incl - run;
+        for (int wi = 0; wi < warp; ++wi) off += sh[wi];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long u = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += u;
-            }
-            warp_tot[lane] = s - t;  // exclusive prefix of warp totals
+        for (int j = 0; j < kItems; ++j) {
+            const long long i = base + (long long)threadIdx.x * kItems + j;
+            if (i < nt) ws.tile_off[i] = off;
+            off += v[j];
         }
         __syncthreads();
-        const unsigned long long carry = carry_sh;
-        const unsigned long long excl = carry + warp_tot[warp] + incl - v;
-        if (i < nt) ws.tile_off[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_sh = excl + v;
+        if (threadIdx.x == kBlock - 1) carry_sh = off;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         ws.hdr[WS_TOTAL] = carry_sh;
+        ws.hdr[WS_TICKET2] = 0;
         stats[CDW_STAT_TOTAL] = (double)carry_sh;
     }
 }
 
-// cdw_smc_resample draws its own uniforms (Philox, keyed by slot) inside the search kernels and lets them re-arm the
-// running-min key: no separate uniforms / fill launches.
+// The final kernel of a resampling call may draw its own uniforms (Philox, keyed by slot).
 struct SearchGen {
     int gen;                              // 0: read `uniforms`; 1: generate (and store to uniforms_out if not NULL)
     unsigned long long seed, stream_id;
     double* uniforms_out;
-    unsigned long long* rearm_key;        // set to ~0 by the kernel (may be NULL)
 };
 
-__device__ __forceinline__ void search_rearm(const SearchGen& g) {
-    if (g.rearm_key && blockIdx.x == 0 && threadIdx.x == 0) *g.rearm_key = ~0ull;
-}
-
-// Systematic resampling needs no search at all: its targets are sorted, so the tile scan that has cdf[j - 1] and cdf[j] in
-// registers can emit item j's slots directly, [first(cdf[j - 1]), first(cdf[j])) with first(c) = min{i : target_i >= c},
-// target_i = floor(((i + u0) / n) T).  first() is estimated in floating point and corrected with the exact forward map,
-// so the ancestors are bit-identical to the search form.  No second pass over the cdf.
+// Sorted targets need no search: the tile scan holds cdf[j - 1] and cdf[j] in registers and emits item j's slots directly,
+// [first(cdf[j - 1]), first(cdf[j])) with first(c) = min{i : target_i >= c}, target_i = floor(((i + u0) (1/n)) total).
+// first() is estimated in floating point and corrected with the exact forward map.  Two uses:
+//   EMIT_ANCESTORS  systematic resampling: slot i's ancestor is j (u0 = the one uniform of the draw);
+//   EMIT_GUIDE      multinomial resampling: with u0 = 0 the same emission is a guide table, guide[b] = first j with
+//                   cdf[j] > floor((b / n) total), which bounds the search of any target that falls into bucket b.
+enum { EMIT_NONE = 0, EMIT_ANCESTORS = 1, EMIT_GUIDE = 2 };
 struct EmitArgs {
     const double* uniforms;   // [1] u0 when gen.gen == 0
     const double* cum_in; double* cum_out; int* anc;
     SearchGen gen;
 };
 
-__device__ __forceinline__ unsigned long long systematic_target(long long i, double u0, long long n, unsigned long long total) {
-    return fixed_target(__ddiv_rn(__dadd_rn((double)i, u0), (double)n), total);
+__device__ __forceinline__ unsigned long long systematic_target(long long i, double u0, double inv_n, unsigned long long total) {
+    return fixed_target(__dmul_rn(__dadd_rn((double)i, u0), inv_n), total);
 }
 
-__device__ __forceinline__ long long first_slot(unsigned long long c, unsigned long long total, double u0, long long n, double n_over_total) {
+__device__ __forceinline__ long long first_slot(unsigned long long c, unsigned long long total, double u0, long long n, double inv_n, double n_over_total) {
     if (c == 0) return 0;
     long long i = (long long)ceil((double)c * n_over_total - u0);
     i = i < 0 ? 0 : (i > n ? n : i);
-    while (i > 0 && systematic_target(i - 1, u0, n, total) >= c) --i;
-    while (i < n && systematic_target(i, u0, n, total) < c) ++i;
+    while (i > 0 && systematic_target(i - 1, u0, inv_n, total) >= c) --i;
+    while (i < n && systematic_target(i, u0, inv_n, total) < c) ++i;
     return i;
 }
 
+template <int EMIT>
 __device__ __forceinline__ void emit_slot(const EmitArgs& e, long long i, long long j, double mean) {
     e.anc[i] = (int)j;
-    if (e.cum_out) {
+    if (EMIT == EMIT_ANCESTORS && e.cum_out) {
         const double c = e.cum_in ? e.cum_in[i] : 0.0;
         e.cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
     }
@@ -262,12 +351,11 @@ __device__ __forceinline__ void emit_slot(const EmitArgs& e, long long i, long l
 constexpr int kHeavyRange = 16;   // longer slot ranges (one ancestor copied many times) are written by the whole block
 constexpr int kHeavyList = 64;
 
-template <bool EMIT>
+template <int EMIT>
 __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __restrict__ w, long long n, const double* __restrict__ stats,
                                                                WsView ws, unsigned long long* __restrict__ cdf, EmitArgs em) {
-    if (EMIT) search_rearm(em.gen);
     if (stats[CDW_STAT_RESAMPLE] == 0.0) {
-        if (EMIT) {
+        if (EMIT == EMIT_ANCESTORS) {
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
                 em.anc[i] = (int)i;
                 if (em.cum_out) em.cum_out[i] = w[i];  // null update: cum += inc (resamplers.py:136-156)
@@ -280,18 +368,18 @@ __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __r
     __shared__ int n_heavy;
     const unsigned long long total = EMIT ? ws.hdr[WS_TOTAL] : 0ull;
     const double mean = stats[CDW_STAT_MEAN];
-    const double u0 = EMIT ? (em.gen.gen ? philox_uniform53(em.gen.seed, em.gen.stream_id, 0) : em.uniforms[0]) : 0.0;
+    const double u0 = EMIT == EMIT_ANCESTORS ? (em.gen.gen ? philox_uniform53(em.gen.seed, em.gen.stream_id, 0) : em.uniforms[0]) : 0.0;
+    const double inv_n = __ddiv_rn(1.0, (double)n);
     const double n_over_total = EMIT ? (double)n / (double)total : 0.0;
-    if (EMIT && em.gen.gen && em.gen.uniforms_out && blockIdx.x == 0 && threadIdx.x == 0) em.gen.uniforms_out[0] = u0;
+    if (EMIT == EMIT_ANCESTORS && em.gen.gen && em.gen.uniforms_out && blockIdx.x == 0 && threadIdx.x == 0) em.gen.uniforms_out[0] = u0;
     if (EMIT && threadIdx.x == 0) n_heavy = 0;
-    const double wmin = stats[CDW_STAT_WMIN];
-    const double scale = pow2((int)ws.hdr[WS_SHIFT]);
+    const int k = (int)ws.hdr[WS_SHIFT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long tile = blockIdx.x; tile < n_tiles_for(n); tile += gridDim.x) {
         unsigned long long q[kItems];
-        load_tile_q(w, n, tile * kTile, wmin, scale, q);
+        load_tile_q(ws.q, n, tile * kTile, k, q);
 #pragma unroll
-        for (int k = 1; k < kItems; ++k) q[k] += q[k - 1];
+        for (int j = 1; j < kItems; ++j) q[j] += q[j - 1];
         const unsigned long long tot = q[kItems - 1];
         unsigned long long incl = tot;
 #pragma unroll
@@ -308,124 +396,71 @@ __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __r
         if (i0 + kItems <= n) {
             ulonglong2* o2 = (ulonglong2*)(cdf + i0);
 #pragma unroll
-            for (int k = 0; k < kItems / 2; ++k) o2[k] = make_ulonglong2(q[2 * k] + off, q[2 * k + 1] + off);
+            for (int j = 0; j < kItems / 2; ++j) o2[j] = make_ulonglong2(q[2 * j] + off, q[2 * j + 1] + off);
         } else {
 #pragma unroll
-            for (int k = 0; k < kItems; ++k)
-                if (i0 + k < n) cdf[i0 + k] = q[k] + off;
-        }
-        // coarse table for the hierarchical search: the last cdf entry of every group of kGroup.  A group ends on the last
-        // item of a thread (kGroup is a multiple of kItems) or at n - 1.  The index uses an unsigned shift on purpose:
-        // nvcc 12.9 dropped the rounding of a signed `i / kGroup` in the n - 1 case (uniform datapath), giving a
-        // misaligned store for n = 2..7.
-        static_assert((1 << kGroupLog2) == kGroup && kGroup % kItems == 0, "groups are whole threads");
-#pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-            const unsigned long long i = (unsigned long long)(i0 + k);
-            const bool ends = (k == kItems - 1 && ((i + 1) & (kGroup - 1)) == 0) || i + 1 == (unsigned long long)n;
-            if (i < (unsigned long long)n && ends) ws.coarse[i >> kGroupLog2] = q[k] + off;
+            for (int j = 0; j < kItems; ++j)
+                if (i0 + j < n) cdf[i0 + j] = q[j] + off;
         }
         if (EMIT) {
-            long long lo = first_slot(off, total, u0, n, n_over_total);
+            long long lo = first_slot(off, total, u0, n, inv_n, n_over_total);
 #pragma unroll
-            for (int k = 0; k < kItems; ++k) {
-                const long long j = i0 + k;
-                const long long hi = j < n ? first_slot(q[k] + off, total, u0, n, n_over_total) : lo;
+            for (int j = 0; j < kItems; ++j) {
+                const long long item = i0 + j;
+                const long long hi = item < n ? first_slot(q[j] + off, total, u0, n, inv_n, n_over_total) : lo;
                 if (hi - lo > kHeavyRange) {
                     const int slot = atomicAdd(&n_heavy, 1);
-                    if (slot < kHeavyList) { heavy[3 * slot] = j; heavy[3 * slot + 1] = lo; heavy[3 * slot + 2] = hi; }
-                    else for (long long i = lo; i < hi; ++i) emit_slot(em, i, j, mean);
+                    if (slot < kHeavyList) { heavy[3 * slot] = item; heavy[3 * slot + 1] = lo; heavy[3 * slot + 2] = hi; }
+                    else for (long long i = lo; i < hi; ++i) emit_slot<EMIT>(em, i, item, mean);
                 } else {
-                    for (long long i = lo; i < hi; ++i) emit_slot(em, i, j, mean);
+                    for (long long i = lo; i < hi; ++i) emit_slot<EMIT>(em, i, item, mean);
                 }
                 lo = hi;
             }
             __syncthreads();
             const int nh = n_heavy < kHeavyList ? n_heavy : kHeavyList;
             for (int h = 0; h < nh; ++h)
-                for (long long i = heavy[3 * h + 1] + threadIdx.x; i < heavy[3 * h + 2]; i += blockDim.x) emit_slot(em, i, heavy[3 * h], mean);
+                for (long long i = heavy[3 * h + 1] + threadIdx.x; i < heavy[3 * h + 2]; i += blockDim.x) emit_slot<EMIT>(em, i, heavy[3 * h], mean);
             __syncthreads();
             if (threadIdx.x == 0) n_heavy = 0;
         }
     }
 }
 
-// ancestor = first j with cdf[j] > target  (== searchsorted(cdf, target, side='right')), found hierarchically:
-//   level 0: a <= 2048-entry sample of the coarse table in shared memory            (11 steps, no global traffic)
-//   level 1: the coarse table (cdf at the end of every 32 entries; n/4 bytes: L2-resident)
-//   level 2: the 32 cdf entries of the group = one 256-byte run of the cdf            (5 steps)
-// so a lookup costs one DRAM sector of the cdf instead of log2(n) dependent probes scattered over 8n bytes.
-constexpr int kTop = 2048;
-
-struct TopTable {
-    long long m, stride;
-    int n_top;
-};
-
-__device__ __forceinline__ TopTable load_top(const unsigned long long* __restrict__ coarse, long long n, unsigned long long* top) {
-    TopTable t;
-    t.m = n_groups_for(n);
-    t.n_top = t.m < kTop ? (int)t.m : kTop;
-    t.stride = (t.m + t.n_top - 1) / t.n_top;
-    for (int k = threadIdx.x; k < t.n_top; k += blockDim.x) {
-        long long g = (long long)(k + 1) * t.stride - 1;
-        top[k] = __ldg(coarse + (g < t.m ? g : t.m - 1));
-    }
-    __syncthreads();
-    return t;
-}
-
-__device__ __forceinline__ long long hier_search(unsigned long long target, const unsigned long long* __restrict__ cdf,
-                                                 const unsigned long long* __restrict__ coarse, const unsigned long long* top, const TopTable& t,
-                                                 long long n) {
-    int lo = 0, hi = t.n_top - 1;  // first k with top[k] > target (top[n_top - 1] == total > target)
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (top[mid] > target) hi = mid; else lo = mid + 1;
-    }
-    long long glo = (long long)lo * t.stride, ghi = glo + t.stride - 1;
-    if (ghi > t.m - 1) ghi = t.m - 1;
-    while (glo < ghi) {  // first group whose last entry exceeds the target
-        const long long mid = (glo + ghi) >> 1;
-        if (__ldg(coarse + mid) > target) ghi = mid; else glo = mid + 1;
-    }
-    long long jlo = glo * kGroup, jhi = jlo + kGroup - 1;
-    if (jhi > n - 1) jhi = n - 1;
-    while (jlo < jhi) {
-        const long long mid = (jlo + jhi) >> 1;
-        if (__ldg(cdf + mid) > target) jhi = mid; else jlo = mid + 1;
-    }
-    return jlo;
-}
-
-// Multinomial (unsorted uniforms): one slot per thread, hierarchical search.
-__global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* __restrict__ w, const double* __restrict__ uniforms,
-                                                        long long n, const double* __restrict__ stats, WsView ws,
-                                                        const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
-                                                        double* __restrict__ cum_out, int* __restrict__ anc, SearchGen g) {
-    __shared__ unsigned long long top[kTop];
-    const bool resample = stats[CDW_STAT_RESAMPLE] != 0.0;
-    const double mean = stats[CDW_STAT_MEAN];
-    search_rearm(g);
-    if (!resample) {
+// Multinomial (unsorted uniforms): ancestor = first j with cdf[j] > target (== searchsorted(cdf, target, side='right')).
+// target = floor(u total) falls into bucket b (floor((b/n) total) <= target < floor(((b+1)/n) total)), and the ancestor into
+// [guide[b], guide[b + 1]] — on average one or two cdf entries: two dependent memory accesses instead of log2(n).
+__global__ void __launch_bounds__(kBlock) lookup_kernel(const double* __restrict__ w, const double* __restrict__ uniforms, long long n,
+                                                        const double* __restrict__ stats, WsView ws, const unsigned long long* __restrict__ cdf,
+                                                        const double* __restrict__ cum_in, double* __restrict__ cum_out, int* __restrict__ anc, SearchGen g) {
+    if (stats[CDW_STAT_RESAMPLE] == 0.0) {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-            if (anc) anc[i] = (int)i;
+            anc[i] = (int)i;
             if (cum_out) cum_out[i] = w[i];  // null update: cum += inc (resamplers.py:136-156)
         }
         return;
     }
+    const double mean = stats[CDW_STAT_MEAN];
     const unsigned long long total = ws.hdr[WS_TOTAL];
-    const double u0 = kind == CDW_RESAMPLE_SYSTEMATIC ? (g.gen ? philox_uniform53(g.seed, g.stream_id, 0) : uniforms[0]) : 0.0;
-    if (g.gen && g.uniforms_out && kind == CDW_RESAMPLE_SYSTEMATIC && blockIdx.x == 0 && threadIdx.x == 0) g.uniforms_out[0] = u0;
-    const TopTable t = load_top(ws.coarse, n, top);
+    const double inv_n = __ddiv_rn(1.0, (double)n), nd = (double)n;
+    const int* __restrict__ guide = ws.guide;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double u;
-        if (kind == CDW_RESAMPLE_SYSTEMATIC) u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
-        else if (g.gen) {
+        if (g.gen) {
             u = philox_uniform53(g.seed, g.stream_id, i);
             if (g.uniforms_out) g.uniforms_out[i] = u;
         } else u = uniforms[i];
-        anc[i] = (int)hier_search(fixed_target(u, total), cdf, ws.coarse, top, t, n);
+        const unsigned long long t = fixed_target(u, total);
+        long long b = (long long)(u * nd);
+        b = b < 0 ? 0 : (b > n - 1 ? n - 1 : b);
+        while (b > 0 && systematic_target(b, 0.0, inv_n, total) > t) --b;
+        while (b + 1 < n && systematic_target(b + 1, 0.0, inv_n, total) <= t) ++b;
+        long long lo = __ldcg(guide + b), hi = b + 1 < n ? (long long)__ldcg(guide + b + 1) : n - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldcg(cdf + mid) > t) hi = mid; else lo = mid + 1;
+        }
+        anc[i] = (int)lo;
         if (cum_out) {
             const double c = cum_in ? cum_in[i] : 0.0;
             cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));  // _update_particle: cum += (mean - cum) (resamplers.py:196-197)
@@ -433,122 +468,75 @@ __global__ void __launch_bounds__(kBlock) search_kernel(int kind, const double* 
     }
 }
 
-// Systematic (sorted targets): a block owns kSysSlots consecutive slots; their ancestors lie in one contiguous window
-// of the cdf, which is staged once in shared memory (8 B of cdf read per slot instead of log2(n) probes).  Windows that do
-// not fit (very uneven weights) fall back to the hierarchical search.
-constexpr int kSysPerThread = 4;
-constexpr int kSysSlots = kBlock * kSysPerThread;
-constexpr int kSysWindow = 3072;
-
-__global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double* __restrict__ w, const double* __restrict__ uniforms, long long n,
-                                                                   const double* __restrict__ stats, WsView ws,
-                                                                   const unsigned long long* __restrict__ cdf, const double* __restrict__ cum_in,
-                                                                   double* __restrict__ cum_out, int* __restrict__ anc, SearchGen g) {
-    __shared__ unsigned long long top[kTop];
-    __shared__ unsigned long long win[kSysWindow];
-    __shared__ long long bounds[2];
-    search_rearm(g);
-    if (stats[CDW_STAT_RESAMPLE] == 0.0) {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-            if (anc) anc[i] = (int)i;
-            if (cum_out) cum_out[i] = w[i];
-        }
-        return;
-    }
-    const double mean = stats[CDW_STAT_MEAN];
-    const unsigned long long total = ws.hdr[WS_TOTAL];
-    const double u0 = g.gen ? philox_uniform53(g.seed, g.stream_id, 0) : uniforms[0];
-    if (g.gen && g.uniforms_out && blockIdx.x == 0 && threadIdx.x == 0) g.uniforms_out[0] = u0;
-    const TopTable t = load_top(ws.coarse, n, top);
-    const long long n_chunks = (n + kSysSlots - 1) / kSysSlots;
-    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const long long i0 = chunk * kSysSlots;
-        const long long i1 = i0 + kSysSlots < n ? i0 + kSysSlots : n;  // slots [i0, i1)
-        __syncthreads();
-        if (threadIdx.x < 2) {
-            const long long i = threadIdx.x == 0 ? i0 : i1 - 1;
-            const double u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
-            bounds[threadIdx.x] = hier_search(fixed_target(u, total), cdf, ws.coarse, top, t, n);
-        }
-        __syncthreads();
-        const long long jlo = bounds[0], jhi = bounds[1];
-        const bool fits = jhi - jlo + 1 <= kSysWindow;
-        if (fits)
-            for (long long j = jlo + threadIdx.x; j <= jhi; j += blockDim.x) win[j - jlo] = __ldg(cdf + j);
-        __syncthreads();
-        for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-            const double u = __ddiv_rn(__dadd_rn((double)i, u0), (double)n);
-            const unsigned long long target = fixed_target(u, total);
-            long long a;
-            if (fits) {
-                int lo = 0, hi = (int)(jhi - jlo);
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (win[mid] > target) hi = mid; else lo = mid + 1;
-                }
-                a = jlo + lo;
-            } else {
-                a = hier_search(target, cdf, ws.coarse, top, t, n);
-            }
-            anc[i] = (int)a;
-            if (cum_out) {
-                const double c = cum_in ? cum_in[i] : 0.0;
-                cum_out[i] = CDW_ADD(c, CDW_ADD(mean, -c));
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ K2 + K3a fused (small n)
-// One launch of 8 cooperating CTAs (cdw_resample.cuh) does everything after the propagate kernel for n <= kFusedMax
-// particles: log-sum-exp / nESS / decision, Philox uniforms, integer cdf, search, cum update, re-arming of the running-min key.
-// Same integer algorithm as the multi-kernel path => same ancestors bit for bit; for batches this small the
-// multi-kernel path is pure launch latency (7 launches for ~30 us of work at n = 1e4).
-constexpr int kFusedThreads = 128;   // x 8 cooperating CTAs = the 1024 virtual threads of the canonical statistics order
-constexpr int kFusedMax = 24576;  // cdf in shared memory: 192 KB (covers 2 x 10^4 particles sharded over two GPUs)
-
-__global__ void __launch_bounds__(kFusedThreads) fused_resample_kernel(ResampleArgs r) {
-    extern __shared__ __align__(16) unsigned long long scratch[];  // 3 x 1024 words: the statistics tree of CTA 0
-    resample_coop<kFusedThreads>(r, (int)blockIdx.x, (int)gridDim.x, scratch);
-}
-
 // ------------------------------------------------------------------------------------------------ K3b: gather
+// One thread per float4 of the destination rows, kGatherUnroll elements in flight per thread: all ancestor indices first, then
+// all row loads (the gather is latency-bound: bytes in flight per SM are what sets the bandwidth).
+constexpr int kGatherUnroll = 4;
+
+template <bool PEER>
 __global__ void __launch_bounds__(kBlock) gather_kernel(const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
-                                                        const int* __restrict__ anc, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-                                                        const double* __restrict__ aux_in, double* __restrict__ aux_out,
-                                                        const int* __restrict__ label_in, int* __restrict__ label_out, long long n, int A) {
+                                                        const float4* const* __restrict__ peer_pos, const float4* const* __restrict__ peer_vel,
+                                                        const double* __restrict__ aux_in, const int* __restrict__ label_in,
+                                                        const double* const* __restrict__ peer_aux, const int* const* __restrict__ peer_label,
+                                                        long long n_per_rank, const int* __restrict__ anc, float4* __restrict__ pos_out,
+                                                        float4* __restrict__ vel_out, double* __restrict__ aux_out, int* __restrict__ label_out,
+                                                        long long n, int A) {
     const long long total = n * A;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long p = idx / A;
-        const int a = (int)(idx - p * A);
-        const long long src = anc[p];
-        pos_out[idx] = __ldg(pos_in + src * A + a);
-        if (vel_in) vel_out[idx] = __ldg(vel_in + src * A + a);
-        if (a == 0) {
-            if (aux_in) aux_out[p] = aux_in[src];
-            if (label_in) label_out[p] = label_in[src];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool with_vel = PEER ? peer_vel != nullptr : vel_in != nullptr;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * kGatherUnroll) {
+        long long p[kGatherUnroll], src[kGatherUnroll];
+        int a[kGatherUnroll];
+#pragma unroll
+        for (int k = 0; k < kGatherUnroll; ++k) {
+            const long long idx = base + k * stride;
+            p[k] = idx < total ? idx / A : -1;
+            a[k] = idx < total ? (int)(idx - p[k] * A) : 0;
+            src[k] = idx < total ? (long long)__ldg(anc + p[k]) : 0;
+        }
+        float4 x[kGatherUnroll], v[kGatherUnroll];
+#pragma unroll
+        for (int k = 0; k < kGatherUnroll; ++k) {
+            x[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = x[k];
+            if (p[k] < 0) continue;
+            if (PEER) {
+                const int r = (int)(src[k] / n_per_rank);
+                const long long l = src[k] - (long long)r * n_per_rank;
+                x[k] = peer_pos[r][l * A + a[k]];  // NVLink load when r is a peer (P2P-mapped pointer)
+                if (with_vel) v[k] = peer_vel[r][l * A + a[k]];
+            } else {
+                x[k] = __ldg(pos_in + src[k] * A + a[k]);
+                if (with_vel) v[k] = __ldg(vel_in + src[k] * A + a[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kGatherUnroll; ++k) {
+            if (p[k] < 0) continue;
+            const long long idx = base + k * stride;
+            pos_out[idx] = x[k];
+            if (with_vel) vel_out[idx] = v[k];
+            if (a[k] == 0) {
+                if (PEER) {
+                    const int r = (int)(src[k] / n_per_rank);
+                    const long long l = src[k] - (long long)r * n_per_rank;
+                    if (peer_aux) aux_out[p[k]] = peer_aux[r][l];
+                    if (peer_label) label_out[p[k]] = peer_label[r][l];
+                } else {
+                    if (aux_in) aux_out[p[k]] = aux_in[src[k]];
+                    if (label_in) label_out[p[k]] = label_in[src[k]];
+                }
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(kBlock) gather_peer_kernel(const float4* const* __restrict__ peer_pos, const float4* const* __restrict__ peer_vel,
-                                                             const double* const* __restrict__ peer_aux, const int* const* __restrict__ peer_label,
-                                                             long long n_per_rank, const int* __restrict__ anc, float4* __restrict__ pos_out,
-                                                             float4* __restrict__ vel_out, double* __restrict__ aux_out, int* __restrict__ label_out,
-                                                             long long n, int A) {
-    const long long total = n * A;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long p = idx / A;
-        const int a = (int)(idx - p * A);
-        const long long g = anc[p];
-        const int r = (int)(g / n_per_rank);
-        const long long src = g - (long long)r * n_per_rank;
-        pos_out[idx] = peer_pos[r][src * A + a];  // NVLink load when r is a peer (P2P-mapped pointer)
-        if (peer_vel) vel_out[idx] = peer_vel[r][src * A + a];
-        if (a == 0) {
-            if (peer_aux) aux_out[p] = peer_aux[r][src];
-            if (peer_label) label_out[p] = peer_label[r][src];
-        }
+// Per-iteration history spill (Particle._incremental_works / _ancestry, particles.py:38-47): after iteration t slot i holds
+// cumulative work cum[i] and the root label of its (possibly resampled) state, label[anc[i]].
+__global__ void __launch_bounds__(kBlock) record_lineage_kernel(const double* __restrict__ cum, const int* __restrict__ label, const int* __restrict__ anc,
+                                                                double* __restrict__ cum_row, int* __restrict__ label_row, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        cum_row[i] = cum[i];
+        label_row[i] = label[anc ? anc[i] : i];
     }
 }
 
@@ -566,6 +554,40 @@ __global__ void philox_uniforms_kernel(unsigned long long seed, unsigned long lo
         out[2 * i] = (double)a * 1.1102230246251565e-16;
         if (2 * i + 1 < n) out[2 * i + 1] = (double)b * 1.1102230246251565e-16;
     }
+}
+
+// One block: tell every peer "this rank has finished its epoch e" and wait until every peer has said so.  flags_local[r] is written
+// by rank r (through its peer-mapped pointer to this rank's array).  The epoch is a device-side counter (*epoch_counter, one
+// increment per call), so the launch carries no host-side constant and can be replayed from a CUDA graph; epochs only grow, the
+// flag arrays never need clearing.  The wait is bounded: after ~2 s it gives up and records the failure in *status (the caller
+// checks it; a hang would cost the whole node).
+__global__ void peer_barrier_kernel(unsigned long long* const* peer_flags, volatile unsigned long long* flags_local, int rank, int world,
+                                    unsigned long long* epoch_counter, int* status) {
+    __shared__ unsigned long long epoch_sh;
+    if (threadIdx.x == 0) {
+        epoch_sh = *epoch_counter + 1ull;
+        *epoch_counter = epoch_sh;
+    }
+    __syncthreads();
+    const unsigned long long epoch = epoch_sh;
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    if (r != rank) {
+        *(volatile unsigned long long*)(peer_flags[r] + rank) = epoch;
+    } else {
+        flags_local[rank] = epoch;
+    }
+    __threadfence_system();
+    long long spins = 0;
+    while (flags_local[r] < epoch) {
+        __nanosleep(100);
+        if (++spins > 20000000ll) {
+            atomicExch(status, 1);
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 template <typename T>
@@ -601,8 +623,9 @@ using namespace cdw;
 
 extern "C" size_t cdw_weight_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    return sizeof(unsigned long long) * WS_HEADER_WORDS + 2 * sizeof(double) * kMaxStatBlocks +
-           2 * sizeof(unsigned long long) * (size_t)(n_tiles_for(n) + 1) + sizeof(unsigned long long) * (size_t)(n_groups_for(n) + 4) + 32;
+    const size_t nt = (size_t)n_tiles_for(n);
+    return sizeof(unsigned long long) * WS_HEADER_WORDS + align16u(sizeof(unsigned long long) * nt) + align16u(sizeof(unsigned long long) * (nt + 1)) +
+           align16u(sizeof(unsigned long long) * (size_t)n) + align16u(sizeof(int) * (size_t)n) + 32;
 }
 
 extern "C" int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
@@ -616,28 +639,27 @@ extern "C" int cdw_weight_update(const double* u_new, const double* aux, const d
 }
 
 static int weight_stats_launch(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats, void* workspace,
-                               size_t workspace_bytes, cdw_stream stream, bool clear_header) {
+                               size_t workspace_bytes, cdw_stream stream, bool clear_header, uint64_t* rearm) {
     CDW_REQUIRE(w && wmin_key && stats && workspace && n > 0, "null argument or n == 0");
     CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
     CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+    CDW_REQUIRE(((size_t)w & 15) == 0 && ((size_t)workspace & 15) == 0, "w and workspace must be 16-byte aligned");
     WsView ws = ws_view(workspace, n);
     // every kernel that uses the header leaves it at rest (zero); a caller-facing call clears it anyway
     if (clear_header) CDW_CUDA(cudaMemsetAsync(ws.hdr, 0, sizeof(unsigned long long) * WS_HEADER_WORDS, (cudaStream_t)stream));
-    int b = 0;
-    while ((1ll << b) < n) ++b;  // ceil(log2 n)
-    int grid = blocks_for(n, kBlock * 4, sm_count() * 8);
-    if (grid > kMaxStatBlocks) grid = kMaxStatBlocks;
-    weight_stats_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(w, n, floor_threshold, (const unsigned long long*)wmin_key, stats, ws, 61 - b);
+    int grid = blocks_for(n, kBlock * 8, sm_count() * 8);
+    weight_stats_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(w, n, floor_threshold, (const unsigned long long*)wmin_key, stats, ws,
+                                                                   (unsigned long long*)rearm);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }
 
 extern "C" int cdw_weight_stats(const double* w, int64_t n, double floor_threshold, const uint64_t* wmin_key, double* stats,
                                 void* workspace, size_t workspace_bytes, cdw_stream stream) {
-    return weight_stats_launch(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream, true);
+    return weight_stats_launch(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream, true, nullptr);
 }
 
-static int resample_indices_launch(int kind, const double* w, const double* uniforms, int64_t n, const double* stats, const double* cum_in,
+static int resample_indices_launch(int kind, const double* w, const double* uniforms, int64_t n, double* stats, const double* cum_in,
                                    double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace, size_t workspace_bytes,
                                    cdw_stream stream, SearchGen gen) {
     CDW_REQUIRE(w && stats && anc_out && cdf_out && workspace && n > 0, "null argument or n == 0");
@@ -645,10 +667,11 @@ static int resample_indices_launch(int kind, const double* w, const double* unif
     CDW_REQUIRE(uniforms || gen.gen, "uniforms are required");
     CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
     CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
+    CDW_REQUIRE(((size_t)cdf_out & 15) == 0 && ((size_t)workspace & 15) == 0, "cdf_out and workspace must be 16-byte aligned");
     WsView ws = ws_view(workspace, n);
     cudaStream_t st = (cudaStream_t)stream;
     const long long nt = n_tiles_for(n);
-    int grid_t = (int)(nt < (long long)sm_count() * 16 ? nt : (long long)sm_count() * 16);
+    int grid_t = (int)(nt < (long long)sm_count() * 8 ? nt : (long long)sm_count() * 8);
     static const bool dbg = getenv("CDW_DEBUG_SYNC") != nullptr;
 #define CDW_DBG(name)                                                                       \
     if (dbg) {                                                                               \
@@ -656,27 +679,21 @@ static int resample_indices_launch(int kind, const double* w, const double* unif
         if (e_ == cudaSuccess) e_ = cudaGetLastError();                                      \
         if (e_ != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e_)); return CDW_ECUDA; } \
     }
-    cdf_tile_sums_kernel<<<grid_t, kBlock, 0, st>>>(w, n, stats, ws);
+    cdf_tile_sums_kernel<<<grid_t, kBlock, 0, st>>>(n, stats, ws);
     CDW_DBG("cdf_tile_sums_kernel")
-    cdf_scan_tiles_kernel<<<1, 1024, 0, st>>>(n, (double*)stats, ws);
-    CDW_DBG("cdf_scan_tiles_kernel")
-    static const bool sys_search = getenv("CDW_SYSTEMATIC_SEARCH") != nullptr;   // A/B: the windowed search form
-    if (kind == CDW_RESAMPLE_SYSTEMATIC && !sys_search) {
-        EmitArgs em = {};
-        em.uniforms = uniforms; em.cum_in = cum_in; em.cum_out = cum_out; em.anc = anc_out; em.gen = gen;
-        cdf_tile_scan_kernel<true><<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out, em);
+    EmitArgs em = {};
+    em.uniforms = uniforms; em.cum_in = cum_in; em.cum_out = cum_out; em.gen = gen;
+    if (kind == CDW_RESAMPLE_SYSTEMATIC) {
+        em.anc = anc_out;
+        cdf_tile_scan_kernel<EMIT_ANCESTORS><<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out, em);
         CDW_CUDA(cudaGetLastError());
         return CDW_OK;
     }
-    cdf_tile_scan_kernel<false><<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out, EmitArgs{});
+    em.anc = ws.guide;
+    cdf_tile_scan_kernel<EMIT_GUIDE><<<grid_t, kBlock, 0, st>>>(w, n, stats, ws, (unsigned long long*)cdf_out, em);
     CDW_DBG("cdf_tile_scan_kernel")
-    if (kind == CDW_RESAMPLE_SYSTEMATIC) {
-        int grid_s = blocks_for(n, kSysSlots, sm_count() * 8);
-        search_systematic_kernel<<<grid_s, kBlock, 0, st>>>(w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out, gen);
-    } else {
-        int grid_s = blocks_for(n, kBlock * 4, sm_count() * 8);
-        search_kernel<<<grid_s, kBlock, 0, st>>>(kind, w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out, gen);
-    }
+    int grid_s = blocks_for(n, kBlock * 2, sm_count() * 8);
+    lookup_kernel<<<grid_s, kBlock, 0, st>>>(w, uniforms, n, stats, ws, (const unsigned long long*)cdf_out, cum_in, cum_out, anc_out, gen);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }
@@ -686,7 +703,7 @@ extern "C" int cdw_resample_indices(int kind, const double* w, const double* uni
                                     cdw_stream stream) {
     CDW_REQUIRE(uniforms, "uniforms are required");
     SearchGen none = {};
-    return resample_indices_launch(kind, w, uniforms, n, stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream, none);
+    return resample_indices_launch(kind, w, uniforms, n, (double*)stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream, none);
 }
 
 extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double floor_threshold, uint64_t* wmin_key, uint64_t seed, uint64_t stream_id,
@@ -695,26 +712,25 @@ extern "C" int cdw_smc_resample(int kind, const double* w, int64_t n, double flo
     CDW_REQUIRE(w && wmin_key && stats && anc_out && cdf_out && uniforms && workspace && n > 0, "null argument or n == 0");
     CDW_REQUIRE(kind == CDW_RESAMPLE_MULTINOMIAL || kind == CDW_RESAMPLE_SYSTEMATIC, "unknown resampler kind");
     CDW_REQUIRE(n < (1ll << 31), "n must fit int32 ancestors");
-    cudaStream_t st = (cudaStream_t)stream;
-    static const char* no_fuse = getenv("CDW_NO_FUSED_RESAMPLE");
-    if (n <= kFusedMax && !no_fuse) {
-        int b = 0;
-        while ((1ll << b) < n) ++b;
-        ResampleArgs r = {};
-        r.kind = kind; r.n = (int)n; r.s1 = 61 - b; r.threshold = floor_threshold; r.w = w; r.wmin_key = (unsigned long long*)wmin_key;
-        r.seed = seed; r.stream_id = stream_id; r.stats = stats; r.cum_in = cum_in; r.cum_out = cum_out; r.anc = anc_out; r.uniforms_out = uniforms;
-        r.cdf_spill = (unsigned long long*)cdf_out; r.ws = workspace;
-        CDW_REQUIRE(workspace_bytes >= cdw_weight_workspace_bytes(n), "workspace too small");
-        fused_resample_kernel<<<kVirtualThreads / kFusedThreads, kFusedThreads, sizeof(unsigned long long) * 3 * kVirtualThreads, st>>>(r);
-        CDW_CUDA(cudaGetLastError());
-        return CDW_OK;
-    }
-    // multi-kernel form: statistics, three scan kernels, search (which also draws the uniforms and re-arms the key): 5 launches
-    int rc = weight_stats_launch(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream, false);
+    // statistics (the last block re-arms the running-min key), tile sums + their scan, tile scan with direct emission, and for
+    // multinomial resampling the lookup, which draws the Philox uniforms itself: 3 or 4 launches, no host decision in between
+    int rc = weight_stats_launch(w, n, floor_threshold, wmin_key, stats, workspace, workspace_bytes, stream, false, wmin_key);
     if (rc) return rc;
     SearchGen gen = {};
-    gen.gen = 1; gen.seed = seed; gen.stream_id = stream_id; gen.uniforms_out = uniforms; gen.rearm_key = (unsigned long long*)wmin_key;
+    gen.gen = 1; gen.seed = seed; gen.stream_id = stream_id; gen.uniforms_out = uniforms;
     return resample_indices_launch(kind, w, uniforms, n, stats, cum_in, cum_out, anc_out, cdf_out, workspace, workspace_bytes, stream, gen);
+}
+
+extern "C" int cdw_smc_weigh_resample(int kind, const double* inc_src, const int32_t* anc_prev, int64_t n, double floor_threshold, uint64_t* wmin_key,
+                                      uint64_t seed, uint64_t stream_id, double* stats, double* cum, double* inc_out, double* w_out, int32_t* anc_out,
+                                      uint64_t* cdf_out, double* uniforms, void* workspace, size_t workspace_bytes, cdw_stream stream) {
+    CDW_REQUIRE(inc_src && cum && w_out && wmin_key && n > 0, "null argument or n == 0");
+    CDW_REQUIRE(anc_prev != anc_out, "the previous and the new ancestors need distinct buffers");
+    int grid = blocks_for(n, kBlock * 4, sm_count() * 8);
+    weight_compose_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(inc_src, anc_prev, cum, n, inc_out, w_out, (unsigned long long*)wmin_key);
+    CDW_CUDA(cudaGetLastError());
+    return cdw_smc_resample(kind, w_out, n, floor_threshold, wmin_key, seed, stream_id, stats, cum, cum, anc_out, cdf_out, uniforms, workspace,
+                            workspace_bytes, stream);
 }
 
 extern "C" int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
@@ -724,9 +740,9 @@ extern "C" int cdw_gather_particles(const float* pos_in, const float* vel_in, co
     CDW_REQUIRE(pos_in != pos_out && (!vel_in || (vel_out && vel_in != vel_out)), "gather needs distinct in/out buffers");
     CDW_REQUIRE((!aux_in || aux_out) && (!label_in || label_out), "missing output");
     if (n == 0) return CDW_OK;
-    int grid = blocks_for(n * n_atoms, kBlock, sm_count() * 16);
-    gather_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const float4*)pos_in, (const float4*)vel_in, anc, (float4*)pos_out, (float4*)vel_out,
-                                                            aux_in, aux_out, label_in, label_out, n, n_atoms);
+    int grid = blocks_for(n * n_atoms, kBlock * kGatherUnroll, sm_count() * 8);
+    gather_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>((const float4*)pos_in, (const float4*)vel_in, nullptr, nullptr, aux_in, label_in, nullptr,
+                                                                   nullptr, 1, anc, (float4*)pos_out, (float4*)vel_out, aux_out, label_out, n, n_atoms);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }
@@ -738,9 +754,28 @@ extern "C" int cdw_gather_particles_peer(const float* const* peer_pos, const flo
     CDW_REQUIRE(peer_pos && pos_out && anc && n_ranks > 0 && n_per_rank > 0 && n_local >= 0 && n_atoms > 0, "null argument");
     CDW_REQUIRE((!peer_vel || vel_out) && (!peer_aux || aux_out) && (!peer_label || label_out), "missing output");
     if (n_local == 0) return CDW_OK;
-    int grid = blocks_for(n_local * n_atoms, kBlock, sm_count() * 16);
-    gather_peer_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const float4* const*)peer_pos, (const float4* const*)peer_vel, peer_aux, peer_label,
-                                                                 n_per_rank, anc, (float4*)pos_out, (float4*)vel_out, aux_out, label_out, n_local, n_atoms);
+    int grid = blocks_for(n_local * n_atoms, kBlock * kGatherUnroll, sm_count() * 8);
+    gather_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(nullptr, nullptr, (const float4* const*)peer_pos, (const float4* const*)peer_vel, nullptr,
+                                                                  nullptr, peer_aux, peer_label, n_per_rank, anc, (float4*)pos_out, (float4*)vel_out, aux_out,
+                                                                  label_out, n_local, n_atoms);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_record_lineage(const double* cum, const int32_t* label, const int32_t* anc, double* cum_row, int32_t* label_row, int64_t n,
+                                  cdw_stream stream) {
+    CDW_REQUIRE(cum && label && cum_row && label_row && n >= 0, "null argument");
+    if (n == 0) return CDW_OK;
+    record_lineage_kernel<<<blocks_for(n, kBlock * 4, sm_count() * 8), kBlock, 0, (cudaStream_t)stream>>>(cum, label, anc, cum_row, label_row, n);
+    CDW_CUDA(cudaGetLastError());
+    return CDW_OK;
+}
+
+extern "C" int cdw_peer_barrier(uint64_t* const* peer_flags, uint64_t* flags_local, int32_t rank, int32_t world, uint64_t* epoch_counter,
+                                int32_t* status, cdw_stream stream) {
+    CDW_REQUIRE(peer_flags && flags_local && epoch_counter && status && world > 0 && world <= 32 && rank >= 0 && rank < world, "bad argument");
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long* const*)peer_flags, (volatile unsigned long long*)flags_local, rank, world,
+                                                           (unsigned long long*)epoch_counter, status);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }

@@ -114,8 +114,14 @@ class ParticleEnsemble:
 
     Mirrors the per-particle fields of `Particle` (coddiwomple/particles.py:11-53): cumulative_work -> cum[P],
     auxiliary_work -> aux[P], ancestry[-1] -> label[P], state -> pos/vel[P][A] float4 rows, iteration -> scalar.
-    pos/vel/aux/label are double-buffered: the resampling copy of the reference (resamplers.py:123-129) is the
-    gather-on-load of the next propagate call.
+    pos/vel/aux/label (and the force rows that travel with a particle) are double-buffered: the resampling copy of the
+    reference (resamplers.py:123-129) is the gather-on-load of the next propagate call.
+
+    Two loops share this state:
+      * look-ahead (MCMC moves, the default): `equip_lookahead` + `iterate_lookahead` — every launch also produces the next
+        iteration's incremental works, and the resampling runs on a side stream beside the next launch (cdw_smc_lookahead,
+        cdw_smc_weigh_resample);
+      * sequential (Euler-Maruyama proposal, work tracking): `propagate_and_weigh` + `resample_fused`.
     """
 
     def __init__(self, system, n_particles, gid0=0, device=None, record_history=False, static_cache=True):
@@ -134,24 +140,35 @@ class ParticleEnsemble:
         self.cum = torch.zeros(P, dtype=torch.float64, device=d)
         self.inc = torch.zeros(P, dtype=torch.float64, device=d)
         self.W = torch.zeros(P, dtype=torch.float64, device=d)
-        self.anc = torch.arange(P, dtype=torch.int32, device=d)
+        # ancestors are double-buffered: the launch of iteration t gathers through anc_bufs[(t - 1) % 2] while the resampling of
+        # iteration t, which runs beside it, writes anc_bufs[t % 2]
+        self.anc_bufs = [torch.arange(P, dtype=torch.int32, device=d) for _ in range(2)]
+        self.anc_cur = 0
         self.nan_flags = torch.zeros(P, dtype=torch.int32, device=d)
         self.wmin_key = torch.zeros(1, dtype=torch.int64, device=d)
         self.uniforms = torch.zeros(max(P, 1), dtype=torch.float64, device=d)
-        self.cdf = torch.zeros(P, dtype=torch.int64, device=d)
+        self.cdf = torch.zeros(P + 2, dtype=torch.int64, device=d)[:P]
         self.ws_bytes = int(self.lib.cdw_weight_workspace_bytes(P))
         self.workspace = torch.zeros((self.ws_bytes + 7) // 8, dtype=torch.int64, device=d)
-        # static-term cache (include/cdw.h: cdw_static_cache): forces / energy of the lambda-independent terms at pos[k],
-        # double-buffered with the rows they belong to and gathered with them
+        # rows that travel with a particle besides (x, v): the look-ahead loop keeps the TOTAL forces F(x; lambda_next) there,
+        # the sequential loop the forces / energy of the lambda-independent terms (include/cdw.h: cdw_static_cache)
         self.static_cache = bool(static_cache)
-        self.fs = torch.zeros(2, P, A, 4, dtype=torch.float32, device=d) if self.static_cache else None
+        self.fs = torch.zeros(2, P, A, 4, dtype=torch.float32, device=d)
         self.us = torch.zeros(2, P, dtype=torch.float64, device=d) if self.static_cache else None
+        self.inc_ahead = torch.zeros(2, P, dtype=torch.float64, device=d)   # [t % 2]: incremental works of iteration t + 1, at the slots of launch t
         self.cache_valid = False
         self.cur = 0
         self.pending_gather = False  # anc has not been applied to (pos, vel, aux, label) yet
         self.iteration = 0
         self.record_history = record_history
         self.history = []
+        self._side = torch.cuda.Stream(device=d)
+        self._resampled = None   # event: the resampling launched last has finished (side stream)
+
+    @property
+    def anc(self):
+        """Ancestors still to be applied to the current rows."""
+        return self.anc_bufs[self.anc_cur]
 
     # ------------------------------------------------------------------ state access
     def set_positions(self, positions, velocities=None):
@@ -166,8 +183,15 @@ class ParticleEnsemble:
             self.vel[self.cur].zero_()
         self.pending_gather = False
 
+    def join(self):
+        """Make the current stream wait for the resampling that runs on the side stream."""
+        if self._resampled is not None:
+            torch.cuda.current_stream().wait_event(self._resampled)
+            self._resampled = None
+
     def materialize(self):
         """Apply a pending resampling gather (K3b) so that pos/vel/aux/label hold the resampled particles."""
+        self.join()
         if self.pending_gather:
             c, n = self.cur, 1 - self.cur
             _lib.check(self.lib.cdw_gather_particles(_lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.anc), _lib.ptr(self.pos[n]),
@@ -175,7 +199,7 @@ class ParticleEnsemble:
                                                     _lib.ptr(self.label[n]), self.P, self.A, _lib.current_stream()), "cdw_gather_particles")
             self.cur = n
             self.pending_gather = False
-            self.cache_valid = False  # the static-term rows were not gathered
+            self.cache_valid = False  # the rows that travel with the particles were not gathered
 
     @property
     def positions(self):
@@ -206,6 +230,62 @@ class ParticleEnsemble:
                                                  _lib.ptr(u), _lib.current_stream()), "cdw_reduced_potential")
         return u
 
+    # ---- look-ahead loop
+    def equip_lookahead(self, lam0, lam1, langevin):
+        """aux = -u_0(x_0), cum = 0 (ProposalFactory.equip_initial_sample, distribution_factories.py:180-220), plus what iteration 1
+        needs: F(x_0; lambda_1) and inc_1 = u_1(x_0) - u_0(x_0) (cdw_smc_lookahead with n_steps = 0)."""
+        self.materialize()
+        c = self.cur
+        prm = langevin.as_struct(0, n_steps=0)
+        _lib.check(self.lib.cdw_smc_lookahead(
+            self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), None, None, None, _lib.ptr(self.fs[c]), self.P, None, None, _lib.ptr(lam0),
+            _lib.ptr(lam1), C.byref(prm), C.c_uint64(0), C.c_uint64(0), C.c_int64(self.gid0), _lib.ptr(self.inc_ahead[0]) if lam1 is not None else None,
+            _lib.ptr(self.aux[c]), None, None, _lib.current_stream()), "cdw_smc_lookahead")
+        self.cum.zero_()
+        self.iteration = 0
+        self.anc_cur = 0
+        self.wmin_key.fill_(-1)  # ~0ull: arm the running min; the statistics kernel re-arms it after every use
+        self.cache_valid = False
+        self._resampled = None
+
+    def iterate_lookahead(self, t, lam_t, lam_next, langevin, seed, stats_row, kind, floor_threshold, resample_seed, randomize_velocities=False,
+                          after_resample=None):
+        """Iteration t of the reference loop (openmm/coddiwomple.py:314-328) as two concurrent pieces:
+          side stream   W_t = cum + inc_t (the works the PREVIOUS launch left behind), nESS, decision, ancestors a_t, cum   (cdw_smc_weigh_resample)
+          this stream   gather by a_{t-1}, (V R O R E V)^n at lambda_t, then E at lambda_{t+1}: forces and inc_{t+1}         (cdw_smc_lookahead)
+        `after_resample(t)` (optional) is called with the side stream current, right behind the resampling."""
+        self.iteration = t
+        main = torch.cuda.current_stream()
+        prev_anc = self.anc_bufs[(t - 1) % 2] if t > 1 else None
+        launched = torch.cuda.Event()
+        launched.record(main)
+        self._side.wait_event(launched)           # the launch that wrote inc_ahead[(t - 1) % 2] (and read anc_bufs[t % 2]) is behind us
+        with torch.cuda.stream(self._side):
+            _lib.check(self.lib.cdw_smc_weigh_resample(
+                int(kind), _lib.ptr(self.inc_ahead[(t - 1) % 2]), _lib.ptr(prev_anc), self.P, float(floor_threshold), _lib.ptr(self.wmin_key),
+                C.c_uint64(resample_seed), C.c_uint64(t), _lib.ptr(stats_row), _lib.ptr(self.cum), _lib.ptr(self.inc), _lib.ptr(self.W),
+                _lib.ptr(self.anc_bufs[t % 2]), _lib.ptr(self.cdf), _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes,
+                _lib.current_stream()), "cdw_smc_weigh_resample")
+            if after_resample is not None:
+                after_resample(t)
+            resampled = torch.cuda.Event()
+            resampled.record(self._side)
+        if self._resampled is not None:           # a_{t-1}: the resampling launched one iteration ago
+            main.wait_event(self._resampled)
+        c, n = self.cur, 1 - self.cur
+        prm = langevin.as_struct(_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0)
+        _lib.check(self.lib.cdw_smc_lookahead(
+            self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.fs[c]), _lib.ptr(self.pos[n]), _lib.ptr(self.vel[n]),
+            _lib.ptr(self.fs[n]), self.P, _lib.ptr(prev_anc), _lib.ptr(self.label[c]), _lib.ptr(lam_t), _lib.ptr(lam_next), C.byref(prm), C.c_uint64(seed),
+            C.c_uint64(t * max(langevin.n_steps, 1)), C.c_int64(self.gid0), _lib.ptr(self.inc_ahead[t % 2]) if lam_next is not None else None,
+            _lib.ptr(self.aux[n]), _lib.ptr(self.label[n]), _lib.ptr(self.nan_flags), _lib.current_stream()), "cdw_smc_lookahead")
+        self._resampled = resampled
+        self.cur = n
+        self.anc_cur = t % 2
+        self.pending_gather = True
+        self.cache_valid = False
+
+    # ---- sequential loop
     def seed_static_cache(self, lam_row, kT, aux_out=None):
         """Evaluate the static terms at the current rows (an n_steps = 0 cdw_smc_propagate_cached call): fills fs/us[cur]
         and, optionally, aux_out = -u(x; lambda)."""
@@ -229,12 +309,15 @@ class ParticleEnsemble:
             self.aux[self.cur].copy_(-u0)
         self.cum.zero_()
         self.iteration = 0
+        self.anc_cur = 0
+        self._resampled = None
         self.wmin_key.fill_(-1)  # ~0ull: arm the running min; cdw_smc_resample re-arms it after every iteration
         return u0
 
     def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None, ula=False):
         """Fused K3b-on-load + K1 + K4 + first half of K2 (include/cdw.h: cdw_smc_propagate).  Advances `iteration`.
         ula=True swaps BAOAB for the Euler-Maruyama proposal and its generalised incremental work (CDW_FLAG_ULA)."""
+        self.join()
         self.iteration += 1
         c, n = self.cur, 1 - self.cur
         flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0) | (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
@@ -259,36 +342,14 @@ class ParticleEnsemble:
         self.cur = n
         self.pending_gather = False
 
-    def iterate(self, lam_row, langevin, seed, stats_row, kind, floor_threshold, resample_seed, stream_id, randomize_velocities=False, ula=False):
-        """One whole SMC iteration in one call (include/cdw.h: cdw_smc_iteration): propagate_and_weigh + resample_fused.
-        For MCMC moves on a batch that fits the GPU at once this is a single kernel launch in which an extra team of thread blocks
-        resamples while the others are still integrating."""
-        self.iteration += 1
-        flags = _lib.CDW_FLAG_ULA if ula else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0)
-        prm = langevin.as_struct(flags)
-        use_cache = self.static_cache and langevin.n_steps > 0
-        if use_cache and not self.cache_valid:
-            self.seed_static_cache(lam_row, langevin.kT)
-        c, n = self.cur, 1 - self.cur
-        cache = _lib.static_cache(self.fs[c], self.us[c], self.fs[n], self.us[n]) if use_cache else None
-        anc = self.anc if self.pending_gather else None
-        _lib.check(self.lib.cdw_smc_iteration(
-            self.system.handle, _lib.ptr(self.pos[c]), _lib.ptr(self.vel[c]), _lib.ptr(self.pos[n]), _lib.ptr(self.vel[n]), self.P, _lib.ptr(anc),
-            _lib.ptr(self.aux[c]), _lib.ptr(self.cum), _lib.ptr(self.label[c]), _lib.ptr(lam_row), C.byref(prm), C.c_uint64(seed),
-            C.c_uint64(self.iteration * max(langevin.n_steps, 1)), C.c_int64(self.gid0), _lib.ptr(self.inc), _lib.ptr(self.W), _lib.ptr(self.aux[n]),
-            _lib.ptr(self.label[n]), _lib.ptr(self.nan_flags), _lib.ptr(self.wmin_key), C.byref(cache) if cache is not None else None, int(kind),
-            float(floor_threshold), C.c_uint64(resample_seed), C.c_uint64(stream_id), _lib.ptr(stats_row), _lib.ptr(self.anc), _lib.ptr(self.cdf),
-            _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_smc_iteration")
-        self.cache_valid = use_cache
-        self.cur = n
-        self.pending_gather = True
-
     def resample_fused(self, stats_row, kind, floor_threshold, seed, stream_id):
         """K2 second half + K3a (+ uniforms, + re-arming the running min) in one call: cdw_smc_resample."""
+        out = self.anc_bufs[1 - self.anc_cur]
         _lib.check(self.lib.cdw_smc_resample(int(kind), _lib.ptr(self.W), self.P, float(floor_threshold), _lib.ptr(self.wmin_key), C.c_uint64(seed),
-                                            C.c_uint64(stream_id), _lib.ptr(stats_row), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(self.anc),
+                                            C.c_uint64(stream_id), _lib.ptr(stats_row), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(out),
                                             _lib.ptr(self.cdf), _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()),
                    "cdw_smc_resample")
+        self.anc_cur = 1 - self.anc_cur
         self.pending_gather = True
 
     def weight_stats(self, stats_row, floor_threshold, w=None, wmin_key=None, n=None):
@@ -305,9 +366,11 @@ class ParticleEnsemble:
     def resample(self, stats_row, kind, uniforms=None):
         """K3a: ancestors from the integer cdf (identity + null update when the decision in stats_row says so)."""
         u = self.uniforms if uniforms is None else uniforms
+        out = self.anc_bufs[1 - self.anc_cur]
         _lib.check(self.lib.cdw_resample_indices(int(kind), _lib.ptr(self.W), _lib.ptr(u), self.P, _lib.ptr(stats_row), _lib.ptr(self.cum),
-                                                _lib.ptr(self.cum), _lib.ptr(self.anc), _lib.ptr(self.cdf), _lib.ptr(self.workspace), self.ws_bytes,
+                                                _lib.ptr(self.cum), _lib.ptr(out), _lib.ptr(self.cdf), _lib.ptr(self.workspace), self.ws_bytes,
                                                 _lib.current_stream()), "cdw_resample_indices")
+        self.anc_cur = 1 - self.anc_cur
         self.pending_gather = True
 
 
@@ -315,17 +378,21 @@ RESAMPLER_KINDS = {"multinomial": _lib.CDW_RESAMPLE_MULTINOMIAL, "systematic": _
 
 
 class SMCEngine:
-    """The whole anneal on one GPU: T-1 iterations of (propagate+weigh, stats, uniforms, resample), no host sync.
+    """The whole anneal on one GPU, no host synchronisation inside (the resampling decision is taken on the device).
 
     Order of operations = the reference loop (openmm/coddiwomple.py:312-331), see oracle/smc.py for the array form.
+    MCMC moves (`proposal="baoab"`) run the look-ahead loop: ONE propagate launch per iteration on the main stream, the weight
+    statistics / resampling of the same iteration beside it on a side stream.  The Euler-Maruyama proposal, whose weights need the
+    move itself, and `lookahead=False` run propagate and resample back to back.
     """
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5,
                  always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None, record_works_every=None,
-                 proposal="baoab", static_cache=True):
+                 proposal="baoab", static_cache=True, record_lineage=False, lookahead=True):
         if proposal not in ("baoab", "ula"):
             raise ValueError("proposal must be 'baoab' (MCMC move, openmm/integrators.py:19-465) or 'ula' (Euler-Maruyama, :666-888)")
         self.proposal = proposal
+        self.lookahead = bool(lookahead) and proposal == "baoab"
         self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history, static_cache=static_cache)
         self.system = self.ensemble.system
         self.langevin = langevin or LangevinParameters()
@@ -344,6 +411,13 @@ class SMCEngine:
             k = self.record_works_every
             self._work_rows = [t for t in range(1, self.T) if t % k == 0 or t == self.T - 1]
             self._works = torch.zeros(len(self._work_rows) + 1, self.ensemble.P, dtype=torch.float64, device=self.ensemble.device)
+        # optional per-iteration spill of (cumulative work, root label) of every slot: what the reference keeps in
+        # Particle._incremental_works / Particle._ancestry (particles.py:38-47); row t - 1 = state of the ensemble after iteration t
+        self.record_lineage = bool(record_lineage)
+        if self.record_lineage:
+            self._cum_hist = torch.zeros(max(self.T - 1, 1), self.ensemble.P, dtype=torch.float64, device=self.ensemble.device)
+            self._label_hist = torch.zeros(max(self.T - 1, 1), self.ensemble.P, dtype=torch.int32, device=self.ensemble.device)
+            self._lineage_due = None
 
     @property
     def beta(self):
@@ -352,42 +426,84 @@ class SMCEngine:
     def load(self, positions, velocities=None):
         """Stage the initial particles (samples of the first target) into buffer 0."""
         e = self.ensemble
-        e.cur, e.pending_gather, e.iteration = 0, False, 0
+        e.cur, e.pending_gather, e.iteration, e.anc_cur, e._resampled = 0, False, 0, 0, None
         e.set_positions(positions, velocities)
+
+    def _equip(self):
+        if self.lookahead:
+            self.ensemble.equip_lookahead(self.lam[0], self.lam[1] if self.T > 1 else None, self.langevin)
+        else:
+            self.ensemble.equip_initial(self.lam[0], self.beta)
+        self.stats.zero_()
+        if self.record_lineage:
+            self._lineage_due = None
 
     def initialize(self, positions, velocities=None):
         self.load(positions, velocities)
-        self.ensemble.equip_initial(self.lam[0], self.beta)
-        self.stats.zero_()
+        self._equip()
 
+    # ------------------------------------------------------------------ sequential loop (also the public two-call form)
     def propagate(self, t):
-        """First kernel of iteration t (1-based): gather-on-load + E/F + incremental work + BAOAB + closing energy."""
+        """First kernel of iteration t (1-based): gather-on-load + E/F + incremental work + move + closing energy."""
         self.ensemble.propagate_and_weigh(self.lam[t], self.langevin, self.seed, randomize_velocities=(t == 1), ula=(self.proposal == "ula"))
 
     def finish_iteration(self, t):
-        """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + search, cum update."""
+        """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + ancestors, cum update."""
         self.ensemble.resample_fused(self.stats[t], self.kind, self.threshold, self.resample_seed, t)
-        self._after_iteration(t)
+        self._after_resample(t)
+        self._record_lineage(t)
 
-    def _after_iteration(self, t):
+    # ------------------------------------------------------------------ bookkeeping hooks
+    def _after_resample(self, t):
+        """Runs right behind the resampling of iteration t (on the stream it ran on)."""
         e = self.ensemble
         if self.record_works_every and t in self._work_rows:
             self._works[self._work_rows.index(t) + 1].copy_(e.cum)
-        n_u = e.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
         if e.record_history:
-            e.history.append(dict(t=t, inc=e.inc.clone(), W=e.W.clone(), cum=e.cum.clone(), anc=e.anc.clone(), uniforms=e.uniforms[:n_u].clone()))
+            n_u = e.P if self.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 1
+            anc = e.anc_bufs[t % 2] if self.lookahead else e.anc
+            e.history.append(dict(t=t, inc=e.inc.clone(), W=e.W.clone(), cum=e.cum.clone(), anc=anc.clone(), uniforms=e.uniforms[:n_u].clone()))
+
+    def _record_lineage(self, t):
+        """Spill (cum, root label) after iteration t; needs both the launch (labels) and the resampling (ancestors, cum) of t."""
+        if not self.record_lineage:
+            return
+        e = self.ensemble
+        _lib.check(e.lib.cdw_record_lineage(_lib.ptr(e.cum), _lib.ptr(e.label[e.cur]), _lib.ptr(e.anc if e.pending_gather else None),
+                                           _lib.ptr(self._cum_hist[t - 1]), _lib.ptr(self._label_hist[t - 1]), e.P, _lib.current_stream()),
+                   "cdw_record_lineage")
 
     def step(self, t):
-        """Iteration t of the reference loop (openmm/coddiwomple.py:314-328): one cdw_smc_iteration call."""
-        self.ensemble.iterate(self.lam[t], self.langevin, self.seed, self.stats[t], self.kind, self.threshold, self.resample_seed, t,
-                              randomize_velocities=(t == 1), ula=(self.proposal == "ula"))
-        self._after_iteration(t)
+        """Iteration t of the reference loop (openmm/coddiwomple.py:314-328)."""
+        if not self.lookahead:
+            self.propagate(t)
+            self.finish_iteration(t)
+            return
+        e = self.ensemble
+        if self.record_lineage and self._lineage_due is not None:
+            # iteration t - 1 is complete once its resampling has finished; cum is rewritten by the resampling of iteration t, so the
+            # spill has to sit between the two (it costs the overlap: histories are a debugging / analysis aid)
+            e.join()
+            self._record_lineage(self._lineage_due)
+            self._lineage_due = None
+        e.iterate_lookahead(t, self.lam[t], self.lam[t + 1] if t + 1 < self.T else None, self.langevin, self.seed, self.stats[t], self.kind,
+                            self.threshold, self.resample_seed, randomize_velocities=(t == 1), after_resample=self._after_resample)
+        if self.record_lineage:
+            self._lineage_due = t
+
+    def finish(self):
+        """Join the side stream, spill the last iteration's history if histories are kept, and apply the last ancestors."""
+        self.ensemble.join()
+        if self.record_lineage and self.lookahead and self._lineage_due is not None:
+            self._record_lineage(self._lineage_due)
+            self._lineage_due = None
+        self.ensemble.materialize()
+        return self
 
     def run(self):
         for t in range(1, self.T):
             self.step(t)
-        self.ensemble.materialize()
-        return self
+        return self.finish()
 
     def anneal(self, positions, velocities=None):
         if self.graph is not None:
@@ -397,29 +513,29 @@ class SMCEngine:
 
     # ------------------------------------------------------------------ CUDA graph of the whole anneal
     def _body(self):
-        self.ensemble.equip_initial(self.lam[0], self.beta)
-        self.stats.zero_()
+        self._equip()
         self.run()
 
     def capture(self):
-        """Capture `equip initial sample + T-1 iterations + final gather` (T + 1 launches for MCMC moves: one per iteration) into one CUDA graph.
-        The loop has no host decision (the resampling test runs on the device), so the whole anneal replays as a
-        single graph launch; positions are (re)staged with load() before each replay."""
+        """Capture `equip initial sample + T-1 iterations + final gather` into one CUDA graph (look-ahead loop: a chain of T-1
+        propagate launches with the resampling kernels forked beside it).  The loop has no host decision (the resampling
+        test runs on the device), so the whole anneal replays as a single graph launch; positions are (re)staged with load()
+        before each replay."""
         e = self.ensemble
         if e.record_history:
             raise ValueError("record_history needs the eager loop")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
-            e.cur, e.pending_gather, e.iteration = 0, False, 0
+            e.cur, e.pending_gather, e.iteration, e.anc_cur, e._resampled = 0, False, 0, 0, None
             self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        e.cur, e.pending_gather, e.iteration = 0, False, 0
+        e.cur, e.pending_gather, e.iteration, e.anc_cur, e._resampled = 0, False, 0, 0, None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._body()
-        self._graph_final = (e.cur, e.pending_gather, e.iteration)
+        self._graph_final = (e.cur, e.pending_gather, e.iteration, e.anc_cur)
         self.graph = g
         return self
 
@@ -427,7 +543,7 @@ class SMCEngine:
         self.load(positions, velocities)
         self.graph.replay()
         e = self.ensemble
-        e.cur, e.pending_gather, e.iteration = self._graph_final
+        e.cur, e.pending_gather, e.iteration, e.anc_cur = self._graph_final
         return self
 
     # ------------------------------------------------------------------ results (host side; these synchronise)
@@ -435,18 +551,23 @@ class SMCEngine:
         return self.ensemble.cum.cpu().numpy()
 
     def free_energy(self):
-        """-log mean exp(-cum) in kT."""
-        c = self.ensemble.cum.cpu().numpy()
-        m = (-c).max()
-        return float(-(m + np.log(np.exp(-c - m).sum())) + np.log(c.size))
+        """-log mean exp(-cum) in kT (reduced on the device)."""
+        c = self.ensemble.cum
+        return float(-torch.logsumexp(-c, 0) + np.log(c.numel()))
 
     def resampled_iterations(self):
-        s = self.stats.cpu().numpy()
-        return [t for t in range(1, self.T) if s[t, _lib.STAT_RESAMPLE] != 0.0]
+        s = self.stats[:, _lib.STAT_RESAMPLE].cpu().numpy()
+        return [t for t in range(1, self.T) if s[t] != 0.0]
 
     def work_history(self):
         """(n_records + 1, P) cumulative works in kT; row 0 is the zero every AIS record starts with."""
         return self._works.cpu().numpy()
+
+    def lineage(self):
+        """dict(cum=(T-1, P) cumulative works, labels=(T-1, P) root labels) after every iteration (host arrays)."""
+        if not self.record_lineage:
+            raise _lib.CdwError("the per-iteration histories were not recorded: construct the engine with record_lineage=True")
+        return dict(cum=self._cum_hist.cpu().numpy(), labels=self._label_hist.cpu().numpy())
 
     def ness_trace(self):
         return self.stats[1:, _lib.STAT_NESS].cpu().numpy()

@@ -59,7 +59,7 @@ def annealed_importance_sampling(system, endstate_cache_filename, directory_name
 def mcmc_smc_resampler(system, endstate_cache_filename, directory_name, trajectory_prefix, md_topology, number_of_particles, parameter_sequence,
                        observable=nESS, threshold=vanilla_floor_threshold, alchemical_composability=RelativeAlchemicalState,
                        integrator_kwargs=DEFAULT_INTEGRATOR_KWARGS, record_state_work_interval=1, trajectory_write_interval=1, resampler=None,
-                       seed=None):
+                       seed=None, record_histories=None):
     """Single-direction annealing SMC in the AIS regime with resampling; returns the particles (ParticleList)."""
     pressure = handle_pressure(system)
     print(f"pressure: {pressure}")
@@ -78,6 +78,6 @@ def mcmc_smc_resampler(system, endstate_cache_filename, directory_name, trajecto
         else np.random.randint(0, num_frames, number_of_particles)
     initial_positions = frames[random_frames]
     particles = SMC(target_factory, proposal_factory, number_of_particles, reporter, resampler, initial_positions=initial_positions,
-                    observable=observable, threshold=threshold, seed=seed,
+                    observable=observable, threshold=threshold, seed=seed, record_histories=record_histories,
                     state_factory=lambda x, v: OpenMMParticleState(positions=x, velocities=v))
     return particles

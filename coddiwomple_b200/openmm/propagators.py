@@ -1,6 +1,7 @@
 """OpenMM Propagator Adapter module — `OMMBIP` with the reference's `apply` signature
 (coddiwomple/openmm/propagators.py:21-261), executed by the fused BAOAB kernel (cdw_baoab)."""
 import ctypes as C
+import logging
 
 import numpy as np
 import torch
@@ -9,6 +10,8 @@ from .. import _lib
 from ..engine import positions_to_rows
 from ..propagators import Propagator
 from .states import OpenMMParticleState
+
+_logger = logging.getLogger("openmm_propagators")
 
 
 class OMMBIP(Propagator):
@@ -73,6 +76,28 @@ class OMMBIP(Propagator):
                                      _lib.ptr(out["u_last"]), _lib.ptr(out["shadow"]), _lib.ptr(out["proposal"]), _lib.ptr(out["nan"]),
                                      _lib.current_stream()), "cdw_baoab")
         self._step_counter += max(int(n_steps), 1)
+        # NaN restart loop (openmm/propagators.py:134-190): a replica whose move produced a non-finite energy was left at its
+        # pre-move state by the kernel; it is integrated again (fresh noise: the step counter has moved on), up to
+        # n_restart_attempts times.  Whatever is still flagged after the last attempt stays reverted, as in the reference.
+        out["attempts"] = 0
+        for attempt in range(int(self.n_restart_attempts)):
+            bad = torch.nonzero(out["nan"]).flatten()
+            if bad.numel() == 0:
+                break
+            _logger.warning(f"Potential energy is NaN after {attempt} attempts of integration with move {self.__class__.__name__} Attempting a restart...")
+            sub_pos, sub_vel = pos_rows[bad].contiguous(), vel_rows[bad].contiguous()
+            n = int(bad.numel())
+            sub = {k: torch.zeros(n, dtype=out[k].dtype, device=d) for k in ("u_first", "u_last", "shadow", "proposal", "nan")}
+            _lib.check(self.lib.cdw_baoab(self.pdf_state.device_system.handle, _lib.ptr(sub_pos), _lib.ptr(sub_vel), n, _lib.ptr(self._context_lambda),
+                                         C.byref(prm), C.c_uint64(self._seed), C.c_uint64(self._step_counter), C.c_int64(gid0), _lib.ptr(sub["u_first"]),
+                                         _lib.ptr(sub["u_last"]), _lib.ptr(sub["shadow"]), _lib.ptr(sub["proposal"]), _lib.ptr(sub["nan"]),
+                                         _lib.current_stream()), "cdw_baoab")
+            self._step_counter += max(int(n_steps), 1)
+            pos_rows[bad] = sub_pos
+            vel_rows[bad] = sub_vel
+            for k in sub:
+                out[k][bad] = sub[k]
+            out["attempts"] = attempt + 1
         return out
 
     def apply(self, particle_state, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, returnable_key=None,
@@ -83,8 +108,7 @@ class OMMBIP(Propagator):
         out = self.apply_batch(pos, vel, n_steps=n_steps, reset_integrator=reset_integrator, apply_pdf_to_context=apply_pdf_to_context,
                                randomize_velocities=randomize_velocities)
         if int(out["nan"].item()):
-            import logging
-            logging.getLogger("openmm_propagators").warning("Potential energy is NaN after 0 attempts of integration with move OMMBIP")
+            _logger.warning(f"Potential energy is NaN after {out['attempts']} attempts of integration with move {self.__class__.__name__}")
         else:
             self.integrator.shadow_work += float(out["shadow"].item())
             self.integrator.proposal_work += float(out["proposal"].item())

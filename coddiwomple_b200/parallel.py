@@ -7,14 +7,16 @@ state"):
     labels of those slots live in ITS HBM only (double-buffered rows, exported to the other ranks with CUDA IPC so
     that every rank can read every rank's rows over NVLink);
   * the per-particle weights are tiny (8 B) and every rank needs the global normaliser, nESS, the resampling decision
-    and the global cdf: after the fused propagate kernel each rank contributes its slice W_loc to ONE NCCL all-gather
-    (the (max, sum-exp) all-reduce of the north star is subsumed: every rank reduces the gathered vector itself, in the
-    same order, so the statistics are bit-identical on all ranks and identical to a single-GPU run);
+    and the global cdf: each rank contributes its slice of incremental works to ONE NCCL all-gather per iteration
+    (the (max, sum-exp) all-reduce of the north star is subsumed: every rank reduces the gathered vector itself with
+    exact integer sums, so the statistics are bit-identical on all ranks and identical to a single-GPU run); in the
+    look-ahead loop that all-gather and the resampling run on a side stream BESIDE the propagate launch;
   * ancestors are global ids; the next propagate kernel loads each slot's ancestor row straight from the owning
     rank's buffer through a peer-mapped pointer: the resampling gather, the NVLink all-to-all migration and the
     propagation are one kernel (cdw_smc_propagate_sharded);
-  * the all-gather is also the cross-rank ordering point: a rank's buffers are only read by peers after that rank's
-    own all-gather contribution, i.e. after its propagate kernel has written them.
+  * cross-rank ordering (a rank's rows are only read by peers after the launch that wrote them has finished) is a
+    one-block peer barrier over NVLink flags in front of every launch (cdw_peer_barrier); in the sequential loop the
+    all-gather itself is the ordering point.
 
 Noise is keyed by the global particle id and the weights are reduced identically everywhere, so an anneal on G GPUs
 is bit-identical to the same anneal on one GPU (tests/multi_gpu_check.py asserts exactly that).
@@ -81,13 +83,22 @@ class _IpcBuffer:
 
 
 class ShardedSMCEngine:
-    """Same loop as SMCEngine over `n_particles` GLOBAL particles, sharded over the ranks of `group` (NCCL)."""
+    """Same loop as SMCEngine over `n_particles` GLOBAL particles, sharded over the ranks of `group` (NCCL).
+
+    MCMC moves run the look-ahead loop (cdw_smc_lookahead_sharded): per iteration and rank
+      main stream   peer barrier (every rank's rows of iteration t - 1 are in place), then ONE launch: gather the ancestors' rows
+                    over NVLink, integrate, evaluate at lambda_{t+1} (forces for the next launch, incremental works inc_{t+1});
+      side stream   all-gather of the 8-byte incremental works, then the global resampling of iteration t on the replicated weight
+                    vector — beside the launch, so neither the collective's latency nor the resampling is on the critical path.
+    The Euler-Maruyama proposal (weights need the move) keeps propagate -> all-gather -> resample back to back.
+    """
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5, always_resample=False,
                  seed=0, resample_seed=1, group=None, proposal="baoab"):
         if proposal not in ("baoab", "ula"):
             raise ValueError("proposal must be 'baoab' or 'ula'")
         self.proposal = proposal
+        self.lookahead = proposal == "baoab"
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (backend nccl, one process per GPU)")
         self.group = group
@@ -108,32 +119,37 @@ class ShardedSMCEngine:
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)
         d, P, Pl, A = self.device, self.P, self.P_loc, self.A
-        # ---- sharded state, double-buffered, IPC-exported
+        # ---- sharded state, double-buffered, IPC-exported ("fs": the force rows that travel with a particle — total forces at the
+        # next lambda in the look-ahead loop, static-term forces in the sequential loop)
         self._opened = []
         self._bufs = {name: [_IpcBuffer(self.lib, shape, dt) for _ in range(2)]
                       for name, shape, dt in (("pos", (Pl, A, 4), torch.float32), ("vel", (Pl, A, 4), torch.float32), ("aux", (Pl,), torch.float64),
                                               ("label", (Pl,), torch.int32), ("fs", (Pl, A, 4), torch.float32), ("us", (Pl,), torch.float64))}
         self.peer = {name: [self._exchange(name, b) for b in range(2)] for name in self._bufs}
+        # cross-rank ordering flags (cdw_peer_barrier): flags[r] = last epoch rank r has completed
+        self._flags = _IpcBuffer(self.lib, (2 * self.world,), torch.float64)   # (uint64 words; the dtype only sizes the buffer)
+        self._peer_flags = self._exchange_buffer(self._flags)
+        self._barrier_status = torch.zeros(1, dtype=torch.int32, device=d)
+        self._epoch_counter = torch.zeros(1, dtype=torch.int64, device=d)   # incremented by the barrier launches themselves (graph-replayable)
         # ---- replicated weights (global length on every rank)
         self.W = torch.zeros(P, dtype=torch.float64, device=d)
+        self.inc = torch.zeros(P, dtype=torch.float64, device=d)
         self.W_loc = torch.zeros(Pl, dtype=torch.float64, device=d)
         self.inc_loc = torch.zeros(Pl, dtype=torch.float64, device=d)
+        self.inc_ahead_loc = torch.zeros(2, Pl, dtype=torch.float64, device=d)   # [t % 2]: inc_{t+1} of this rank's slots after launch t
+        self.inc_ahead = torch.zeros(P, dtype=torch.float64, device=d)           # all-gathered
         self.cum = torch.zeros(P, dtype=torch.float64, device=d)
-        # ancestors are double-buffered: iteration t gathers through anc_bufs[(t - 1) % 2] while its resampling, which overlaps
-        # the integration, already writes anc_bufs[t % 2]
+        # ancestors are double-buffered: launch t gathers through anc_bufs[(t - 1) % 2] while the resampling of iteration t, which
+        # runs beside it, writes anc_bufs[t % 2]
         self.anc_bufs = [torch.arange(P, dtype=torch.int32, device=d) for _ in range(2)]
         self.anc_cur = 0
-        self.f_open = torch.zeros(Pl, A, 4, dtype=torch.float32, device=d)   # hand-over between the two launches of a split iteration
-        self.u_open = torch.zeros(Pl, dtype=torch.float64, device=d)
-        self._token = torch.zeros(1, dtype=torch.float32, device=d)
         self._side = torch.cuda.Stream(device=d)
-        # split every MCMC iteration so that the weight exchange + resampling overlap the integration (step_overlapped)
-        self.overlap = os.environ.get("CDW_SHARDED_OVERLAP", "0") == "1"
+        self._resampled = None
         self.nan_flags = torch.zeros(Pl, dtype=torch.int32, device=d)
         self.wmin_key = torch.zeros(1, dtype=torch.int64, device=d)
         self.scratch_key = torch.zeros(1, dtype=torch.int64, device=d)
         self.uniforms = torch.zeros(P, dtype=torch.float64, device=d)
-        self.cdf = torch.zeros(P, dtype=torch.int64, device=d)
+        self.cdf = torch.zeros(P + 2, dtype=torch.int64, device=d)[:P]
         self.W_copy = torch.zeros(P, dtype=torch.float64, device=d)
         self.ws_bytes = int(self.lib.cdw_weight_workspace_bytes(P))
         self.workspace = torch.zeros((self.ws_bytes + 7) // 8, dtype=torch.int64, device=d)
@@ -143,9 +159,8 @@ class ShardedSMCEngine:
         self.pending_gather = False
 
     # ------------------------------------------------------------------ plumbing
-    def _exchange(self, name, b):
-        """All-gather the IPC handles of buffer (name, b); returns a device array of world-size base pointers."""
-        mine = self._bufs[name][b]
+    def _exchange_buffer(self, mine):
+        """All-gather the IPC handle of `mine`; returns a device array of world-size base pointers."""
         handles = [None] * self.world
         dist.all_gather_object(handles, mine.handle(), group=self.group)
         ptrs = []
@@ -159,12 +174,24 @@ class ShardedSMCEngine:
                 ptrs.append(out.value)
         return torch.tensor(ptrs, dtype=torch.int64, device=self.device)
 
+    def _exchange(self, name, b):
+        return self._exchange_buffer(self._bufs[name][b])
+
     def local(self, name, b=None):
         return self._bufs[name][self.cur if b is None else b].tensor
 
     @property
     def beta(self):
         return 1.0 / self.langevin.kT
+
+    def peer_barrier(self):
+        """Every rank's launches so far (this stream) are complete before any rank continues (cdw_peer_barrier; bounded wait)."""
+        _lib.check(self.lib.cdw_peer_barrier(_lib.ptr(self._peer_flags), C.c_void_p(self._flags.ptr.value), self.rank, self.world,
+                                            _lib.ptr(self._epoch_counter), _lib.ptr(self._barrier_status), _lib.current_stream()), "cdw_peer_barrier")
+
+    def check_barriers(self):
+        if int(self._barrier_status.item()) != 0:
+            raise _lib.CdwError("a peer did not reach a cdw_peer_barrier within its time limit: the results of this run are not valid")
 
     # ------------------------------------------------------------------ the loop
     def initialize(self, positions_local, velocities_local=None):
@@ -176,21 +203,34 @@ class ShardedSMCEngine:
             self.local("vel").zero_()
         else:
             self.local("vel").copy_(velocities_local if torch.is_tensor(velocities_local) else positions_to_rows(velocities_local, self.device))
-        # aux = -u_0(x_0) and the static-term cache of the initial rows, in one n_steps = 0 call (as SMCEngine does)
-        prm = _lib.LangevinParams(0.0, 0.0, float(self.langevin.kT), 1e-6, 0, 0)
-        cache = _lib.static_cache(None, None, self.local("fs"), self.local("us"))
-        _lib.check(self.lib.cdw_smc_propagate_cached(
-            self.system.handle, _lib.ptr(self.local("pos")), _lib.ptr(self.local("vel")), None, None, self.P_loc, None, None, None, None, _lib.ptr(self.lam[0]),
-            C.byref(prm), C.c_uint64(0), C.c_uint64(0), C.c_int64(self.first), None, None, _lib.ptr(self.local("aux")), None, None, None, None, None, None, None,
-            C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_cached")
+        if self.lookahead:
+            # aux = -u_0(x_0), F(x_0; lambda_1) and inc_1 in one n_steps = 0 call (as SMCEngine does)
+            prm = self.langevin.as_struct(0, n_steps=0)
+            lam1 = self.lam[1] if self.T > 1 else None
+            _lib.check(self.lib.cdw_smc_lookahead(
+                self.system.handle, _lib.ptr(self.local("pos")), _lib.ptr(self.local("vel")), None, None, None, _lib.ptr(self.local("fs")), self.P_loc, None,
+                None, _lib.ptr(self.lam[0]), _lib.ptr(lam1), C.byref(prm), C.c_uint64(0), C.c_uint64(0), C.c_int64(self.first),
+                _lib.ptr(self.inc_ahead_loc[0]) if lam1 is not None else None, _lib.ptr(self.local("aux")), None, None, _lib.current_stream()),
+                "cdw_smc_lookahead")
+        else:
+            # aux = -u_0(x_0) and the static-term cache of the initial rows, in one n_steps = 0 call
+            prm = _lib.LangevinParams(0.0, 0.0, float(self.langevin.kT), 1e-6, 0, 0)
+            cache = _lib.static_cache(None, None, self.local("fs"), self.local("us"))
+            _lib.check(self.lib.cdw_smc_propagate_cached(
+                self.system.handle, _lib.ptr(self.local("pos")), _lib.ptr(self.local("vel")), None, None, self.P_loc, None, None, None, None,
+                _lib.ptr(self.lam[0]), C.byref(prm), C.c_uint64(0), C.c_uint64(0), C.c_int64(self.first), None, None, _lib.ptr(self.local("aux")), None, None,
+                None, None, None, None, None, C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_cached")
         self.local("label").copy_(torch.arange(self.first, self.last, dtype=torch.int32, device=self.device))
         self.cum.zero_()
         self.anc_cur = 0
         self.anc.copy_(torch.arange(self.P, dtype=torch.int32, device=self.device))
+        self.wmin_key.fill_(-1)
         self.scratch_key.fill_(-1)
         self.stats.zero_()
         self.iteration = 0
         self.pending_gather = False
+        self._resampled = None
+        torch.cuda.current_stream().synchronize()
         dist.barrier(group=self.group)  # every rank's initial rows are in place before any peer read
 
     @property
@@ -198,80 +238,93 @@ class ShardedSMCEngine:
         """Ancestors still to be applied to the current rows (global ids)."""
         return self.anc_bufs[self.anc_cur]
 
-    def _launch(self, t, phase_flag, c, n, anc, with_outputs, with_key):
-        flags = _lib.CDW_FLAG_ULA if self.proposal == "ula" else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
-        prm = self.langevin.as_struct(flags | phase_flag)
-        cache = _lib.static_cache(None, None, self.local("fs", n), self.local("us", n), self.peer["fs"][c], self.peer["us"][c], self.f_open, self.u_open)
-        _lib.check(self.lib.cdw_smc_propagate_sharded_cached(
-            self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]),
-            self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), self.P_loc, _lib.ptr(anc[self.first:self.last]),
-            _lib.ptr(self.cum[self.first:self.last]), _lib.ptr(self.lam[t]), C.byref(prm), C.c_uint64(self.seed),
-            C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc) if with_key else None,
-            _lib.ptr(self.W_loc) if with_key else None, _lib.ptr(self.local("aux", n)) if with_outputs else None,
-            _lib.ptr(self.local("label", n)) if with_outputs else None, _lib.ptr(self.nan_flags) if with_outputs else None,
-            None, C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_sharded_cached")
+    # ---- look-ahead loop
+    def step_lookahead(self, t):
+        self.iteration = t
+        main = torch.cuda.current_stream()
+        prev_anc = self.anc_bufs[(t - 1) % 2]
+        launched = torch.cuda.Event()
+        launched.record(main)
+        self._side.wait_event(launched)
+        with torch.cuda.stream(self._side):
+            # C1: one all-gather of the 8-byte incremental works this rank's last launch left behind
+            dist.all_gather_into_tensor(self.inc_ahead, self.inc_ahead_loc[(t - 1) % 2], group=self.group)
+            # every rank forms the SAME weight vector and reduces it with integer sums: statistics, decision and ancestors are
+            # bit-identical on all ranks and to a single-GPU run
+            _lib.check(self.lib.cdw_smc_weigh_resample(
+                self.kind, _lib.ptr(self.inc_ahead), _lib.ptr(prev_anc if t > 1 else None), self.P, self.threshold, _lib.ptr(self.wmin_key),
+                C.c_uint64(self.resample_seed), C.c_uint64(t), _lib.ptr(self.stats[t]), _lib.ptr(self.cum), _lib.ptr(self.inc), _lib.ptr(self.W),
+                _lib.ptr(self.anc_bufs[t % 2]), _lib.ptr(self.cdf), _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()),
+                "cdw_smc_weigh_resample")
+            resampled = torch.cuda.Event()
+            resampled.record(self._side)
+        if self._resampled is not None:
+            main.wait_event(self._resampled)
+        # the rows this launch gathers were written by the peers' launches of iteration t - 1, and the buffer it writes is the one the
+        # peers' launches of iteration t - 1 read: both need every rank to be through iteration t - 1
+        self.peer_barrier()
+        c, n = self.cur, 1 - self.cur
+        prm = self.langevin.as_struct(_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
+        lam_next = self.lam[t + 1] if t + 1 < self.T else None
+        _lib.check(self.lib.cdw_smc_lookahead_sharded(
+            self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["fs"][c]), _lib.ptr(self.peer["label"][c]),
+            self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), _lib.ptr(self.local("fs", n)), self.P_loc,
+            _lib.ptr(prev_anc[self.first:self.last]), _lib.ptr(self.lam[t]), _lib.ptr(lam_next), C.byref(prm), C.c_uint64(self.seed),
+            C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_ahead_loc[t % 2]) if lam_next is not None else None,
+            _lib.ptr(self.local("aux", n)), _lib.ptr(self.local("label", n)), _lib.ptr(self.nan_flags), _lib.current_stream()), "cdw_smc_lookahead_sharded")
+        self._resampled = resampled
+        self.cur = n
+        self.anc_cur = t % 2
+        self.pending_gather = True
 
+    def join(self):
+        if self._resampled is not None:
+            torch.cuda.current_stream().wait_event(self._resampled)
+            self._resampled = None
+
+    # ---- sequential loop (Euler-Maruyama proposal)
     def propagate(self, t):
-        """The whole propagate call of iteration t (gather over peer memory, weights, integration) as one launch."""
+        """The whole propagate call of iteration t (gather over peer memory, weights, move) as one launch."""
         self.iteration = t
         c, n = self.cur, 1 - self.cur
-        self._launch(t, 0, c, n, self.anc, True, True)
+        flags = _lib.CDW_FLAG_ULA if self.proposal == "ula" else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
+        prm = self.langevin.as_struct(flags)
+        cache = _lib.static_cache(None, None, self.local("fs", n), self.local("us", n), self.peer["fs"][c], self.peer["us"][c])
+        _lib.check(self.lib.cdw_smc_propagate_sharded_cached(
+            self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]),
+            self.world, self.P_loc, _lib.ptr(self.local("pos", n)), _lib.ptr(self.local("vel", n)), self.P_loc, _lib.ptr(self.anc[self.first:self.last]),
+            _lib.ptr(self.cum[self.first:self.last]), _lib.ptr(self.lam[t]), C.byref(prm), C.c_uint64(self.seed),
+            C.c_uint64(t * max(self.langevin.n_steps, 1)), C.c_int64(self.first), _lib.ptr(self.inc_loc), _lib.ptr(self.W_loc), _lib.ptr(self.local("aux", n)),
+            _lib.ptr(self.local("label", n)), _lib.ptr(self.nan_flags), None, C.byref(cache), _lib.current_stream()), "cdw_smc_propagate_sharded_cached")
         self.cur = n
 
-    def _exchange_and_resample(self, t, anc_out):
-        # C1: one all-gather of the 8-byte weights
+    def finish_iteration(self, t):
+        """Weight exchange + global resampling after a propagate call; the all-gather is also the ordering point for the
+        peer reads of the next iteration."""
+        anc_out = self.anc_bufs[1 - self.anc_cur]
         dist.all_gather_into_tensor(self.W, self.W_loc, group=self.group)
-        # every rank reduces the SAME vector in the SAME order: global min, log-sum-exp, nESS, decision
-        # (scratch_key is armed once in initialize(); cdw_smc_resample re-arms it after every use)
+        # every rank reduces the SAME vector: global min, log-sum-exp, nESS, decision (scratch_key is armed once in initialize();
+        # the statistics kernel re-arms it after every use)
         _lib.check(self.lib.cdw_weight_update(_lib.ptr(self.W), None, None, None, self.P, None, _lib.ptr(self.W_copy), _lib.ptr(self.scratch_key),
                                              _lib.current_stream()), "cdw_weight_update")
         _lib.check(self.lib.cdw_smc_resample(self.kind, _lib.ptr(self.W), self.P, self.threshold, _lib.ptr(self.scratch_key), C.c_uint64(self.resample_seed),
                                             C.c_uint64(t), _lib.ptr(self.stats[t]), _lib.ptr(self.cum), _lib.ptr(self.cum), _lib.ptr(anc_out), _lib.ptr(self.cdf),
                                             _lib.ptr(self.uniforms), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream()), "cdw_smc_resample")
-
-    def finish_iteration(self, t):
-        """Weight exchange + global resampling after an unsplit propagate; the all-gather is also the ordering point for the
-        peer reads of the next iteration."""
-        self._exchange_and_resample(t, self.anc_bufs[1 - self.anc_cur])
-        self.anc_cur = 1 - self.anc_cur
-        self.pending_gather = True
-
-    def step_overlapped(self, t):
-        """Iteration t as two launches (CDW_FLAG_PHASE_OPEN / _REST): the weights are final after the opening evaluation, so the
-        all-gather of W and the global resampling run on a side stream WHILE this rank integrates; a one-element all-reduce
-        after the integration is the cross-rank ordering point for the next iteration's peer reads."""
-        self.iteration = t
-        c, n = self.cur, 1 - self.cur
-        main = torch.cuda.current_stream()
-        anc_in, anc_out = self.anc_bufs[self.anc_cur], self.anc_bufs[1 - self.anc_cur]
-        self._launch(t, _lib.CDW_FLAG_PHASE_OPEN, c, n, anc_in, False, True)
-        opened = torch.cuda.Event()
-        opened.record(main)
-        self._side.wait_event(opened)
-        with torch.cuda.stream(self._side):
-            self._exchange_and_resample(t, anc_out)
-        self._launch(t, _lib.CDW_FLAG_PHASE_REST, c, n, anc_in, True, False)
-        integrated = torch.cuda.Event()
-        integrated.record(main)
-        self._side.wait_event(integrated)
-        with torch.cuda.stream(self._side):
-            dist.all_reduce(self._token, group=self.group)   # every rank's rows of iteration t are in place
-            joined = torch.cuda.Event()
-            joined.record(self._side)
-        main.wait_event(joined)
-        self.cur = n
         self.anc_cur = 1 - self.anc_cur
         self.pending_gather = True
 
     def step(self, t):
-        if self.overlap and self.proposal != "ula" and self.langevin.n_steps > 0:
-            return self.step_overlapped(t)
+        if self.lookahead:
+            return self.step_lookahead(t)
         self.propagate(t)
         self.finish_iteration(t)
 
     def materialize(self):
         """Apply the last resampling to this rank's block (peer gather over NVLink)."""
+        self.join()
         if self.pending_gather:
+            if self.lookahead:
+                self.peer_barrier()   # every rank's last launch has written its rows
             c, n = self.cur, 1 - self.cur
             _lib.check(self.lib.cdw_gather_particles_peer(
                 _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]), self.world,
@@ -281,6 +334,7 @@ class ShardedSMCEngine:
             dist.barrier(group=self.group)  # nobody reuses the source buffers before every rank has pulled its rows
             self.cur = n
             self.pending_gather = False
+        self.check_barriers()
 
     def run(self):
         for t in range(1, self.T):
@@ -291,8 +345,9 @@ class ShardedSMCEngine:
     graph = None
 
     def capture(self, positions_local, velocities_local=None):
-        """Capture iterations 1..T-1 (fused propagate with peer-mapped gather, NCCL all-gather of W, global resample)
-        into one CUDA graph per rank; every rank must call this collectively.  `anneal` then replays it."""
+        """Capture iterations 1..T-1 (per iteration: peer barrier + the fused launch over peer memory on the main branch, NCCL
+        all-gather + global resample on a side branch) into one CUDA graph per rank; every rank must call this collectively.
+        `anneal` then replays it."""
         self.graph = None
         self.initialize(positions_local, velocities_local)
         side = torch.cuda.Stream()
@@ -300,6 +355,7 @@ class ShardedSMCEngine:
         with torch.cuda.stream(side):  # warm-up outside capture (lazy loading, NCCL channel setup, cudaFuncSetAttribute)
             for t in range(1, self.T):
                 self.step(t)
+            self.join()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
@@ -309,6 +365,7 @@ class ShardedSMCEngine:
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             for t in range(1, self.T):
                 self.step(t)
+            self.join()
         self._graph_final = (self.cur, self.pending_gather, self.iteration, self.anc_cur)
         self.graph = g
         torch.cuda.synchronize()
@@ -329,13 +386,12 @@ class ShardedSMCEngine:
         return self.cum.cpu().numpy()
 
     def free_energy(self):
-        c = self.cum.cpu().numpy()
-        m = (-c).max()
-        return float(-(m + np.log(np.exp(-c - m).sum())) + np.log(c.size))
+        c = self.cum
+        return float(-torch.logsumexp(-c, 0) + np.log(c.numel()))
 
     def resampled_iterations(self):
-        s = self.stats.cpu().numpy()
-        return [t for t in range(1, self.T) if s[t, _lib.STAT_RESAMPLE] != 0.0]
+        s = self.stats[:, _lib.STAT_RESAMPLE].cpu().numpy()
+        return [t for t in range(1, self.T) if s[t] != 0.0]
 
     def close(self):
         """Unmap the peers' buffers, then (after every rank has done so) free this rank's own."""
@@ -348,3 +404,4 @@ class ShardedSMCEngine:
         for bufs in self._bufs.values():
             for b in bufs:
                 b.free()
+        self._flags.free()

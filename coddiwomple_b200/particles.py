@@ -73,13 +73,28 @@ for _name, _slot in (("cumulative_work", "_w"), ("incremental_works", "_dw"), ("
 del _name, _slot
 
 
+class _NoHistory(list):
+    """Placeholder for a per-iteration history that was not spilled from the device: reading it raises instead of handing back
+    a silently truncated list (the reference's lists grow by one entry per iteration, particles.py:38-47)."""
+
+    def __init__(self, what):
+        super().__init__()
+        self._what = what
+
+    def _fail(self, *a, **k):
+        raise RuntimeError(f"Particle.{self._what} was not recorded for this run: pass record_histories=True to SMC() / mcmc_smc_resampler() "
+                           "(one (work, label) pair per particle and iteration is then kept on the device and copied out once)")
+
+    __getitem__ = __iter__ = __len__ = __repr__ = __eq__ = _fail
+
+
 class ParticleList:
     """Sequence view of a device-resident ParticleEnsemble.  Host copies are fetched once, on first access."""
 
     def __init__(self, ensemble, state_factory=None, histories=None):
         self.ensemble = ensemble
         self._state_factory = state_factory
-        self._histories = histories  # optional dict(cum=[T][P], labels=[T][P]) host arrays
+        self._histories = histories  # optional dict(cum=[T-1][P], labels=[T-1][P]) host arrays, or a callable returning it (fetched lazily)
         self._host = None
 
     def __len__(self):
@@ -108,12 +123,15 @@ class ParticleList:
         p = Particle(index=int(self.ensemble.gid0 + i), iteration=self.ensemble.iteration)
         p._w = float(h["cum"][i])
         p._aux = float(h["aux"][i])
+        if callable(self._histories):
+            self._histories = self._histories()
         if self._histories is not None:
             cums = self._histories["cum"][:, i]
             p._dw = list(np.diff(np.concatenate([[0.0], cums])))
             p._line = [int(self.ensemble.gid0 + i)] + [int(l) for l in self._histories["labels"][:, i]]
         else:
-            p._line = [int(self.ensemble.gid0 + i), int(h["label"][i])]
+            p._dw = _NoHistory("incremental_works")
+            p._line = _NoHistory("ancestry")
         p._pw = [0.] * (self.ensemble.iteration + 1)
         if self._state_factory is not None:
             p._x = self._state_factory(h["pos"][i], h["vel"][i])

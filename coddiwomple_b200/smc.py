@@ -21,7 +21,8 @@ def _resampler_kind(resampler):
 
 
 def SMC(target_factory, proposal_factory, num_initial_particles, reporter, resampler, initial_positions=None, observable=nESS,
-        threshold=vanilla_floor_threshold, floor_threshold=0.5, seed=None, state_factory=None, record_history=False, **kwargs):
+        threshold=vanilla_floor_threshold, floor_threshold=0.5, seed=None, state_factory=None, record_history=False, record_histories=None,
+        **kwargs):
     """
     arguments (as the reference)
         target_factory : TargetFactory        — pdf_state + parameter_sequence of the targets
@@ -32,6 +33,10 @@ def SMC(target_factory, proposal_factory, num_initial_particles, reporter, resam
     extra keyword arguments
         initial_positions : (num_initial_particles, A, 3) array in nm — samples of the first target
         observable / threshold : the stock nESS / vanilla_floor_threshold pair, or None to always resample
+        record_histories : keep every particle's per-iteration cumulative work and root label on the device so that
+            `particle.incremental_works` / `particle.ancestry` have one entry per iteration like the reference's
+            (particles.py:38-47).  None (default): on when particles x iterations <= 5e7 (12 bytes each), else off — reading those
+            two properties then raises instead of returning truncated lists.
 
     returns
         particles : ParticleList (sequence of Particle views of the device-resident ensemble)
@@ -45,12 +50,14 @@ def SMC(target_factory, proposal_factory, num_initial_particles, reporter, resam
         raise NotImplementedError("the device loop supports the stock nESS / vanilla_floor_threshold pair (or None)")
     if seed is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1))
+    if record_histories is None:
+        record_histories = num_initial_particles * len(target_factory.parameter_sequence) <= 50_000_000
     engine = SMCEngine(pdf_state.device_system, num_initial_particles, target_factory.parameter_sequence, langevin=propagator.integrator,
                        resampler=_resampler_kind(resampler), floor_threshold=floor_threshold, always_resample=always, seed=seed,
-                       resample_seed=seed + 1, record_history=record_history)
+                       resample_seed=seed + 1, record_history=record_history, record_lineage=record_histories)
     engine.anneal(initial_positions)
     resampler._resampling_logger.extend(engine.resampled_iterations())
-    particles = ParticleList(engine.ensemble, state_factory=state_factory)
+    particles = ParticleList(engine.ensemble, state_factory=state_factory, histories=engine.lineage if record_histories else None)
     particles.engine = engine
     if reporter is not None:
         reporter.record(particles, save_to_disk=True)

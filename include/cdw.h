@@ -120,14 +120,6 @@ typedef struct cdw_langevin_params {
  *   inc = u_t(x_t) + aux + proposal_work   (distribution_factories.py:98-131; troubleshooting/csmc.py:174-191).
  * Velocities are not used (vel_in / vel_out may be NULL); gamma is ignored. */
 #define CDW_FLAG_ULA 4u
-/* Split launches of one MCMC propagate call (used by the sharded loop to overlap the weight exchange and the resampling
- * with the integration): PHASE_OPEN gathers the rows, runs the opening evaluation only and writes inc_out / w_out (and the
- * running min) plus the hand-over buffers cdw_static_cache.force_open / u_open; PHASE_REST gathers the rows again, takes
- * the opening forces and energy from those buffers and does everything else (integration, closing evaluation, outputs).
- * OPEN followed by REST equals one unsplit call bit for bit.  Both need a cdw_static_cache with force_open / u_open. */
-#define CDW_FLAG_PHASE_OPEN 8u
-#define CDW_FLAG_PHASE_REST 16u
-
 #define CDW_RESAMPLE_MULTINOMIAL 0
 #define CDW_RESAMPLE_SYSTEMATIC 1
 
@@ -208,8 +200,6 @@ typedef struct cdw_static_cache {
     double* energy_out;
     const float* const* peer_force_in;   /* cdw_smc_propagate_sharded_cached only */
     const double* const* peer_energy_in;
-    float* force_open;                   /* CDW_FLAG_PHASE_OPEN (out) / CDW_FLAG_PHASE_REST (in): [P][A][4] and [P], local slots */
-    double* u_open;
 } cdw_static_cache;
 
 /* cdw_smc_propagate with a static-term cache (cache == NULL: identical to cdw_smc_propagate). */
@@ -220,22 +210,35 @@ CDW_API int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_in,
                              double* u_first_out, double* u_last_out, double* shadow_out, double* proposal_out,
                              int32_t* nan_flags, uint64_t* wmin_key, const cdw_static_cache* cache, cdw_stream stream);
 
-/* One whole SMC iteration of the reference loop (openmm/coddiwomple.py:314-328): cdw_smc_propagate_cached followed by
- * cdw_smc_resample on its weights, with `cum` updated in place and the new ancestors in anc_out (anc_in, the ancestors
- * still to be applied to the input rows, may be the same buffer or NULL).  For MCMC moves the incremental work is final
- * right after the opening evaluation; when the whole batch fits the GPU at once the library therefore adds ONE thread
- * block to the propagate launch that waits for the weights and resamples while the other blocks are still integrating:
- * the iteration is a single kernel launch and the resampling costs no time.  Otherwise (Euler-Maruyama proposal, batches
- * of several waves) the two kernels are launched back to back.  Results are identical either way.  `workspace` as for
- * cdw_weight_stats (zero-initialised once); w_out, wmin_key (armed with ~0 before the first call), stats, cdf, uniforms
- * are required. */
-CDW_API int cdw_smc_iteration(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
-                              int64_t n_particles, const int32_t* anc_in, const double* aux_in, double* cum, const int32_t* label_in,
-                              const double* lambda, const cdw_langevin_params* params, uint64_t seed, uint64_t step0, int64_t gid0,
-                              double* inc_out, double* w_out, double* aux_out, int32_t* label_out, int32_t* nan_flags, uint64_t* wmin_key,
-                              const cdw_static_cache* cache, int kind, double floor_threshold, uint64_t resample_seed, uint64_t stream_id,
-                              double* stats, int32_t* anc_out, uint64_t* cdf, double* uniforms, void* workspace, size_t workspace_bytes,
-                              cdw_stream stream);
+/* The look-ahead iteration: the hot loop of the reference (openmm/coddiwomple.py:312-331) for an MCMC move (OMMLI "V R O R V",
+ * openmm/integrators.py:297-350, driven by OMMBIP.apply, openmm/propagators.py:89-219), cut at a different place.
+ * The incremental work of iteration t + 1, u_{t+1}(x_t) + aux with aux = -u_t(x_t) (distribution_factories.py:124-129;
+ * openmm/coddiwomple.py:315, 326-327), only needs the coordinates iteration t ENDS with.  This call therefore does
+ *     [gather rows by anc]  (V R O R E_t V)^n_steps  E_{t+1}
+ * on forces that arrive with the particle: force_in holds F(x_{t-1}; lambda_t) of the input rows, force_out receives
+ * F(x_t; lambda_{t+1}), inc_next_out[p] = u_{t+1}(x_t) - u_t(x_t), aux_out[p] = -u_t(x_t).  The resampling of iteration t + 1
+ * (cdw_smc_weigh_resample) then has all its inputs before launch t + 1 starts and runs BESIDE it on another stream: nothing
+ * but propagate launches is left on the critical path, for any batch size and any number of GPUs.
+ *   n_steps = 0 equips the initial sample (ProposalFactory.equip_initial_sample, distribution_factories.py:180-220):
+ *     aux_out = -u_0(x_0), force_out = F(x_0; lambda_1), inc_next_out = u_1(x_0) - u_0(x_0); force_in is not read.
+ *   lambda_next = NULL / inc_next_out = NULL on the last iteration (force_out is then scratch).
+ * Energies and forces of the terms that no global parameter enters are evaluated once per call and shared by E_t and E_{t+1}.
+ * A move that ends in a non-finite energy is reverted (openmm/propagators.py:166-186): outputs are those of the input state.
+ * flags: CDW_FLAG_RANDOMIZE_VELOCITIES only.  Rows are float4 [P][A]; in/out buffers must be distinct when anc != NULL. */
+CDW_API int cdw_smc_lookahead(const cdw_system* sys, const float* pos_in, const float* vel_in, const float* force_in, float* pos_out,
+                              float* vel_out, float* force_out, int64_t n_particles, const int32_t* anc, const int32_t* label_in,
+                              const double* lambda, const double* lambda_next, const cdw_langevin_params* params, uint64_t seed,
+                              uint64_t step0, int64_t gid0, double* inc_next_out, double* aux_out, int32_t* label_out,
+                              int32_t* nan_flags, cdw_stream stream);
+
+/* Sharded form for one rank of a multi-GPU run (see cdw_smc_propagate_sharded): anc holds GLOBAL ancestors, the rows, forces
+ * and labels of an ancestor are read from the owning rank through peer-mapped pointers (NVLink). */
+CDW_API int cdw_smc_lookahead_sharded(const cdw_system* sys, const float* const* peer_pos, const float* const* peer_vel,
+                                      const float* const* peer_force, const int32_t* const* peer_label, int32_t n_ranks,
+                                      int64_t n_per_rank, float* pos_out, float* vel_out, float* force_out, int64_t n_particles,
+                                      const int32_t* anc, const double* lambda, const double* lambda_next,
+                                      const cdw_langevin_params* params, uint64_t seed, uint64_t step0, int64_t gid0,
+                                      double* inc_next_out, double* aux_out, int32_t* label_out, int32_t* nan_flags, cdw_stream stream);
 
 /* Sharded form of cdw_smc_propagate for one rank of a multi-GPU run (particles are partitioned in contiguous blocks
  * of n_per_rank by global id; this rank propagates its n local slots, whose global ids start at gid0).
@@ -265,8 +268,10 @@ CDW_API int cdw_baoab(const cdw_system* sys, float* pos, float* vel, int64_t n_p
 /* K2. replaces: TargetFactory.compute_incremental_work's sum (distribution_factories.py:124-129) + nESS
  * (utils.py:41-64) + the normaliser of Resampler.resample (resamplers.py:102-107).
  * cdw_weight_update: inc[p] = u_new[p] + aux[p] (+ proposal[p] if not NULL); w_out[p] = cum[p] + inc[p]; min W -> wmin_key.
- * cdw_weight_stats : second pass over W: sum e, sum e^2, integer total; the last block finalises stats[] including
- *                    the resampling decision (threshold < 0: always resample, as observable=None does). */
+ * cdw_weight_stats : second pass over W: ONE deterministic exponential per particle, kept in the workspace as the integer
+ *                    rint(e 2^62); sum e and sum e^2 are exact 128-bit integer sums (any grid, any order, any number of GPUs
+ *                    give the same bits); the last block finalises stats[] including the resampling decision
+ *                    (threshold < 0: always resample, as observable=None does).  w and workspace 16-byte aligned. */
 CDW_API int cdw_weight_update(const double* u_new, const double* aux, const double* proposal, const double* cum, int64_t n,
                       double* inc_out, double* w_out, uint64_t* wmin_key, cdw_stream stream);
 CDW_API size_t cdw_weight_workspace_bytes(int64_t n);
@@ -274,23 +279,32 @@ CDW_API int cdw_weight_stats(const double* w, int64_t n, double floor_threshold,
                      void* workspace, size_t workspace_bytes, cdw_stream stream);
 
 /* K3a. replaces: MultinomialResampler._resample (resamplers.py:254-272); systematic is new.
- * Uses the exactly-associative integer cdf; cdf_out[n] uint64 is caller-provided scratch/output.
- * uniforms: n doubles in [0,1) (multinomial) or 1 double (systematic).  If stats[CDW_STAT_RESAMPLE] == 0 the kernels
- * write the identity ancestors and cum_out = W (the null update, resamplers.py:136-156); otherwise
- * cum_out[p] = cum_in[p] + (mean - cum_in[p]) (resamplers.py:196-197). */
+ * Must follow cdw_weight_stats on the same workspace (it reads the quantised weights from there).  The cdf is the uint64
+ * prefix sum of those integers (cdf_out[n], caller-provided, 16-byte aligned).  Systematic ancestors (targets
+ * floor(((i + u0) (1/n)) total), sorted) are emitted by the scan itself; multinomial ancestors are looked up through a guide
+ * table the scan emits the same way.  uniforms: n doubles in [0,1) (multinomial) or 1 double (systematic).
+ * If stats[CDW_STAT_RESAMPLE] == 0 the kernels write the identity ancestors and cum_out = W (the null update,
+ * resamplers.py:136-156); otherwise cum_out[p] = cum_in[p] + (mean - cum_in[p]) (resamplers.py:196-197). */
 CDW_API int cdw_resample_indices(int kind, const double* w, const double* uniforms, int64_t n, const double* stats,
                          const double* cum_in, double* cum_out, int32_t* anc_out, uint64_t* cdf_out, void* workspace,
                          size_t workspace_bytes, cdw_stream stream);
 
-/* K2 (second half) + K3a in one call: everything between two propagate launches of the SMC loop
+/* K2 (second half) + K3a in one call: everything Resampler.resample does between two propagate calls of the SMC loop
  * (openmm/coddiwomple.py:318).  Uniforms come from Philox (seed, stream_id): n draws for multinomial, one for systematic
- * (written to `uniforms` for inspection).  *wmin_key (the running min left by cdw_smc_propagate) is consumed and re-armed
- * to ~0.  For n <= 24576 this is ONE launch of 8 cooperating thread blocks (the routine cdw_smc_iteration runs inside the
- * propagate launch); larger batches run statistics + three scan kernels + a search kernel that draws the uniforms itself
- * (5 launches).  Same ancestors either way.  `workspace` must be zero when first used; the kernels leave it at rest. */
+ * (written to `uniforms` for inspection).  *wmin_key (the running min left by the weight pass) is consumed and re-armed
+ * to ~0.  Three launches (systematic) or four (multinomial), no host decision in between.  `workspace` must be zero when
+ * first used; the kernels leave it at rest. */
 CDW_API int cdw_smc_resample(int kind, const double* w, int64_t n, double floor_threshold, uint64_t* wmin_key, uint64_t seed,
                              uint64_t stream_id, double* stats, const double* cum_in, double* cum_out, int32_t* anc_out,
                              uint64_t* cdf_out, double* uniforms, void* workspace, size_t workspace_bytes, cdw_stream stream);
+
+/* The resampling of the look-ahead loop: W[i] = cum[i] + inc_src[anc_prev[i]] (the incremental work cdw_smc_lookahead left at
+ * the slot the state lived in before the previous resampling moved it to slot i; anc_prev NULL: identity), then
+ * cdw_smc_resample on W with `cum` updated in place.  inc_out (may be NULL) receives the per-slot incremental works. */
+CDW_API int cdw_smc_weigh_resample(int kind, const double* inc_src, const int32_t* anc_prev, int64_t n, double floor_threshold,
+                                   uint64_t* wmin_key, uint64_t seed, uint64_t stream_id, double* stats, double* cum, double* inc_out,
+                                   double* w_out, int32_t* anc_out, uint64_t* cdf_out, double* uniforms, void* workspace,
+                                   size_t workspace_bytes, cdw_stream stream);
 
 /* K3b. replaces: the per-particle deepcopy loop of Resampler.resample (resamplers.py:123-129,193). */
 CDW_API int cdw_gather_particles(const float* pos_in, const float* vel_in, const int32_t* anc, float* pos_out, float* vel_out,
@@ -303,6 +317,21 @@ CDW_API int cdw_gather_particles_peer(const float* const* peer_pos, const float*
                               const int32_t* const* peer_label, int32_t n_ranks, int64_t n_per_rank, const int32_t* anc,
                               float* pos_out, float* vel_out, double* aux_out, int32_t* label_out, int64_t n_local,
                               int32_t n_atoms, cdw_stream stream);
+
+/* History spill. replaces: the per-iteration appends to Particle._incremental_works / Particle._ancestry
+ * (particles.py:38-47; resamplers.py:115,129,196-200): cum_row[i] = cum[i], label_row[i] = label[anc[i]] (anc NULL: identity).
+ * `label` holds the root labels of the states BEFORE this iteration's ancestors are applied. */
+CDW_API int cdw_record_lineage(const double* cum, const int32_t* label, const int32_t* anc, double* cum_row, int32_t* label_row,
+                               int64_t n, cdw_stream stream);
+
+/* Cross-GPU ordering point of the sharded loop (one tiny launch): every rank tells every peer that its launches up to here
+ * have completed (a store into the peer's flag array through a peer-mapped pointer) and waits until all peers have said so.
+ * peer_flags: device array of `world` base pointers to the ranks' flag arrays (uint64[world] each, zero-initialised);
+ * *epoch_counter (device, zero-initialised, private to the rank) is incremented by the launch itself, so the call can be
+ * captured in a CUDA graph and replayed; every rank must call it the same number of times.  *status is set to 1 if a peer did
+ * not show up within ~2 s (the wait is bounded). */
+CDW_API int cdw_peer_barrier(uint64_t* const* peer_flags, uint64_t* flags_local, int32_t rank, int32_t world, uint64_t* epoch_counter,
+                             int32_t* status, cdw_stream stream);
 
 /* utilities */
 CDW_API int cdw_fill_u64(uint64_t* ptr, uint64_t value, int64_t n, cdw_stream stream);

@@ -11,7 +11,7 @@ Two restatements of `MultinomialResampler._resample` (coddiwomple/resamplers.py:
   error of numpy's sequential fp64 cumsum (tests count those; none occur in the committed cases).
 
 Systematic resampling does not exist in the reference; it is defined here by its textbook
-form u_i = (u0 + i)/N with the same search.  Parity unpinned for it.
+form u_i = (u0 + i)/N (evaluated as (u0 + i) * (1/N)) with the same search.  Parity unpinned for it.
 """
 import numpy as np
 from scipy.special import softmax
@@ -50,27 +50,33 @@ def multinomial_float(works, uniforms):
 
 
 def systematic_uniforms(u0, n):
-    """u_i = (u0 + i)/n evaluated with one correctly-rounded add and one divide (deterministic on CPU and GPU)."""
-    return (np.arange(n, dtype=np.float64) + float(u0)) / float(n)
+    """u_i = (u0 + i) * (1/n) evaluated with one correctly-rounded add and one multiply by the rounded reciprocal
+    (deterministic on CPU and GPU, and a multiply instead of a divide per slot on the GPU)."""
+    return (np.arange(n, dtype=np.float64) + float(u0)) * (1.0 / float(n))
+
+
+def quantised_exponentials(works):
+    """q_i = rint(det_exp(min W - W_i) * 2^62) as uint64 (<= 2^62): the ONE exponential per particle the kernels evaluate;
+    everything downstream (statistics, cdf, search) is integer arithmetic on q.  Returns (q, e, wmin)."""
+    w = np.asarray(works, dtype=np.float64)
+    wmin = w.min()
+    e = det_exp(wmin - w)
+    return np.rint(e * 2.0 ** 62).astype(np.uint64), e, float(wmin)
 
 
 def fixed_point_weights(works):
     """Quantise w_i = exp(-(W_i - min W)) to integers whose total T satisfies 2^59 <= T < 2^61.
 
-    pass 1: q1_i = rint(e_i * 2^S1), S1 = 61 - ceil(log2 N)  -> T1 = sum q1 (exact integer, <= 2^61)
-    pass 2: shift s = 60 - bitlength(T1) (>= 0 is enforced), q_i = rint(e_i * 2^(S1+s))
-    Returns (q uint64[N], S1 + s).
+    q62_i = rint(e_i 2^62); S1 = sum q62 (exact, Python ints); k = max(0, bitlength(S1) - 60);
+    q_i = (q62_i >> k) rounded half up.  Returns (q uint64[N], k).
     """
-    w = np.asarray(works, dtype=np.float64)
-    n = w.shape[0]
-    e = det_exp(-(w - w.min()))
-    b = int(np.ceil(np.log2(n))) if n > 1 else 0
-    s1 = 61 - b
-    q1 = np.rint(e * 2.0 ** s1).astype(np.uint64)
-    t1 = int(q1.sum(dtype=np.uint64))
-    s = max(0, 60 - t1.bit_length())
-    q = np.rint(e * 2.0 ** (s1 + s)).astype(np.uint64)
-    return q, s1 + s
+    q62, _, _ = quantised_exponentials(works)
+    s1 = int(q62.sum(dtype=object)) if q62.size < 4096 else sum(int(x) for x in np.add.reduceat(q62.astype(object), np.arange(0, q62.size, 1024)))
+    k = max(0, s1.bit_length() - 60)
+    if k == 0:
+        return q62, 0
+    q = ((q62 >> np.uint64(k - 1)) + np.uint64(1)) >> np.uint64(1)
+    return q, k
 
 
 def _mul_shift53(u53, total):
@@ -107,29 +113,24 @@ def ancestors(works, uniforms, kind="multinomial", u0=None):
     return ancestors_fixed(works, uniforms)
 
 
+def u128_to_double(v):
+    """(hi 2^64 + lo) with two correctly rounded conversions and one add — what the kernel does with its two 64-bit words."""
+    hi, lo = v >> 64, v & (2 ** 64 - 1)
+    return float(hi) * 18446744073709551616.0 + float(lo)
+
+
 def canonical_statistics(works):
-    """(sum e, sum e^2) of e_i = det_exp(min W - W_i) in the order the one-launch resampling team uses
-    (coddiwomple_b200/csrc/cdw_resample.cuh): 1024 virtual threads, element i belongs to virtual thread i mod 1024 and is
-    added in index order; the 1024 partials are combined by the fixed binary tree p[k] += p[k + s], s = 512 .. 1.
-    With det_exp bit-identical on CPU and GPU this makes sum e bit-reproducible (the device accumulates e^2 with a fused
-    multiply-add and uses its own log, so sum e^2, nESS and the normaliser agree to ~1e-15, not bitwise).
+    """(sum e, sum e^2, nESS, normaliser) as the kernels define them (coddiwomple_b200/csrc/cdw_weights.cu:weight_stats_kernel):
+    EXACT integer sums S1 = sum rint(e_i 2^62), S2 = sum rint((e_i e_i) 2^62) (order-free, hence identical for any grid, any
+    sharding), converted once: sum_e = double(S1) 2^-62.  With det_exp bit-identical on CPU and GPU, sum e, sum e^2 and nESS
+    are bit-reproducible; the normaliser uses the device's log (~1 ulp).
     Returns (wmin, sum_e, sum_e2, nESS, mean) with mean = wmin - log(sum_e) + log(N) (resamplers.py:107, utils.py:41-64)."""
-    w = np.asarray(works, dtype=np.float64)
-    n = w.size
-    wmin = w.min()
-    e = det_exp(wmin - w)
-    V = 1024
-    pe, pe2 = np.zeros(V), np.zeros(V)
-    for start in range(0, n, V):          # row r of the (n / 1024, 1024) layout is added to the partials in index order
-        chunk = e[start:start + V]
-        pe[:chunk.size] += chunk
-        pe2[:chunk.size] += chunk * chunk
-    s = V // 2
-    while s > 0:
-        pe[:s] += pe[s:2 * s]
-        pe2[:s] += pe2[s:2 * s]
-        s //= 2
-    sum_e, sum_e2 = float(pe[0]), float(pe2[0])
+    q62, e, wmin = quantised_exponentials(works)
+    n = q62.size
+    q2 = np.rint((e * e) * 2.0 ** 62).astype(np.uint64)
+    s1 = sum(int(x) for x in q62)
+    s2 = sum(int(x) for x in q2)
+    sum_e, sum_e2 = u128_to_double(s1) * 2.0 ** -62, u128_to_double(s2) * 2.0 ** -62
     ness = (sum_e * sum_e) / (float(n) * sum_e2)
     mean = wmin - np.log(sum_e) + np.log(float(n))
     return float(wmin), sum_e, sum_e2, float(ness), float(mean)

@@ -99,8 +99,28 @@ class HostSystem:
         o["v"] = o["vel"][..., :3].astype(np.float64)
         return o
 
-    def smc_propagate_cached(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, cache=None,
-                             handover=None):
+    def smc_lookahead(self, x, v, f, lam, lam_next, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, labels=None):
+        """cdw_smc_lookahead on the host.  x, v: (P, A, 3); f: (P, A, 4) float32 force rows F(x; lam) (None with n_steps = 0);
+        lam_next None on the last iteration.  Returns dict(x, v, pos, vel, force, inc_next, aux, label, nan)."""
+        pos = self.rows(x)
+        vel = self.rows(v) if v is not None else None
+        frc = None if f is None else np.ascontiguousarray(f, dtype=np.float32)
+        P = pos.shape[0]
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        lam_next = None if lam_next is None else np.ascontiguousarray(lam_next, dtype=np.float64)
+        prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags)
+        o = dict(pos=np.zeros_like(pos), vel=np.zeros_like(pos), force=np.zeros_like(pos), inc_next=np.zeros(P), aux=np.zeros(P),
+                 label=np.zeros(P, dtype=np.int32), nan=np.zeros(P, dtype=np.int32))
+        anc = None if anc is None else np.ascontiguousarray(anc, dtype=np.int32)
+        labels = None if labels is None else np.ascontiguousarray(labels, dtype=np.int32)
+        lib().hh_smc_lookahead(self.handle, _p(pos), _p(vel), _p(frc), _p(o["pos"]), _p(o["vel"]), _p(o["force"]), C.c_int64(P), _p(anc), _p(labels),
+                               _p(lam), _p(lam_next), C.byref(prm), C.c_uint64(seed), C.c_uint64(step0), C.c_int64(gid0),
+                               _p(o["inc_next"]) if lam_next is not None else None, _p(o["aux"]), _p(o["label"]), _p(o["nan"]))
+        o["x"] = o["pos"][..., :3].astype(np.float64)
+        o["v"] = o["vel"][..., :3].astype(np.float64)
+        return o
+
+    def smc_propagate_cached(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, cache=None):
         """cdw_smc_propagate_cached on the host: `cache` = (fs rows (P, A, 4) float32, us (P,)) at the input rows, or None.
         Returns the usual outputs plus out["cache"] at the output rows."""
         pos = self.rows(x)
@@ -116,11 +136,9 @@ class HostSystem:
         fs_in = None if cache is None else np.ascontiguousarray(cache[0], dtype=np.float32)
         us_in = None if cache is None else np.ascontiguousarray(cache[1], dtype=np.float64)
         fs_out, us_out = np.zeros_like(pos), np.zeros(P)
-        f_open, u_open = handover if handover is not None else (np.zeros_like(pos), np.zeros(P))
-        o["handover"] = (f_open, u_open)
         lib().hh_smc_propagate_cached(self.handle, _p(pos), _p(vel), _p(o["pos"]), _p(o["vel"]), C.c_int64(P), _p(anc), _p(aux), _p(cum), _p(lam), C.byref(prm),
                                       C.c_uint64(seed), C.c_uint64(step0), C.c_int64(gid0), _p(o["inc"]), _p(o["w"]), _p(o["aux"]), _p(o["u_first"]),
-                                      _p(o["u_last"]), _p(o["proposal"]), _p(o["nan"]), _p(fs_in), _p(us_in), _p(fs_out), _p(us_out), _p(f_open), _p(u_open))
+                                      _p(o["u_last"]), _p(o["proposal"]), _p(o["nan"]), _p(fs_in), _p(us_in), _p(fs_out), _p(us_out))
         o["x"] = o["pos"][..., :3].astype(np.float64)
         o["v"] = o["vel"][..., :3].astype(np.float64)
         o["cache"] = (fs_out, us_out)

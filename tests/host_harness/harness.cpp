@@ -159,7 +159,7 @@ extern "C" int hh_smc_propagate_cached(const hh_system* s, const float* pos_in, 
                                        const int32_t* anc, const double* aux_in, const double* cum_in, const double* lambda,
                                        const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
                                        double* aux_out, double* u_first_out, double* u_last_out, double* proposal_out, int32_t* nan_flags,
-                                       const float* fs_in, const double* us_in, float* fs_out, double* us_out, float* f_open, double* u_open) {
+                                       const float* fs_in, const double* us_in, float* fs_out, double* us_out) {
     PropArgs a = {};
     a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out;
     a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.lambda = lambda;
@@ -170,9 +170,49 @@ extern "C" int hh_smc_propagate_cached(const hh_system* s, const float* pos_in, 
     if (a.flags & CDW_FLAG_ULA) { a.vel_in = nullptr; a.vel_out = nullptr; }
     a.fs_out = (float4*)fs_out; a.us_out = us_out;
     if (fs_in && a.n_steps > 0) { a.fs_in = (const float4*)fs_in; a.us_in = us_in; }
-    a.f_open = (float4*)f_open; a.u_open = u_open;
-    if (a.flags & CDW_FLAG_PHASE_OPEN) { a.pos_out = nullptr; a.vel_out = nullptr; }
     return run(s, a, true);
+}
+
+// the look-ahead iteration (cdw_smc_lookahead): part A with the tables of lambda, part B with those of lambda_next
+extern "C" int hh_smc_lookahead(const hh_system* s, const float* pos_in, const float* vel_in, const float* force_in, float* pos_out, float* vel_out,
+                                float* force_out, int64_t n, const int32_t* anc, const int32_t* label_in, const double* lambda, const double* lambda_next,
+                                const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_next_out, double* aux_out,
+                                int32_t* label_out, int32_t* nan_flags) {
+    PropArgs a = {};
+    a.pos_in = (const float4*)pos_in; a.vel_in = (const float4*)vel_in; a.fs_in = prm->n_steps > 0 ? (const float4*)force_in : nullptr;
+    a.pos_out = (float4*)pos_out; a.vel_out = (float4*)vel_out; a.fs_out = (float4*)force_out;
+    a.n = n; a.anc = anc; a.label_in = label_in; a.lambda = lambda; a.lambda_next = lambda_next; a.have_next = inc_next_out != nullptr;
+    a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;
+    a.seed = seed; a.step0 = step0; a.gid0 = gid0;
+    a.inc_next_out = inc_next_out; a.aux_out = aux_out; a.label_out = label_out; a.nan_flags = nan_flags;
+    const int T_ = g_team;
+    const Layout L = make_layout(s->dev, true, 1, T_);
+    std::vector<unsigned char> smem(L.total + 64, 0);
+    unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));
+    const Tables T = table_pointers(L, base);
+    for (long long p = 0; p < a.n; ++p) {
+        build_tables(s->dev, T, a.lambda, a.kT, true);
+        cta_load_rows(s->dev, a, base, L, 0, p, 1, true);
+        std::vector<AheadState> st(T_);
+        auto team = [&](auto&& body) {
+            if (T_ == 1) { body(0); return; }
+            std::barrier<> bar(T_);
+            std::vector<double> exchange(T_, 0.0);
+            std::vector<std::thread> lanes;
+            for (int tl = 0; tl < T_; ++tl)
+                lanes.emplace_back([&, tl]() {
+                    g_team_barrier = &bar; g_team_exchange = exchange.data();
+                    body(tl);
+                    g_team_barrier = nullptr; g_team_exchange = nullptr;
+                });
+            for (auto& t : lanes) t.join();
+        };
+        team([&](int tl) { st[tl] = lane_ahead_main(s->dev, T, lane_pointers(L, base, T_, tl), a, p); });
+        if (a.have_next) build_tables(s->dev, T, a.lambda_next, a.kT, true);
+        team([&](int tl) { lane_ahead_next(s->dev, T, lane_pointers(L, base, T_, tl), a, p, st[tl], a.have_next != 0); });
+        cta_store_rows_ahead(s->dev, a, base, L, 0, p, 1);
+    }
+    return 0;
 }
 
 extern "C" void hh_det_exp(const double* x, int64_t n, double* out) {

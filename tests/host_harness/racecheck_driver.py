@@ -31,12 +31,17 @@ lam0, lam = spec.lambda_vector(relative_lambdas(0.2)), spec.lambda_vector(relati
 hh.set_team(T)
 if mode == "baoab":        # unsplit evaluation, shadow / proposal work bookkeeping, Maxwell-Boltzmann velocities
     hs.smc_propagate(X, V, lam, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=3, aux=np.zeros(2), cum=np.zeros(2))
-elif mode == "cached":     # static + dynamic passes, cache rows in and out, gather through ancestors, split launches
+elif mode == "cached":     # static + dynamic passes, cache rows in and out, gather through ancestors
     s0 = hs.smc_propagate_cached(X, V, lam0, 0.002, 1.0, kT, 0, seed=7, step0=0)
     kw = dict(anc=np.array([1, 0]), aux=np.zeros(2), cum=np.zeros(2), cache=s0["cache"])
     hs.smc_propagate_cached(X, V, lam, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=1, **kw)
-    first = hs.smc_propagate_cached(X, V, lam, 0.002, 1.0, kT, 1, seed=7, step0=3, flags=_lib.CDW_FLAG_PHASE_OPEN, **kw)
-    hs.smc_propagate_cached(X, V, lam, 0.002, 1.0, kT, 1, seed=7, step0=3, flags=_lib.CDW_FLAG_PHASE_REST, handover=first["handover"], **kw)
+elif mode == "lookahead":  # the look-ahead iteration: forces travel with the particle, second table image, a reverted replica
+    lam2 = spec.lambda_vector(relative_lambdas(0.4))
+    e = hs.smc_lookahead(X, V, None, lam0, lam, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    b = hs.smc_lookahead(X, V, e["force"], lam, lam2, 0.002, 1.0, kT, 2, seed=7, step0=2, flags=1, anc=np.array([1, 0]))
+    Vbad = V.copy()
+    Vbad[1, 0, 0] = np.inf
+    hs.smc_lookahead(b["x"], Vbad, b["force"], lam2, None, 0.002, 1.0, kT, 1, seed=7, step0=4)
 elif mode == "ula":        # Euler-Maruyama move with constraint projection and both kernel densities
     hs.smc_propagate(X, None, lam, 0.0005, 0.0, kT, 2, seed=7, step0=3, flags=_lib.CDW_FLAG_ULA, aux=np.zeros(2), cum=np.zeros(2))
 print("racecheck-done", system, T, mode)

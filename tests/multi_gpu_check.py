@@ -2,9 +2,9 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
-The sharded anneal (particles split over the ranks, weights all-gathered, resampled rows pulled over NVLink inside the
-propagate kernel) must be BIT-IDENTICAL to the single-GPU anneal of the same global ensemble: noise is keyed by the
-global particle id and every rank reduces the same weight vector in the same order."""
+The sharded anneal (particles split over the ranks, incremental works all-gathered on a side stream, resampled rows pulled over
+NVLink inside the propagate kernel behind a peer barrier) must be BIT-IDENTICAL to the single-GPU anneal of the same global
+ensemble: noise is keyed by the global particle id and every rank reduces the same weight vector with exact integer sums."""
 import os
 import sys
 
@@ -30,13 +30,12 @@ def main():
     ok = True
     cases = (("multinomial", 0.9999, 4096, 8, "baoab"), ("systematic", 0.9999, 4096, 8, "baoab"), ("multinomial", 0.5, 2048 * world, 12, "baoab"),
              ("multinomial", 0.9999, 4096, 8, "ula"),
-             ("systematic", 0.9999, 1024 * 12 * world, 6, "baoab"))   # a batch whose per-rank share is launched very differently from the whole   # BASELINE configs[3]: the Euler-Maruyama proposal, sharded
+             ("systematic", 0.9999, 1024 * 12 * world, 6, "baoab"))   # (ula: BASELINE configs[3], the Euler-Maruyama proposal, sharded; last: a batch whose per-rank share is launched very differently from the whole)
     for kind, thr, P, T, proposal in cases:
         x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
         seq = ts.relative_alchemical_sequence(T)
         lang = LangevinParameters(timestep=0.0005) if proposal == "ula" else LangevinParameters()
         sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
-        sharded.overlap = kind == "systematic" and P == 4096   # one case through the opt-in split-launch loop (CDW_FLAG_PHASE_OPEN / _REST)
         sharded.anneal(x0[sharded.first:sharded.last])
         if os.environ.get("CDW_CHECK_GRAPH") and proposal == "baoab" and kind == "multinomial" and thr != 0.5:
             eager_cum = sharded.cum.clone()
@@ -57,7 +56,7 @@ def main():
             e = single.ensemble
             same = (torch.equal(torch.cat(pos_parts), e.pos[e.cur]) and torch.equal(torch.cat(vel_parts), e.vel[e.cur]) and
                     torch.equal(torch.cat(lab_parts), e.labels) and torch.equal(sharded.cum, e.cum) and torch.equal(sharded.stats, single.stats))
-            print(f"[multi_gpu_check] world={world} {proposal} {kind} thr={thr} P={P}{' (split launches)' if sharded.overlap else ''}: sharded == single-GPU bitwise: {same}; "
+            print(f"[multi_gpu_check] world={world} {proposal} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
                   f"resampled at {sharded.resampled_iterations()} FE={sharded.free_energy():.6f}", flush=True)
             ok &= bool(same) and len(sharded.resampled_iterations()) > 0 or (thr == 0.5 and bool(same))
         sharded.close()

@@ -248,10 +248,10 @@ def test_K2_large_reduction_accuracy(gpu):
 
 
 @pytest.mark.parametrize("n,kind", [(1, 0), (7, 1), (1000, 0), (10000, 0), (10000, 1), (24576, 0)])
-def test_cooperative_resample_statistics_follow_the_canonical_order(gpu, n, kind):
-    """cdw_smc_resample (8 cooperating CTAs, the routine cdw_smc_iteration runs inside the propagate launch): the
-    log-sum-exp statistics follow oracle.resampling.canonical_statistics — the plain sum bit for bit (det_exp and the
-    1024-virtual-thread order are fully specified), the rest to 1e-13 — and the ancestors equal the oracle's."""
+def test_resample_statistics_are_exact_integer_sums(gpu, n, kind):
+    """cdw_smc_resample: sum e and sum e^2 are 128-bit integer sums of the quantised exponentials (oracle.resampling.
+    canonical_statistics): bit for bit the oracle's, whatever the grid; nESS follows bitwise, the normaliser to 1e-13 (the
+    device's own log); the ancestors equal the oracle's; the workspace is left at rest."""
     import ctypes as C
     from coddiwomple_b200 import kernels
     lib = _lib.load()
@@ -268,21 +268,51 @@ def test_cooperative_resample_statistics_follow_the_canonical_order(gpu, n, kind
                                     _lib.ptr(cum), _lib.ptr(anc), _lib.ptr(ws.cdf), _lib.ptr(u), _lib.ptr(ws.buf), ws.bytes, _lib.current_stream()))
     s = ws.stats.cpu().numpy()
     wmin, sum_e, sum_e2, ness, mean = resampling.canonical_statistics(W_host)
-    assert s[_lib.STAT_WMIN] == wmin and s[_lib.STAT_SUM_E] == sum_e
-    assert s[_lib.STAT_SUM_E2] == pytest.approx(sum_e2, rel=1e-13) and s[_lib.STAT_NESS] == pytest.approx(ness, rel=1e-13)
+    assert s[_lib.STAT_WMIN] == wmin and s[_lib.STAT_SUM_E] == sum_e and s[_lib.STAT_SUM_E2] == sum_e2 and s[_lib.STAT_NESS] == ness
     assert s[_lib.STAT_MEAN] == pytest.approx(mean, rel=1e-13, abs=1e-13)
     uni = u.cpu().numpy()
     ref = resampling.ancestors(W_host, uni if kind == 0 else None, kind="multinomial" if kind == 0 else "systematic", u0=None if kind == 0 else uni[0])
     np.testing.assert_array_equal(anc.cpu().numpy(), ref)
     np.testing.assert_allclose(cum.cpu().numpy(), np.full(n, s[_lib.STAT_MEAN]), rtol=1e-15, atol=1e-15)
     assert int(ws.wmin_key.item()) == -1                     # re-armed
-    assert int(ws.buf[4].item()) == 0 and int(ws.buf[5].item()) == 0   # team counters back at rest
+    hdr = ws.buf[:8].cpu().numpy()
+    assert not hdr[[0, 1, 2, 3, 4, 7]].any()                 # accumulators and tickets back at rest
+    q, k = resampling.fixed_point_weights(W_host)
+    assert int(hdr[5]) == k and int(hdr[6]) == int(q.sum(dtype=object)) == int(s[_lib.STAT_TOTAL])
+
+
+def test_weigh_resample_composes_the_weights_through_the_previous_ancestors(gpu):
+    """cdw_smc_weigh_resample (the resampling of the look-ahead loop): W[i] = cum[i] + inc_src[anc_prev[i]], then exactly
+    cdw_smc_resample on W."""
+    import ctypes as C
+    from coddiwomple_b200 import kernels
+    lib = _lib.load()
+    n = 5000
+    r = np.random.RandomState(4)
+    inc_src, cum0, prev = r.normal(0, 1.0, n), r.normal(0, 0.5, n), r.randint(0, n, n).astype(np.int32)
+    for anc_prev in (prev, None):
+        ws = kernels.WeightWorkspace(n)
+        ws.wmin_key.fill_(-1)
+        d = lambda a, dt=torch.float64: torch.as_tensor(a, dtype=dt).cuda()
+        cum, inc, W, u = d(cum0), torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+        anc = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ap = None if anc_prev is None else d(anc_prev, torch.int32)
+        _lib.check(lib.cdw_smc_weigh_resample(0, _lib.ptr(d(inc_src)), _lib.ptr(ap), n, 0.5, _lib.ptr(ws.wmin_key), C.c_uint64(5), C.c_uint64(2), _lib.ptr(ws.stats),
+                                              _lib.ptr(cum), _lib.ptr(inc), _lib.ptr(W), _lib.ptr(anc), _lib.ptr(ws.cdf), _lib.ptr(u), _lib.ptr(ws.buf), ws.bytes,
+                                              _lib.current_stream()))
+        inc_ref = inc_src if anc_prev is None else inc_src[anc_prev]
+        np.testing.assert_array_equal(inc.cpu().numpy(), inc_ref)
+        np.testing.assert_array_equal(W.cpu().numpy(), cum0 + inc_ref)
+        ref = weights.resample_step(cum0, inc_ref, np.zeros(n), np.arange(n), uniforms=u.cpu().numpy(), kind="multinomial", floor_threshold=0.5)
+        np.testing.assert_array_equal(anc.cpu().numpy(), ref["ancestors"])
+        np.testing.assert_allclose(cum.cpu().numpy(), ref["cum"], rtol=1e-12, atol=1e-12)
+        assert bool(ws.stats[_lib.STAT_RESAMPLE].item()) == ref["resampled"]
 
 
 @pytest.mark.parametrize("n,kind", [(50000, 0), (50000, 1), (100003, 0)])
 def test_multi_kernel_resample_draws_its_own_uniforms(gpu, n, kind):
-    """cdw_smc_resample above 24 576 particles (statistics + scan + a search / emit kernel that draws the Philox uniforms
-    itself and re-arms the key): the uniforms are the documented counter-based stream and the ancestors are the oracle's."""
+    """cdw_smc_resample at sizes of several tiles (statistics + tile sums + tile scan with emission + the lookup that draws the
+    Philox uniforms itself): the uniforms are the documented counter-based stream and the ancestors are the oracle's."""
     import ctypes as C
     from coddiwomple_b200 import kernels
     lib = _lib.load()

@@ -145,6 +145,31 @@ def test_mcmc_smc_resampler_signature_and_result():
     assert np.isfinite(average_free_energy)
     p = particles[0]
     assert p.state.positions.shape == (13, 3) and p.ancestry[0] == 0 and len(p.proposal_works) == 10
+    # per-iteration histories like the reference's Particle (particles.py:38-47; appended at resamplers.py:115,129,196-200):
+    # one incremental work and one root label per iteration; the works add up to the cumulative work; labels are roots
+    eng = particles.engine
+    stats = eng.stats.cpu().numpy()
+    resampled = [t for t in range(1, 10) if stats[t, _lib.STAT_RESAMPLE]]
+    for i in (0, 17, 2999):
+        p = particles[i]
+        assert len(p.incremental_works) == 9 and len(p.ancestry) == 10 and p.ancestry[0] == i
+        assert sum(p.incremental_works) == pytest.approx(p.cumulative_work, abs=1e-9)
+        assert all(0 <= a < 3000 for a in p.ancestry)
+        for t in range(1, 10):   # the root label only changes at iterations that resampled
+            if t not in resampled:
+                assert p.ancestry[t] == p.ancestry[t - 1]
+    assert particles[5].ancestry[-1] == int(eng.ensemble.labels[5])
+    if resampled:   # right after a resampling every particle carries the ensemble normaliser (resamplers.py:107,129)
+        t = resampled[0]
+        assert len({round(sum(particles[i].incremental_works[:t]), 12) for i in (0, 17, 2999)}) == 1
+    np.random.seed(2)
+    lean = mcmc_smc_resampler(system_xml("fluorobenzene"), os.path.join(GOLDEN, "fluorobenzene_cache.npy"), None, None, None, 64, lambda_sequence,
+                              record_histories=False)
+    assert np.isfinite(lean[0].cumulative_work)
+    with pytest.raises(RuntimeError):
+        len(lean[0].incremental_works)
+    with pytest.raises(RuntimeError):
+        lean[0].ancestry[-1]
 
 
 def test_OpenMMPDFState_contract():
@@ -213,6 +238,27 @@ def test_OMMLI_and_OMMBIP_contract():
     assert np.isfinite(particle_state.positions).all()
     with pytest.raises(NotImplementedError):
         OMMLI(splitting="O V R V O")
+
+
+def test_OMMBIP_restart_attempts():
+    """openmm/propagators.py:134-190: a move that ends in a non-finite energy is retried n_restart_attempts times (fresh
+    noise); only the failed replicas are integrated again; what still fails stays at its pre-move state."""
+    from coddiwomple_b200.engine import positions_to_rows
+    from coddiwomple_b200.openmm.integrators import OMMLI
+    from coddiwomple_b200.openmm.propagators import OMMBIP
+    from coddiwomple_b200.openmm.states import OpenMMPDFState, RelativeAlchemicalState
+    X = cache_frames()[:48].astype(np.float64)
+    X[7, 12] = X[7, 5]            # two atoms on top of each other: the energy is not finite whatever the noise
+    runs = {}
+    for attempts in (0, 2):
+        pdf_state = OpenMMPDFState(system_xml("fluorobenzene"), RelativeAlchemicalState, temperature=300.0, pressure=None)
+        prop = OMMBIP(pdf_state, OMMLI(), n_restart_attempts=attempts, seed=3)
+        pos, vel = positions_to_rows(X), torch.zeros(48, 13, 4, device="cuda")
+        out = prop.apply_batch(pos, vel, n_steps=2, randomize_velocities=True, apply_pdf_to_context=True)
+        assert out["attempts"] == attempts and int(out["nan"].sum()) == 1 and int(out["nan"][7]) == 1
+        np.testing.assert_array_equal(pos[7, :, :3].cpu().numpy(), X[7].astype(np.float32))   # reverted
+        runs[attempts] = pos.cpu().numpy()
+    np.testing.assert_array_equal(runs[0], runs[2])   # the 47 good replicas were integrated exactly once
 
 
 def test_batched_equilibrium_statistics_many_particles():
@@ -382,52 +428,46 @@ def test_config2_full_size_graph_replay_equals_eager_loop():
     assert labels.min() >= 0 and labels.max() < P
 
 
-@pytest.mark.parametrize("kind,P", [("multinomial", 3000), ("systematic", 10000), ("multinomial", 12001)])
-def test_one_launch_iteration_equals_two_launches(kind, P):
-    """cdw_smc_iteration resamples inside the propagate launch (one extra thread block that waits for the weights);
-    every output is bitwise what cdw_smc_propagate_cached + cdw_smc_resample give."""
-    import os
-    if os.environ.get("CDW_NO_FUSED_RESAMPLE") or os.environ.get("CDW_NO_INLINE_RESAMPLE"):
-        pytest.skip("debug switches change which (differently ordered) statistics path runs")
+@pytest.mark.parametrize("kind,P,n_steps", [("multinomial", 3000, 1), ("systematic", 10000, 1), ("multinomial", 12001, 2), ("multinomial", 40000, 1)])
+def test_lookahead_loop_equals_the_sequential_loop(kind, P, n_steps):
+    """The look-ahead loop (cdw_smc_lookahead: the evaluation that opens iteration t + 1 closes launch t, the resampling runs on a
+    side stream beside the next launch) and the sequential loop (propagate, then resample, openmm/coddiwomple.py:314-328 in
+    order) give bitwise the same anneal: weights, statistics, ancestors, states."""
     from coddiwomple_b200.engine import LangevinParameters
     xml, _ = ts.alanine_dipeptide_shaped_xml()
     x0 = ts.alanine_dipeptide_shaped_ensemble(P, seed=4)
     seq = ts.relative_alchemical_sequence(9)
     runs = []
-    for one_launch in (True, False):
-        eng = _engine(xml, P, seq, langevin=LangevinParameters(), resampler=kind, seed=8, resample_seed=9, floor_threshold=0.9999)
+    for lookahead in (True, False):
+        eng = _engine(xml, P, seq, langevin=LangevinParameters(n_steps=n_steps), resampler=kind, seed=8, resample_seed=9, floor_threshold=0.9999,
+                      lookahead=lookahead, record_lineage=True)
         eng.initialize(x0)
         for t in range(1, eng.T):
-            if one_launch:
-                eng.step(t)
-            else:
-                eng.propagate(t)
-                eng.finish_iteration(t)
+            eng.step(t)
+        eng.finish()
         e = eng.ensemble
-        e.materialize()
-        runs.append([v.cpu().numpy().copy() for v in (e.cum, eng.stats, e.anc, e.pos[e.cur], e.vel[e.cur], e.aux[e.cur], e.label[e.cur], e.inc, e.W)])
+        lin = eng.lineage()
+        runs.append([v.cpu().numpy().copy() for v in (e.cum, eng.stats, e.anc, e.pos[e.cur], e.vel[e.cur], e.aux[e.cur], e.label[e.cur], e.inc, e.W)]
+                    + [lin["cum"], lin["labels"]])
         assert len(eng.resampled_iterations()) >= 2
-    for a, b in zip(*runs):
-        np.testing.assert_array_equal(a, b)
+        assert int(e.nan_flags.sum()) == 0
+    for k, (a, b) in enumerate(zip(*runs)):
+        np.testing.assert_array_equal(a, b, err_msg=str(k))
 
 
 @pytest.mark.parametrize("team", [1, 2, 8])
-def test_in_launch_resampling_with_other_team_sizes(team, tmp_path):
-    """CDW_TEAM = 1, 2 (32- / 64-thread CTAs: the in-launch resampling role is not available, cdw_smc_iteration must fall back
-    to the separate launch) and 8 (256-thread CTAs, four role CTAs): statistics, ancestors and state equal the run that never
-    resamples in-launch (CDW_NO_INLINE_RESAMPLE), bit for bit."""
+def test_other_team_sizes_run_both_loops(team, tmp_path):
+    """CDW_TEAM = 1, 2 (32- / 64-thread CTAs) and 8 (256-thread CTAs): for every launch shape the look-ahead loop and the
+    sequential loop agree bit for bit (the team size only changes the summation order inside a replica, for both alike)."""
     import os
     import subprocess
     import sys
     probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "team_probe.py")
     outs = []
-    for no_inline in (False, True):
+    for mode in ("lookahead", "sequential"):
         env = dict(os.environ, CDW_TEAM=str(team))
-        env.pop("CDW_NO_INLINE_RESAMPLE", None)
-        if no_inline:
-            env["CDW_NO_INLINE_RESAMPLE"] = "1"
-        out = str(tmp_path / f"team{team}_{int(no_inline)}.npz")
-        subprocess.run([sys.executable, probe, out], env=env, check=True, timeout=600)
+        out = str(tmp_path / f"team{team}_{mode}.npz")
+        subprocess.run([sys.executable, probe, out, mode], env=env, check=True, timeout=600)
         outs.append(np.load(out))
     for k in outs[0].files:
         np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
@@ -437,7 +477,7 @@ def test_in_launch_resampling_with_other_team_sizes(team, tmp_path):
 
 
 @pytest.mark.parametrize("P", [1, 2, 5, 33])
-def test_tiny_ensembles_run_through_the_one_launch_iteration(P):
+def test_tiny_ensembles(P):
     """Edge sizes: fewer particles than one warp team / one CTA; ancestors stay in range, a single particle keeps weight 1."""
     frames = cache_frames()
     x0 = frames[np.random.RandomState(9).randint(0, len(frames), P)]

@@ -56,8 +56,8 @@ def test_team_baoab_matches_oracle(name, T):
 
 
 @pytest.mark.parametrize("T", [4])
-def test_team_static_cache_and_split_launch(T):
-    """Cached iterations (static + dynamic passes, cache rows through the ancestor) and the OPEN / REST split with a team."""
+def test_team_static_cache_and_lookahead(T):
+    """Cached iterations (static + dynamic passes, cache rows through the ancestor) and the look-ahead form with a team."""
     o, spec, hs, X = _setup("fluorobenzene", P=6)
     P = X.shape[0]
     V = np.zeros_like(X)
@@ -70,12 +70,16 @@ def test_team_static_cache_and_split_launch(T):
     plain = hs.smc_propagate(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1, anc=anc, aux=-seed_out["u_first"], cum=np.zeros(P))
     for k, tol in (("x", 2e-7), ("v", 2e-5), ("u_first", 1e-10), ("u_last", 2e-4), ("inc", 1e-9)):
         assert np.abs(cached[k] - plain[k]).max() <= tol, k
-    first = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1 | _lib.CDW_FLAG_PHASE_OPEN, **kw)
-    rest = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1 | _lib.CDW_FLAG_PHASE_REST, handover=first["handover"], **kw)
-    np.testing.assert_array_equal(first["w"], cached["w"])
-    for k in ("x", "v", "aux", "u_last"):
-        np.testing.assert_array_equal(rest[k], cached[k])
-    np.testing.assert_array_equal(rest["cache"][0], cached["cache"][0])
+    # the look-ahead form of the same iteration (the evaluation that opens it was made by the previous call): bitwise equal
+    lam2 = spec.lambda_vector(relative_lambdas(0.4))
+    eq = hs.smc_lookahead(X, V, None, lam0, lam1, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    np.testing.assert_array_equal(eq["aux"], -seed_out["u_first"])
+    ahead = hs.smc_lookahead(X, V, eq["force"], lam1, lam2, 0.002, 1.0, kT, 1, seed=7, step0=1, flags=1, anc=anc)
+    np.testing.assert_array_equal(eq["inc_next"][anc], cached["inc"])
+    for k in ("x", "v", "aux"):
+        np.testing.assert_array_equal(ahead[k], cached[k])
+    nxt = hs.smc_propagate_cached(cached["x"], cached["v"], lam2, 0.002, 1.0, kT, 0, seed=7, step0=2, aux=cached["aux"], cum=np.zeros(P), cache=cached["cache"])
+    np.testing.assert_array_equal(ahead["inc_next"], nxt["inc"])
     # the oracle, too
     ref = langevin.baoab(lambda xx: o.energy_forces(xx, relative_lambdas(0.3)), X[anc], V[anc], o.masses, o.constraints, 0.002, 1.0, kT, 1, seed=7,
                          gids=np.arange(P), step0=1, randomize_velocities=True)

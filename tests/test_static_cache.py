@@ -94,24 +94,66 @@ def test_nan_guard_keeps_the_ancestors_cache():
     assert out["cache"][1][1] == seed_out["cache"][1][1] or (np.isnan(out["cache"][1][1]) and np.isnan(seed_out["cache"][1][1]))
 
 
-@pytest.mark.parametrize("flags", [0, 1])
-def test_split_launch_equals_one_launch(flags):
-    """CDW_FLAG_PHASE_OPEN followed by CDW_FLAG_PHASE_REST (the sharded loop's way to overlap the weight exchange with the
-    integration) gives bit for bit what the unsplit call gives."""
+def _two_iterations(hs, spec, X, V, n_steps, lookahead, bad_row=None):
+    """Two SMC iterations (lambda 0.2 -> 0.3 -> 0.4, a resampling gather in between) through the cached path or the look-ahead
+    path of the device code; returns what both must agree on."""
+    P = X.shape[0]
+    lam0, lam1, lam2 = (spec.lambda_vector(relative_lambdas(q)) for q in (0.2, 0.3, 0.4))
+    anc = np.array([1, 1, 0, 5, 4, 2])[:P]
+    if not lookahead:
+        seed = hs.smc_propagate_cached(X, V, lam0, 0.002, 1.0, kT, 0, seed=7, step0=0)
+        a1 = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, n_steps, seed=7, step0=n_steps, flags=1, aux=-seed["u_first"], cum=np.zeros(P), cache=seed["cache"])
+        a2 = hs.smc_propagate_cached(a1["x"], a1["v"], lam2, 0.002, 1.0, kT, n_steps, seed=7, step0=2 * n_steps, anc=anc, aux=a1["aux"], cum=np.zeros(P),
+                                     cache=a1["cache"])
+        return dict(aux0=-seed["u_first"], inc1=a1["inc"], x1=a1["x"], v1=a1["v"], aux1=a1["aux"], inc2=a2["inc"], x2=a2["x"], v2=a2["v"], aux2=a2["aux"],
+                    nan1=a1["nan"], nan2=a2["nan"])
+    e = hs.smc_lookahead(X, V, None, lam0, lam1, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    b1 = hs.smc_lookahead(X, V, e["force"], lam1, lam2, 0.002, 1.0, kT, n_steps, seed=7, step0=n_steps, flags=1)
+    b2 = hs.smc_lookahead(b1["x"], b1["v"], b1["force"], lam2, None, 0.002, 1.0, kT, n_steps, seed=7, step0=2 * n_steps, anc=anc, labels=np.arange(P) + 10)
+    assert list(b2["label"]) == list(anc + 10)
+    return dict(aux0=e["aux"], inc1=e["inc_next"], x1=b1["x"], v1=b1["v"], aux1=b1["aux"], inc2=b1["inc_next"][anc], x2=b2["x"], v2=b2["v"], aux2=b2["aux"],
+                nan1=b1["nan"], nan2=b2["nan"])
+
+
+@pytest.mark.parametrize("n_steps", [1, 3])
+def test_lookahead_iterations_equal_cached_iterations(n_steps):
+    """cdw_smc_lookahead moves the evaluation that opens iteration t + 1 to the end of launch t (the next weights become a
+    by-product, the forces travel with the particle): states, auxiliary works and incremental works are BITWISE those of the
+    cached path, where launch t + 1 opens with that evaluation."""
     o, spec, hs = _pair(system_xml("fluorobenzene"))
     X = cache_frames()[:6].astype(np.float64)
-    P = X.shape[0]
-    V = np.random.RandomState(2).normal(0, 0.2, X.shape).astype(np.float32).astype(np.float64)
-    lam0, lam1 = (spec.lambda_vector(relative_lambdas(q)) for q in (0.2, 0.3))
-    seed_out = hs.smc_propagate_cached(X, V, lam0, 0.002, 1.0, kT, 0, seed=7, step0=0)
-    anc = np.array([1, 1, 0, 5, 4, 2])
-    kw = dict(anc=anc, aux=-seed_out["u_first"], cum=np.arange(P) * 0.1, cache=seed_out["cache"])
-    full = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=flags, **kw)
-    first = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=flags | _lib.CDW_FLAG_PHASE_OPEN, **kw)
-    np.testing.assert_array_equal(first["inc"], full["inc"])
-    np.testing.assert_array_equal(first["w"], full["w"])
-    rest = hs.smc_propagate_cached(X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=3, flags=flags | _lib.CDW_FLAG_PHASE_REST, handover=first["handover"], **kw)
-    for k in ("x", "v", "aux", "u_last", "nan"):
-        np.testing.assert_array_equal(rest[k], full[k])
-    np.testing.assert_array_equal(rest["cache"][0], full["cache"][0])
-    np.testing.assert_array_equal(rest["cache"][1], full["cache"][1])
+    V = np.zeros_like(X)
+    a = _two_iterations(hs, spec, X, V, n_steps, lookahead=False)
+    b = _two_iterations(hs, spec, X, V, n_steps, lookahead=True)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    # and the oracle: incremental work of iteration 1 is u_1(x_0) - u_0(x_0)
+    np.testing.assert_allclose(b["inc1"], o.reduced_potential(X, relative_lambdas(0.3)) - o.reduced_potential(X, relative_lambdas(0.2)), rtol=1e-8, atol=1e-10)
+
+
+def test_lookahead_reverts_a_move_that_ends_in_a_non_finite_energy():
+    """openmm/propagators.py:166-186: the replica keeps its pre-move state; its aux and its next incremental work are those of
+    the state that is kept (what openmm/coddiwomple.py:315, 326-327 compute on the reverted particle)."""
+    o, spec, hs = _pair(system_xml("fluorobenzene"))
+    X = cache_frames()[:4].astype(np.float64)
+    V = np.zeros_like(X)
+    V[2, 0, 0] = np.inf   # finite at rest, not after a step
+    lam1, lam2 = (spec.lambda_vector(relative_lambdas(q)) for q in (0.3, 0.4))
+    e = hs.smc_lookahead(X, V, None, lam1, lam1, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    for team in (1, 4):
+        hh.set_team(team)
+        b = hs.smc_lookahead(X, V, e["force"], lam1, lam2, 0.002, 1.0, kT, 1, seed=7, step0=1)
+        hh.set_team(1)
+        assert list(b["nan"]) == [0, 0, 1, 0]
+        np.testing.assert_array_equal(b["pos"][2], hs.rows(X)[2])
+        np.testing.assert_array_equal(b["vel"][2], hs.rows(V)[2])
+        keep = hs.smc_lookahead(X[2:3], V[2:3], None, lam1, lam2, 0.002, 1.0, kT, 0, seed=7, step0=0)
+        assert np.isfinite(keep["aux"][0]) and np.isfinite(keep["inc_next"][0])
+        np.testing.assert_allclose(b["aux"][2], keep["aux"][0], rtol=1e-13)              # (team size changes the summation order)
+        np.testing.assert_allclose(b["inc_next"][2], keep["inc_next"][0], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(b["aux"][2], -o.reduced_potential(X[2:3], relative_lambdas(0.3))[0], rtol=1e-10)
+        # the other replicas are untouched by their neighbour's revert
+        ok = hs.smc_lookahead(X[[0, 1]], V[[0, 1]], e["force"][[0, 1]], lam1, lam2, 0.002, 1.0, kT, 1, seed=7, step0=1)
+        if team == 1:
+            np.testing.assert_array_equal(ok["pos"], b["pos"][:2])
+            np.testing.assert_array_equal(ok["inc_next"], b["inc_next"][:2])
