@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py — particle-Langevin-steps/s and SMC anneals/s of the B200 SMC annealing hot path.
 
-Workload (BASELINE.json configs[1]): AlanineDipeptideVacuum-shaped alchemical annealing, 10^4 particles per GPU,
-100 lambda states, 1 BAOAB step per lambda, multinomial resampling at nESS <= 0.5, synthetic replicas
-(coddiwomple_b200/testsystems.py).  One "step" = one full anneal (99 SMC iterations over all particles).
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): perses-style vacuum ligand mutation — the
+benzene -> fluorobenzene hybrid of coddiwomple/data/perses_data (13 atoms), 10^5 particles per GPU drawn from the reference's
+lambda = 0 cache, the reference's alchemical protocol (coddiwomple/tests/legacy_tests.py:58-76) on 100 lambda states, 1 BAOAB step
+per lambda, multinomial resampling.  One "step" = one full anneal (99 SMC iterations over all particles).  Multi-GPU runs keep
+10^5 particles PER GPU (weak scaling).  BASELINE configs[1] (10^4 x 22-atom AlanineDipeptideVacuum shape) is timed beside it and
+reported under "config2"; on 8 GPUs configs[3] (10^6 particles, BAOAB and Euler-Maruyama proposals) under "config4".
 
   python bench.py --gpus N --steps K --warmup W          # our arm (N > 1: launched under torchrun, one rank per GPU)
-  python bench.py --impl reference --steps K --warmup W  # the CPU oracle port of the reference path on the host cores
+  python bench.py --impl reference --steps K --warmup W  # the CPU arm: the same loop compiled for the host, all cores
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §6 for how every field is measured.
 """
@@ -18,18 +21,28 @@ import sys
 import threading
 import time
 
-if "reference" in sys.argv:  # one numpy worker per core: keep BLAS/OpenMP from oversubscribing the host
-    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ.setdefault(_k, "1")
-
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_PARTICLES = 10_000
+N_PARTICLES = 100_000          # per GPU
 N_LAMBDA = 100
-WORKLOAD = "AlanineDipeptideVacuum-shaped alchemical annealing (synthetic 22-atom perses-form hybrid), 1e4 particles/GPU, 100 lambda, 1 BAOAB step/lambda"
+FLOOR_THRESHOLD = 0.5          # vanilla_floor_threshold's default (coddiwomple/utils.py:67-72)
+CPU_SAMPLE_PARTICLES = 10_000  # the CPU arm times a bounded sample of the same workload: this many of the 10^5 particles, all 100 lambda
+WORKLOAD = ("perses-style vacuum ligand mutation (benzene->fluorobenzene hybrid, 13 atoms, reference fixture), 1e5 particles/GPU, 100 lambda "
+            "(legacy_tests.py:58-76 protocol), 1 BAOAB step/lambda, multinomial resampling")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def workload_inputs(P, seed):
+    """(xml, x0 host (P, 13, 3) float32, parameter sequence) of configs[2]; particles drawn with replacement from the 151 lambda = 0 frames."""
+    from coddiwomple_b200 import testsystems as ts
+    from coddiwomple_b200.system import load_xml
+    xml = load_xml(os.path.join(GOLDEN, "systems", "fluorobenzene.vacuum.xml.gz"))
+    frames = np.load(os.path.join(GOLDEN, "fluorobenzene_cache.npy"))
+    x0 = frames[np.random.RandomState(3 + seed).randint(0, len(frames), P)]
+    return xml, x0, ts.relative_alchemical_sequence(N_LAMBDA)
 
 
 def algorithmic_flops(spec, n_steps=1):
@@ -103,31 +116,6 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_rate(n_particles, n_lambda, seed=0):
-    """Time the oracle port (fp64 numpy restatement of the reference's loop) on a bounded sample of the workload."""
-    from coddiwomple_b200 import testsystems as ts
-    from oracle import smc
-    from oracle.potential import XmlSystemOracle
-    xml, _ = ts.alanine_dipeptide_shaped_xml()
-    o = XmlSystemOracle(xml)
-    x0 = ts.alanine_dipeptide_shaped_ensemble(n_particles)
-    seq = ts.relative_alchemical_sequence(n_lambda)
-    t0 = time.perf_counter()
-    out = smc.anneal(o, x0, seq, seed=seed, resample_seed=seed + 1)
-    dt = time.perf_counter() - t0
-    return n_particles * (n_lambda - 1) / dt, dt, out["free_energy"]
-
-
-CPU_SAMPLE_PARTICLES = 128  # per worker and step: ~3 s of the numpy port per step on one core
-
-
-def _cpu_worker(job):
-    P, T, seed = job
-    _, dt, fe = cpu_port_rate(P, T, seed=seed)
-    return dt, fe
-
-
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -135,49 +123,62 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
 def run_reference(args):
-    """The reference arm: the CPU restatement of the reference's loop on ALL host cores.  The reference's own engine
-    (OpenMM's CPU platform) is not installable offline; the numpy port is single-threaded per anneal, so the host is
-    filled with one independent anneal of CPU_SAMPLE_PARTICLES particles per core and the rates are summed."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference arm: the hot loop compiled for the host (oracle/cpu_port: C++ / OpenMP over particles, every host core), on a
+    bounded sample of the same workload.  The reference's own engine (OpenMM's CPU platform) is not installable offline, so `kind` is
+    "port": the per-particle arithmetic is this library's per-replica code built by g++, the loop is the reference's."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import multiprocessing as mp
-    from concurrent.futures import ProcessPoolExecutor
-    cores = host_cores()
-    P, T = CPU_SAMPLE_PARTICLES, N_LAMBDA
-    rates, times = [], []
-    with ProcessPoolExecutor(cores, mp_context=mp.get_context("fork")) as pool:
-        for _ in range(max(args.warmup, 1)):
-            list(pool.map(_cpu_worker, [(8, 10, 0)] * cores))
-        for k in range(args.steps):
-            t0 = time.perf_counter()
-            list(pool.map(_cpu_worker, [(P, T, 1000 * k + c) for c in range(cores)]))
-            dt = time.perf_counter() - t0
-            times.append(dt); rates.append(cores * P * (T - 1) / dt)
-    value = float(np.mean(rates))
-    sample = (f"oracle/ (fp64 numpy restatement of openmm/coddiwomple.py:312-331 + OpenMM's arithmetic), per step {cores} independent anneals "
-              f"(one per core) of {P} particles x {T} lambda, vectorised over particles; the reference itself cannot run: OpenMM is not installable offline")
+    from coddiwomple_b200.system import spec_from_xml
+    from oracle import cpu_port
+    cores = cpu_port.threads()
+    P = CPU_SAMPLE_PARTICLES
+    xml, x0, seq = workload_inputs(P, 0)
+    port = cpu_port.CpuPort(spec_from_xml(xml))
+    for _ in range(max(args.warmup, 1)):
+        port.anneal(x0[:256], seq[:10], floor_threshold=FLOOR_THRESHOLD)
+    times, fe = [], None
+    for k in range(args.steps):
+        t0 = time.perf_counter()
+        out = port.anneal(x0, seq, floor_threshold=FLOOR_THRESHOLD, seed=k, resample_seed=1000 + k)
+        times.append(time.perf_counter() - t0)
+        fe = out["free_energy"]
+    value = P * (N_LAMBDA - 1) / float(np.mean(times))
+    sample = (f"oracle/cpu_port (the loop of openmm/coddiwomple.py:312-331 in C++/OpenMP around the library's per-replica code built by g++ -O3 -march=native), "
+              f"{cores} threads, per step one anneal of {P} of the 1e5 particles x {N_LAMBDA} lambda; the reference itself cannot run: OpenMM is not installable offline")
     line = {"impl": "reference", "metric": "particle-Langevin-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{cores} x {P} particles x {T} lambda per step"},
-            "anneals_per_s": value / (N_PARTICLES * (N_LAMBDA - 1)),
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{P} of the 1e5 particles x {N_LAMBDA} lambda per step", "same_config": True},
+            "anneals_per_s": value / (N_PARTICLES * (N_LAMBDA - 1)), "free_energy_kT": fe,
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_subprocess():
-    """Run the reference arm in a child process (a fork pool after CUDA initialisation is not safe) on a bounded sample."""
-    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    """B2 (compiled port, all cores) on a bounded sample, in a child process; B1 (the reference's own Python classes driving the numpy
+    oracle, one particle at a time) is quoted from the committed measurement made where /root/reference exists."""
+    env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         env.pop(k, None)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"], env=env,
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=900)
+    base = None
     for ln in reversed(out.stdout.splitlines()):
         if ln.startswith("{"):
-            return json.loads(ln)["cpu_baseline"]
-    raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
+            base = json.loads(ln)["cpu_baseline"]
+            break
+    if base is None:
+        raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_cpu_baseline_b1.json")) as fh:
+            b1 = json.load(fh)
+        base["b1_reference_python_loop"] = {k: b1[k] for k in ("value", "unit", "cores", "kind", "particles", "n_lambda", "where")}
+    except (OSError, KeyError):
+        pass
+    base["b0_reference_notebook"] = {"value": 3.0e2, "unit": "particle-steps/s", "source": "troubleshooting/troubleshoot.ipynb JSON 137: 10 x 500 OpenMM-CPU steps in 16 s (quoted, not re-measured)"}
+    return base
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -197,17 +198,16 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
-    xml, _ = ts.alanine_dipeptide_shaped_xml()
-    spec = spec_from_xml(xml)
-    seq = ts.relative_alchemical_sequence(N_LAMBDA)
     P = N_PARTICLES
-    x0_host = ts.alanine_dipeptide_shaped_ensemble(P, seed=2 + rank)
+    xml, x0_host, seq = workload_inputs(P, rank)
+    spec = spec_from_xml(xml)
     langevin = LangevinParameters(temperature=300.0, collision_rate=1.0, timestep=0.002, n_steps=1)
+    thr = float(args.threshold)
     if world > 1:
         from coddiwomple_b200.parallel import ShardedSMCEngine
-        eng = ShardedSMCEngine(xml, P * world, seq, langevin=langevin, seed=0, resample_seed=1)
+        eng = ShardedSMCEngine(xml, P * world, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr)
     else:
-        eng = SMCEngine(xml, P, seq, langevin=langevin, seed=0, resample_seed=1)
+        eng = SMCEngine(xml, P, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr)
     x0_pinned = positions_to_rows(x0_host, device=None, pinned=True)
     x0_dev = x0_pinned.cuda()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
@@ -224,7 +224,7 @@ def run_gpu(args):
         eng.load(x0_dev)
         eng.capture()   # the whole anneal (no host decisions inside) as one CUDA graph
     elif use_graph:
-        eng.capture(x0_dev)   # per rank: T-1 x (fused propagate over peer memory, NCCL all-gather of W, global resample)
+        eng.capture(x0_dev)   # per rank: T-1 x (peer barrier + launch over peer memory | all-gather + global resample on a side branch)
 
     def anneal_resident():
         eng.anneal(x0_dev)
@@ -239,7 +239,7 @@ def run_gpu(args):
     def timed(fn, steps):
         ms = []
         for _ in range(steps):
-            flush.fill_(1.0)  # L2 flush between anneals (the working set of one anneal is L2-resident by design)
+            flush.fill_(1.0)  # L2 flush between anneals (one iteration's rows are 62 MB: L2-sized)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -262,59 +262,56 @@ def run_gpu(args):
     value = units_per_step / (np.mean(ms) * 1e-3)
     e2e_value = units_per_step / (np.mean(ms_e2e) * 1e-3)
     fe = eng.free_energy()
+    n_resampled = len(eng.resampled_iterations())
 
-    # ---- roofline of the dominant kernel: the fused propagate kernel, timed with CUDA events on its stream
-    flops = algorithmic_flops(spec, langevin.n_steps)
-    eng.graph = None  # per-launch timing uses the eager loop
-    eng.initialize(x0_dev)
-    evs = []
-    loop0, loop1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loop0.record()
-    for t in range(1, eng.T):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if world == 1:
-            eng.step(t)          # ONE launch: the propagate kernel with the in-launch resample block (cdw_smc_iteration)
-            e1.record()
-        else:
-            eng.propagate(t)
-            e1.record()
-            eng.finish_iteration(t)
-        evs.append((e0, e1))
-    loop1.record()
-    torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    loop_ms = float(loop0.elapsed_time(loop1))  # the same eager loop end to end: the kernel's share is taken against it
+    # ---- parity probe (outside the timed region): the multi-GPU anneal against the single-GPU one, or on one GPU the look-ahead loop
+    # against the sequential loop, bit for bit
+    probe = parity_probe(torch, dist, world, rank, xml)
+
+    # ---- extra workloads, rank-collective ones first
+    config4 = config4_runs(torch, dist, world, rank, xml, langevin) if world == 8 else None
+    sharded_sweep = sharded_resampling(torch, dist, _lib, world, rank, spec.n_atoms) if world > 1 else None
+
     line = None
     if rank == 0:
+        flops = algorithmic_flops(spec, langevin.n_steps)
         fp64_peak, _ = kernels.fma_peak(True, 8192)
         fp32_peak, _ = kernels.fma_peak(False, 8192)
+        # the dominant kernel runs once per iteration and nothing else is on the critical path: the whole graph-timed anneal divided
+        # by its T - 1 launches is an UPPER bound of the launch duration (it also holds the equip launch, the final gather and, on
+        # several GPUs, the peer barriers)
+        k_ms = float(np.mean(ms)) / (N_LAMBDA - 1)
         achieved = flops["per_iteration"] * P / (k_ms * 1e-3) / 1e12
         peaks, peaks_src = measured_peaks()
-        share = k_ms * (eng.T - 1) / loop_ms
         traffic = measured_traffic()
-        # ---- HBM-bound resampling kernels at sweep size (config 5), for the record
-        sweep = resampling_sweep(torch, kernels, _lib, 1 << 24, spec.n_atoms if spec.n_atoms < 14 else 13) if world == 1 else None
+        config2 = config2_run(torch, ts, SMCEngine, LangevinParameters, positions_to_rows, spec_from_xml, kernels, fp64_peak, args) if world == 1 else None
+        sweep = resampling_sweep(torch, kernels, _lib, 1 << 24, 13, peaks.get("hbm_gbs")) if world == 1 else None
         cpu_base = cpu_baseline_subprocess() if world == 1 else None
+        per_iter = 1 + (5 if eng.kind == _lib.CDW_RESAMPLE_MULTINOMIAL else 4) + (1 if world > 1 else 0)
         line = {"metric": "particle-Langevin-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "particles_per_gpu": P, "parallelism": (f"particles sharded over {world} GPUs; all-gather of W + peer-mapped gather-on-load" if world > 1 else "single GPU"), "n_lambda": N_LAMBDA, "atoms": spec.n_atoms, "resampler": "multinomial@nESS<=0.5",
-                           "step": "one full anneal = 99 SMC iterations (single GPU: one kernel launch each)", "l2": "flushed between anneals by a 256 MiB write", "terms": spec.counts()},
-                "anneals_per_s": 1e3 / float(np.mean(ms)), "free_energy_kT": fe, "resampled_iterations": len(eng.resampled_iterations()),
+                "config": {"workload": WORKLOAD, "particles_per_gpu": P, "n_lambda": N_LAMBDA, "atoms": spec.n_atoms, "floor_threshold": thr,
+                           "parallelism": (f"particles sharded over {world} GPUs; per iteration: peer barrier + ONE launch gathering ancestors over NVLink; all-gather of "
+                                           f"incremental works + global resampling on a side stream" if world > 1 else "single GPU"),
+                           "step": "one full anneal = 99 SMC iterations (one propagate launch each; the resampling of iteration t runs beside launch t on a side stream)",
+                           "l2": "flushed between anneals by a 256 MiB write; one iteration's rows (62 MB) are L2-sized", "terms": spec.counts()},
+                "anneals_per_s": 1e3 / float(np.mean(ms)), "free_energy_kT": fe, "resampled_iterations": n_resampled,
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": float(np.mean(ms_e2e)), "h2d_bytes_per_step": int(x0_pinned.numel() * 4),
                         "d2h_bytes_per_step": int(cum_host.numel() * 8), "api": "SMCEngine.anneal(pinned host rows) + cumulative works to host", "cuda_graph": use_graph},
-                # both timed loops; single GPU: seed + ONE launch per iteration (propagate with the in-launch resample block) + final
-                # gather; sharded: seed + (propagate, weight_update, fused resample or its 7-kernel form above 24576 particles) per
-                # iteration + final peer gather
-                "gpu_launches": int(args.steps * 2 * (1 + (1 if world == 1 else (3 if P * world <= 24576 else 9)) * (N_LAMBDA - 1) + 1)),
-                "roofline": {"bound": "fp64", "kernel": "smc_propagate_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                # both timed loops; per anneal: equip + (T - 1) x (look-ahead launch + weight compose + statistics + tile sums + tile scan [+ lookup]
+                # [+ peer barrier]) + final gather [+ its barrier]
+                "gpu_launches": int(args.steps * 2 * (1 + per_iter * (N_LAMBDA - 1) + (2 if world > 1 else 1))),
+                "parity_probe": probe,
+                "roofline": {"bound": "fp64", "kernel": "smc_lookahead_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
-                             "avg_launch_ms": k_ms, "share_of_step": share,
+                             "avg_launch_ms": k_ms, "avg_launch_ms_is": "ms_per_step / (n_lambda - 1): upper bound, the graph-timed anneal holds nothing else on its critical path",
+                             "share_of_step": (traffic or {}).get("share_of_step"),
                              "algorithmic_flop_per_particle_iteration": flops["per_iteration"],
                              "peak_source": "cdw_fma_peak(fp64) micro-benchmark run in this process (MEASURED_PEAKS.json has no FP pipe figure)",
                              "fp32_fma_peak_tflops": fp32_peak, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
-                "resampling_sweep": sweep,
+                "config2": config2, "config4": config4,
+                "resampling_sweep": sweep, "resampling_sweep_sharded": sharded_sweep,
                 "cpu_baseline": cpu_base,
                 "clocks": clocks.summary()}
         print(json.dumps(line))
@@ -323,14 +320,147 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def resampling_sweep(torch, kernels, _lib, n, A):
-    """GB/s of the HBM-bound kernels at n particles: K2 stats, K3a scan (3 kernels) + search, K3b gather (pos+vel rows)."""
+def parity_probe(torch, dist, world, rank, xml):
+    """True iff a small anneal run two ways gives bitwise the same cumulative works, statistics and particles."""
+    from coddiwomple_b200 import testsystems as ts
+    from coddiwomple_b200.engine import SMCEngine
+    frames = np.load(os.path.join(GOLDEN, "fluorobenzene_cache.npy"))
+    seq = ts.relative_alchemical_sequence(8)
+    if world == 1:
+        P = 4096
+        x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
+        outs = []
+        for lookahead in (True, False):
+            e = SMCEngine(xml, P, seq, seed=3, resample_seed=4, floor_threshold=0.9999, lookahead=lookahead)
+            e.anneal(x0)
+            outs.append((e.ensemble.cum.clone(), e.stats.clone(), e.ensemble.positions.clone(), e.ensemble.labels.clone()))
+        same = all(torch.equal(a, b) for a, b in zip(*outs))
+        return {"ok": bool(same), "what": "look-ahead loop == sequential loop, bitwise (4096 particles, 8 lambda, 7 resamplings)"}
+    from coddiwomple_b200.parallel import ShardedSMCEngine
+    P = 2048 * world
+    x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
+    sh = ShardedSMCEngine(xml, P, seq, seed=3, resample_seed=4, floor_threshold=0.9999)
+    sh.anneal(x0[sh.first:sh.last])
+    parts = [torch.empty_like(sh.local("pos")) for _ in range(world)]
+    dist.all_gather(parts, sh.local("pos").contiguous())
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    if rank == 0:
+        single = SMCEngine(xml, P, seq, seed=3, resample_seed=4, floor_threshold=0.9999)
+        single.anneal(x0)
+        e = single.ensemble
+        same = torch.equal(torch.cat(parts), e.pos[e.cur]) and torch.equal(sh.cum, e.cum) and torch.equal(sh.stats, single.stats)
+        ok.fill_(1 if same else 0)
+    dist.broadcast(ok, 0)
+    sh.close()
+    return {"ok": bool(int(ok.item())), "what": f"{world}-GPU sharded anneal == single-GPU anneal, bitwise ({P} particles, 8 lambda, 7 resamplings)"}
+
+
+def config2_run(torch, ts, SMCEngine, LangevinParameters, positions_to_rows, spec_from_xml, kernels, fp64_peak, args):
+    """BASELINE configs[1]: AlanineDipeptideVacuum-shaped annealing, 10^4 particles, 100 lambda (last round's headline workload)."""
+    xml, _ = ts.alanine_dipeptide_shaped_xml()
+    P = 10_000
+    rows = positions_to_rows(ts.alanine_dipeptide_shaped_ensemble(P, seed=2))
+    eng = SMCEngine(xml, P, ts.relative_alchemical_sequence(N_LAMBDA), langevin=LangevinParameters(), seed=0, resample_seed=1)
+    eng.load(rows)
+    eng.capture()
+    for _ in range(3):
+        eng.anneal(rows)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(max(args.steps // 2, 5)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.anneal(rows); e1.record(); e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    flops = algorithmic_flops(spec_from_xml(xml))
+    k_ms = float(np.mean(ms)) / (N_LAMBDA - 1)
+    achieved = flops["per_iteration"] * P / (k_ms * 1e-3) / 1e12
+    return {"workload": "AlanineDipeptideVacuum-shaped alchemical annealing (synthetic 22-atom perses-form hybrid), 1e4 particles, 100 lambda, 1 BAOAB step/lambda",
+            "value": P * (N_LAMBDA - 1) / (np.mean(ms) * 1e-3), "unit": "particle-steps/s", "ms_per_anneal": float(np.mean(ms)), "anneals_per_s": 1e3 / float(np.mean(ms)),
+            "free_energy_kT": eng.free_energy(), "resampled_iterations": len(eng.resampled_iterations()),
+            "roofline_frac_fp64": achieved / fp64_peak, "algorithmic_flop_per_particle_iteration": flops["per_iteration"]}
+
+
+def config4_runs(torch, dist, world, rank, xml, langevin):
+    """BASELINE configs[3]: 10^6 particles of the small-molecule vacuum system sharded over 8 GPUs (125 000 per GPU), with the MCMC
+    (BAOAB) move and with the Euler-Maruyama proposal + generalised weight of the controlled-SMC scripts (troubleshooting/csmc.py:96-191)."""
+    from coddiwomple_b200 import testsystems as ts
+    from coddiwomple_b200.engine import LangevinParameters, positions_to_rows
+    from coddiwomple_b200.parallel import ShardedSMCEngine
+    frames = np.load(os.path.join(GOLDEN, "fluorobenzene_cache.npy"))
+    P = 1_000_000
+    seq = ts.relative_alchemical_sequence(N_LAMBDA)
+    out = {}
+    for proposal, lang in (("baoab", langevin), ("ula", LangevinParameters(timestep=0.0005))):
+        eng = ShardedSMCEngine(xml, P, seq, langevin=lang, seed=0, resample_seed=1, proposal=proposal)
+        rows = positions_to_rows(frames[np.random.RandomState(11 + rank).randint(0, len(frames), eng.P_loc)])
+        eng.capture(rows)
+        for _ in range(2):
+            eng.anneal(rows)
+        ms = []
+        for _ in range(5):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.anneal(rows); e1.record(); e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms.append(float(t.item()))
+        out[proposal] = {"particles": P, "particles_per_gpu": eng.P_loc, "n_lambda": N_LAMBDA, "ms_per_anneal": float(np.mean(ms)),
+                         "value": P * (N_LAMBDA - 1) / (np.mean(ms) * 1e-3), "unit": "particle-steps/s", "free_energy_kT": eng.free_energy(),
+                         "resampled_iterations": len(eng.resampled_iterations())}
+        eng.close()
+    return out
+
+
+def sharded_resampling(torch, dist, _lib, world, rank, A):
+    """BASELINE configs[4] on several GPUs: one resampling step of the sharded loop at 2^22 particles per GPU — all-gather of the
+    incremental works (NCCL), global weigh + resample on every rank (replicated, bit-identical), this rank's share of the peer gather."""
+    import ctypes as C
+    lib = _lib.load()
+    n_loc = 1 << 22
+    n = n_loc * world
+    g = torch.Generator("cuda").manual_seed(5 + rank)
+    inc_loc = torch.randn(n_loc, dtype=torch.float64, device="cuda", generator=g)
+    inc = torch.empty(n, dtype=torch.float64, device="cuda")
+    cum, W = torch.zeros(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda")
+    anc = torch.empty(n, dtype=torch.int32, device="cuda")
+    cdf = torch.empty(n + 2, dtype=torch.int64, device="cuda")[:n]
+    u = torch.empty(n, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+    key = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+    ws_bytes = int(lib.cdw_weight_workspace_bytes(n))
+    ws = torch.zeros((ws_bytes + 7) // 8, dtype=torch.int64, device="cuda")
+    st = _lib.current_stream()
+    out = {"particles": n, "particles_per_gpu": n_loc}
+    for kind, name in ((0, "multinomial"), (1, "systematic")):
+        def step():
+            dist.all_gather_into_tensor(inc, inc_loc)
+            cum.zero_()
+            _lib.check(lib.cdw_smc_weigh_resample(kind, _lib.ptr(inc), None, n, -1.0, _lib.ptr(key), C.c_uint64(6), C.c_uint64(1), _lib.ptr(stats), _lib.ptr(cum), None,
+                                                  _lib.ptr(W), _lib.ptr(anc), _lib.ptr(cdf), _lib.ptr(u), _lib.ptr(ws), ws_bytes, st))
+        step(); torch.cuda.synchronize()
+        ms = []
+        for _ in range(5):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record(); e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms.append(float(t.item()))
+        out[name] = {"ms": float(np.min(ms)), "particles_per_s": n / (np.min(ms) * 1e-3)}
+    return out
+
+
+def resampling_sweep(torch, kernels, _lib, n, A, hbm_peak):
+    """GB/s of the HBM-bound kernels at n particles (BASELINE configs[4] on one GPU; the full 1e3 .. 1e8 sweep is
+    tools/resampling_sweep.py -> profiles/): K2 update + statistics, K3a tile sums + scan (+ emission / lookup), K3b gather of
+    pos + vel rows.  Bytes per particle are SURVEY.md §8(d)'s algorithmic figures."""
     lib = _lib.load()
     g = torch.Generator("cuda").manual_seed(5)
     W = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
     u = kernels.philox_uniforms(6, 0, n)
     ws = kernels.WeightWorkspace(n)
     anc = torch.empty(n, dtype=torch.int32, device="cuda")
+    Wc = torch.empty_like(W)
     nP = min(n, 1 << 22)
     pos = torch.randn(nP, A, 4, device="cuda"); vel = torch.randn(nP, A, 4, device="cuda")
     pos_o, vel_o = torch.empty_like(pos), torch.empty_like(vel)
@@ -350,7 +480,7 @@ def resampling_sweep(torch, kernels, _lib, n, A):
 
     def stats():
         ws.wmin_key.fill_(-1)
-        _lib.check(lib.cdw_weight_update(_lib.ptr(W), None, None, None, n, None, _lib.ptr(ws.cdf.view(torch.float64)), _lib.ptr(ws.wmin_key), st))
+        _lib.check(lib.cdw_weight_update(_lib.ptr(W), None, None, None, n, None, _lib.ptr(Wc), _lib.ptr(ws.wmin_key), st))
         _lib.check(lib.cdw_weight_stats(_lib.ptr(W), n, -1.0, _lib.ptr(ws.wmin_key), _lib.ptr(ws.stats), _lib.ptr(ws.buf), ws.bytes, st))
 
     def resample(kind):
@@ -366,10 +496,11 @@ def resampling_sweep(torch, kernels, _lib, n, A):
     ms_mul = t(lambda: resample(_lib.CDW_RESAMPLE_MULTINOMIAL))
     ms_g = t(gather)
     gb = lambda b, ms: b / (ms * 1e-3) / 1e9
-    return {"n": n, "weights_pass12_gbs": gb(n * 40.0, ms_stats), "scan_search_systematic_gbs": gb(n * (16.0 + 12.0), ms_sys),
-            "scan_search_multinomial_gbs": gb(n * (16.0 + 20.0), ms_mul), "gather_n": nP,
-            "gather_gbs": gb(nP * (2 * 2 * A * 16.0 + 4 + 16 + 8), ms_g), "ms": {"stats": ms_stats, "systematic": ms_sys, "multinomial": ms_mul, "gather": ms_g},
-            "bytes_model": "SURVEY.md 8(d): update+stats 40 B, scan 16 B, search 12-20 B, gather 2*(2*A*16)+28 B per particle"}
+    rates = {"ess_update_stats_gbs": gb(n * 24.0, ms_stats), "scan_search_systematic_gbs": gb(n * (16.0 + 12.0), ms_sys),
+             "scan_search_multinomial_gbs": gb(n * (16.0 + 20.0), ms_mul), "gather_gbs": gb(nP * (2 * 2 * A * 16.0 + 4 + 16 + 8), ms_g)}
+    return dict(n=n, gather_n=nP, **rates, frac_of_hbm_peak={k[:-4]: v / hbm_peak for k, v in rates.items()} if hbm_peak else None,
+                ms={"stats": ms_stats, "systematic": ms_sys, "multinomial": ms_mul, "gather": ms_g},
+                bytes_model="SURVEY.md 8(d), algorithmic: update+stats 24 B, scan 16 B, search 12 (systematic) / 20 (multinomial) B, gather 2*(2*A*16)+28 B per particle")
 
 
 def main():
@@ -378,6 +509,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--threshold", type=float, default=FLOOR_THRESHOLD, help="resample iff nESS <= threshold")
     ap.add_argument("--no-graph", action="store_true", help="run the anneal as individual launches instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

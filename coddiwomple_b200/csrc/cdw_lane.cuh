@@ -392,13 +392,13 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M, in
     return e;
 }
 
-// One out-of-line copy for callers with several call sites (the look-ahead kernel evaluates in part A and in part B): the body is
-// ~1.5 k SASS instructions, and the instruction cache is what an SM with four resident CTAs of this kernel runs out of first.
-// (-DCDW_ENERGY_INLINE builds the fully inlined variant for A/B timing.)
-#if defined(CDW_ENERGY_INLINE)
-CDW_HD double lane_energy_forces(const SysDev& s, const Tables& T, const LaneMem& M, int part) { return lane_energy<true>(s, T, M, part); }
-#else
+// The look-ahead kernel evaluates in part A and in part B.  Both call sites are inlined: an out-of-line copy (-DCDW_ENERGY_NOINLINE,
+// 1 k fewer SASS instructions) measured 17 % SLOWER on B200 (fluorobenzene, 1e5 replicas: 339 vs 289 us per iteration; the
+// 22-atom system, 1e4 replicas: 128 vs 110 us) — the call pins the table pointers and counts in local memory.
+#if defined(CDW_ENERGY_NOINLINE)
 CDW_NOINLINE_HD inline double lane_energy_forces(const SysDev& s, const Tables& T, const LaneMem& M, int part) { return lane_energy<true>(s, T, M, part); }
+#else
+CDW_HD double lane_energy_forces(const SysDev& s, const Tables& T, const LaneMem& M, int part) { return lane_energy<true>(s, T, M, part); }
 #endif
 
 // ------------------------------------------------------------------------------------------------ constraints

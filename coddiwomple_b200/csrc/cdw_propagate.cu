@@ -255,7 +255,8 @@ static int launch(const cdw_system* sys, PropArgs& a, LaunchKind kind, cudaStrea
     const long long need = (a.n + sh.R - 1) / sh.R, cap = (long long)sms * per_sm;
     // the look-ahead kernel runs one CTA per batch (CTAs retire continuously: the resampling kernel of the same iteration, on another
     // stream, finds room beside it); the others are persistent
-    int grid = (int)(ahead ? (need < (1ll << 30) ? need : (1ll << 30)) : (need < cap ? need : cap));
+    static const bool ahead_persistent = getenv("CDW_AHEAD_PERSISTENT") != nullptr;   // A/B switch
+    int grid = (int)(ahead && !ahead_persistent ? (need < (1ll << 30) ? need : (1ll << 30)) : (need < cap ? need : cap));
     void* args[] = {(void*)&sys->dev, (void*)&a, (void*)&sh};
     CDW_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(nthr), args, L.total, st));
     return CDW_OK;

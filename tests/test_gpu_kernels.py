@@ -278,7 +278,8 @@ def test_resample_statistics_are_exact_integer_sums(gpu, n, kind):
     hdr = ws.buf[:8].cpu().numpy()
     assert not hdr[[0, 1, 2, 3, 4, 7]].any()                 # accumulators and tickets back at rest
     q, k = resampling.fixed_point_weights(W_host)
-    assert int(hdr[5]) == k and int(hdr[6]) == int(q.sum(dtype=object)) == int(s[_lib.STAT_TOTAL])
+    total = int(q.sum(dtype=object))
+    assert int(hdr[5]) == k and int(hdr[6]) == total and s[_lib.STAT_TOTAL] == float(total)
 
 
 def test_weigh_resample_composes_the_weights_through_the_previous_ancestors(gpu):

@@ -27,14 +27,22 @@ else:
     frames = np.load(os.path.join(golden, "fluorobenzene_cache.npy"))
     x0 = frames[np.random.RandomState(3).randint(0, len(frames), P)]
 seq = ts.relative_alchemical_sequence(100)
-eng = SMCEngine(xml, P, seq, langevin=LangevinParameters(), seed=0, resample_seed=1, always_resample=("--always" in sys.argv))
+lookahead = "--sequential" not in sys.argv
+eng = SMCEngine(xml, P, seq, langevin=LangevinParameters(), seed=0, resample_seed=1, always_resample=("--always" in sys.argv), lookahead=lookahead)
 eng.initialize(x0)
 evs = []
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for t in range(1, iters + 1):
+    if t == 3:
+        t0.record()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); eng.step(t); e1.record()
     evs.append((e0, e1))
+eng.ensemble.join()
+t1.record()
 torch.cuda.synchronize()
 if "--time" in sys.argv:
-    print("iteration us:", " ".join(f"{1e3 * a.elapsed_time(b):.1f}" for a, b in evs))
-print("ok", system, P, eng.free_energy())
+    print("launch us:", " ".join(f"{1e3 * a.elapsed_time(b):.1f}" for a, b in evs))
+    if iters > 3:
+        print(f"{'look-ahead' if lookahead else 'sequential'} loop: {1e3 * t0.elapsed_time(t1) / (iters - 2):.1f} us per iteration (iterations 3..{iters}, resampling included)")
+print("ok", system, P, eng.free_energy(), "resampled at", eng.resampled_iterations())
