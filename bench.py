@@ -4,7 +4,8 @@
 Workload (BASELINE.json configs[2], the largest single-GPU configuration): perses-style vacuum ligand mutation — the
 benzene -> fluorobenzene hybrid of coddiwomple/data/perses_data (13 atoms), 10^5 particles per GPU drawn from the reference's
 lambda = 0 cache, the reference's alchemical protocol (coddiwomple/tests/legacy_tests.py:58-76) on 100 lambda states, 1 BAOAB step
-per lambda, multinomial resampling.  One "step" = one full anneal (99 SMC iterations over all particles).  Multi-GPU runs keep
+per lambda, multinomial resampling at EVERY iteration (the reference's observable=None mode: all 99 launches gather random
+ancestor rows, over NVLink on several GPUs).  One "step" = one full anneal (99 SMC iterations over all particles).  Multi-GPU runs keep
 10^5 particles PER GPU (weak scaling).  BASELINE configs[1] (10^4 x 22-atom AlanineDipeptideVacuum shape) is timed beside it and
 reported under "config2"; on 8 GPUs configs[3] (10^6 particles, BAOAB and Euler-Maruyama proposals) under "config4".
 
@@ -28,10 +29,12 @@ sys.path.insert(0, ROOT)
 
 N_PARTICLES = 100_000          # per GPU
 N_LAMBDA = 100
-FLOOR_THRESHOLD = 0.5          # vanilla_floor_threshold's default (coddiwomple/utils.py:67-72)
+FLOOR_THRESHOLD = -1.0         # < 0: resample at EVERY iteration — the reference's observable=None / threshold=None mode (resamplers.py:90-92).
+#                                With vanilla_floor_threshold's 0.5 (utils.py:67-72) this workload never resamples (min nESS over the anneal is
+#                                0.99995): the hard case is timed, the 0.5 case is reported beside it ("threshold_0.5")
 CPU_SAMPLE_PARTICLES = 10_000  # the CPU arm times a bounded sample of the same workload: this many of the 10^5 particles, all 100 lambda
 WORKLOAD = ("perses-style vacuum ligand mutation (benzene->fluorobenzene hybrid, 13 atoms, reference fixture), 1e5 particles/GPU, 100 lambda "
-            "(legacy_tests.py:58-76 protocol), 1 BAOAB step/lambda, multinomial resampling")
+            "(legacy_tests.py:58-76 protocol), 1 BAOAB step/lambda, multinomial resampling at every iteration (observable=None, resamplers.py:90-92)")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -141,7 +144,7 @@ def run_reference(args):
     times, fe = [], None
     for k in range(args.steps):
         t0 = time.perf_counter()
-        out = port.anneal(x0, seq, floor_threshold=FLOOR_THRESHOLD, seed=k, resample_seed=1000 + k)
+        out = port.anneal(x0, seq, floor_threshold=FLOOR_THRESHOLD, seed=k, resample_seed=1000 + k)   # (negative threshold: resample always)
         times.append(time.perf_counter() - t0)
         fe = out["free_energy"]
     value = P * (N_LAMBDA - 1) / float(np.mean(times))
@@ -203,11 +206,12 @@ def run_gpu(args):
     spec = spec_from_xml(xml)
     langevin = LangevinParameters(temperature=300.0, collision_rate=1.0, timestep=0.002, n_steps=1)
     thr = float(args.threshold)
+    always = thr < 0.0
     if world > 1:
         from coddiwomple_b200.parallel import ShardedSMCEngine
-        eng = ShardedSMCEngine(xml, P * world, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr)
+        eng = ShardedSMCEngine(xml, P * world, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr, always_resample=always)
     else:
-        eng = SMCEngine(xml, P, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr)
+        eng = SMCEngine(xml, P, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr, always_resample=always)
     x0_pinned = positions_to_rows(x0_host, device=None, pinned=True)
     x0_dev = x0_pinned.cuda()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
@@ -264,6 +268,20 @@ def run_gpu(args):
     fe = eng.free_energy()
     n_resampled = len(eng.resampled_iterations())
 
+    # ---- the same anneal with the reference's default rule (nESS <= 0.5: this workload then never resamples), for the record
+    thr_half = None
+    if always:
+        eng.threshold = 0.5
+        if use_graph:
+            if world == 1:
+                eng.load(x0_dev); eng.capture()
+            else:
+                eng.capture(x0_dev)
+        for _ in range(2):
+            anneal_resident()
+        ms_half = timed(anneal_resident, max(args.steps // 4, 3))
+        thr_half = {"ms_per_step": float(np.mean(ms_half)), "value": units_per_step / (np.mean(ms_half) * 1e-3), "resampled_iterations": len(eng.resampled_iterations())}
+
     # ---- parity probe (outside the timed region): the multi-GPU anneal against the single-GPU one, or on one GPU the look-ahead loop
     # against the sequential loop, bit for bit
     probe = parity_probe(torch, dist, world, rank, xml)
@@ -302,6 +320,7 @@ def run_gpu(args):
                 # both timed loops; per anneal: equip + (T - 1) x (look-ahead launch + weight compose + statistics + tile sums + tile scan [+ lookup]
                 # [+ peer barrier]) + final gather [+ its barrier]
                 "gpu_launches": int(args.steps * 2 * (1 + per_iter * (N_LAMBDA - 1) + (2 if world > 1 else 1))),
+                "threshold_0.5": thr_half,
                 "parity_probe": probe,
                 "roofline": {"bound": "fp64", "kernel": "smc_lookahead_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
@@ -504,12 +523,18 @@ def resampling_sweep(torch, kernels, _lib, n, A, hbm_peak):
 
 
 def main():
+    # a hang (a rank waiting for a peer that is gone) must not hold a GPU node until the caller's time limit: dump where every thread is
+    # and leave.  CDW_WATCHDOG_S overrides the limit (0 disables it).
+    import faulthandler
+    limit = int(os.environ.get("CDW_WATCHDOG_S", "1500"))
+    if limit > 0:
+        faulthandler.dump_traceback_later(limit, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--threshold", type=float, default=FLOOR_THRESHOLD, help="resample iff nESS <= threshold")
+    ap.add_argument("--threshold", type=float, default=FLOOR_THRESHOLD, help="resample iff nESS <= threshold (negative: at every iteration)")
     ap.add_argument("--no-graph", action="store_true", help="run the anneal as individual launches instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

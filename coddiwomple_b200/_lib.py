@@ -124,7 +124,7 @@ _SIGNATURES = {
     "cdw_gather_particles": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "cdw_gather_particles_peer": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "cdw_record_lineage": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
-    "cdw_peer_barrier": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "cdw_peer_barrier": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "cdw_fill_u64": (C.c_int, [_P, C.c_uint64, C.c_int64, _P]),
     "cdw_philox_uniforms": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, _P, _P]),
     "cdw_ipc_get_handle": (C.c_int, [_P, _P]),

@@ -592,7 +592,9 @@ CDW_HD void cta_load_rows(const SysDev& s, const PropArgs& a, unsigned char* sme
         }
     }
     // The rows are gathered (latency, not bandwidth, is the cost): on the device every component goes global -> shared
-    // with a 4-byte cp.async (LDGSTS), no register staging, so ALL of a thread's loads are in flight at once; one
+    // with a 4-byte cp.async (LDGSTS), no register staging, so ALL of a thread's loads are in flight at once (measured
+    // alternatives, profiles/r2_notes.md: a register-staged 16-byte load for rows that come over NVLink, +20-30 % per anneal on 2
+    // GPUs; lanes copying consecutive words of a row so that every sector is requested once, +4 % on one GPU, +9 % on two); one
     // wait_all before the CTA barrier.
     CDW_CTA_THREADS(tid, nt) {
         float* Fc = (float*)(smem + L.f);

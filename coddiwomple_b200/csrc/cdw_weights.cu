@@ -561,8 +561,11 @@ __global__ void philox_uniforms_kernel(unsigned long long seed, unsigned long lo
 // increment per call), so the launch carries no host-side constant and can be replayed from a CUDA graph; epochs only grow, the
 // flag arrays never need clearing.  The wait is bounded: after ~2 s it gives up and records the failure in *status (the caller
 // checks it; a hang would cost the whole node).
+// skip_if_zero_a / _b (may be NULL): device flags that are identical on every rank (the resampling decisions of the two previous
+// iterations); when both are given and zero the ancestors involved are the identity, no rank touches a peer's rows, and the wait
+// is skipped (the signal is still sent: epochs stay in step).
 __global__ void peer_barrier_kernel(unsigned long long* const* peer_flags, volatile unsigned long long* flags_local, int rank, int world,
-                                    unsigned long long* epoch_counter, int* status) {
+                                    unsigned long long* epoch_counter, int* status, const double* skip_if_zero_a, const double* skip_if_zero_b) {
     __shared__ unsigned long long epoch_sh;
     if (threadIdx.x == 0) {
         epoch_sh = *epoch_counter + 1ull;
@@ -579,6 +582,7 @@ __global__ void peer_barrier_kernel(unsigned long long* const* peer_flags, volat
         flags_local[rank] = epoch;
     }
     __threadfence_system();
+    if (skip_if_zero_a && skip_if_zero_b && *skip_if_zero_a == 0.0 && *skip_if_zero_b == 0.0) return;
     long long spins = 0;
     while (flags_local[r] < epoch) {
         __nanosleep(100);
@@ -772,10 +776,10 @@ extern "C" int cdw_record_lineage(const double* cum, const int32_t* label, const
 }
 
 extern "C" int cdw_peer_barrier(uint64_t* const* peer_flags, uint64_t* flags_local, int32_t rank, int32_t world, uint64_t* epoch_counter,
-                                int32_t* status, cdw_stream stream) {
+                                int32_t* status, const double* skip_if_zero_a, const double* skip_if_zero_b, cdw_stream stream) {
     CDW_REQUIRE(peer_flags && flags_local && epoch_counter && status && world > 0 && world <= 32 && rank >= 0 && rank < world, "bad argument");
     peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long* const*)peer_flags, (volatile unsigned long long*)flags_local, rank, world,
-                                                           (unsigned long long*)epoch_counter, status);
+                                                           (unsigned long long*)epoch_counter, status, skip_if_zero_a, skip_if_zero_b);
     CDW_CUDA(cudaGetLastError());
     return CDW_OK;
 }

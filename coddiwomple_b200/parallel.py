@@ -184,10 +184,17 @@ class ShardedSMCEngine:
     def beta(self):
         return 1.0 / self.langevin.kT
 
-    def peer_barrier(self):
-        """Every rank's launches so far (this stream) are complete before any rank continues (cdw_peer_barrier; bounded wait)."""
+    def peer_barrier(self, t=None):
+        """Every rank's launches so far (this stream) are complete before any rank continues (cdw_peer_barrier; bounded wait).
+        In front of the launch of iteration t the wait is skipped on the device when neither iteration t - 1 nor t - 2 resampled
+        (all ancestors involved are the identity: nobody touches a peer's rows)."""
+        a = b = None
+        if t is not None and t >= 2:
+            a = self.stats[t - 1, _lib.STAT_RESAMPLE:]
+            b = self.stats[t - 2, _lib.STAT_RESAMPLE:]   # (row 0 is never written: zero, the initial ancestors are the identity)
         _lib.check(self.lib.cdw_peer_barrier(_lib.ptr(self._peer_flags), C.c_void_p(self._flags.ptr.value), self.rank, self.world,
-                                            _lib.ptr(self._epoch_counter), _lib.ptr(self._barrier_status), _lib.current_stream()), "cdw_peer_barrier")
+                                            _lib.ptr(self._epoch_counter), _lib.ptr(self._barrier_status), _lib.ptr(a), _lib.ptr(b),
+                                            _lib.current_stream()), "cdw_peer_barrier")
 
     def check_barriers(self):
         if int(self._barrier_status.item()) != 0:
@@ -262,7 +269,7 @@ class ShardedSMCEngine:
             main.wait_event(self._resampled)
         # the rows this launch gathers were written by the peers' launches of iteration t - 1, and the buffer it writes is the one the
         # peers' launches of iteration t - 1 read: both need every rank to be through iteration t - 1
-        self.peer_barrier()
+        self.peer_barrier(t)
         c, n = self.cur, 1 - self.cur
         prm = self.langevin.as_struct(_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
         lam_next = self.lam[t + 1] if t + 1 < self.T else None
@@ -394,7 +401,11 @@ class ShardedSMCEngine:
         return [t for t in range(1, self.T) if s[t] != 0.0]
 
     def close(self):
-        """Unmap the peers' buffers, then (after every rank has done so) free this rank's own."""
+        """Drop the captured graph (NCCL refuses to tear a communicator down while a graph that holds its collectives is alive:
+        destroy_process_group then blocks for ever), unmap the peers' buffers, then (after every rank has done so) free this rank's own."""
+        import gc
+        self.graph = None
+        gc.collect()
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         for ptr in self._opened:

@@ -329,9 +329,11 @@ CDW_API int cdw_record_lineage(const double* cum, const int32_t* label, const in
  * peer_flags: device array of `world` base pointers to the ranks' flag arrays (uint64[world] each, zero-initialised);
  * *epoch_counter (device, zero-initialised, private to the rank) is incremented by the launch itself, so the call can be
  * captured in a CUDA graph and replayed; every rank must call it the same number of times.  *status is set to 1 if a peer did
- * not show up within ~2 s (the wait is bounded). */
+ * not show up within ~2 s (the wait is bounded).  skip_if_zero_a / _b (device, may be NULL): when both are given and 0.0 the wait
+ * is skipped (the signal is not) — pass the CDW_STAT_RESAMPLE entries of the two previous iterations, which are identical on every
+ * rank: if neither resampled, every ancestor is the identity and no rank reads or overwrites rows a peer still needs. */
 CDW_API int cdw_peer_barrier(uint64_t* const* peer_flags, uint64_t* flags_local, int32_t rank, int32_t world, uint64_t* epoch_counter,
-                             int32_t* status, cdw_stream stream);
+                             int32_t* status, const double* skip_if_zero_a, const double* skip_if_zero_b, cdw_stream stream);
 
 /* utilities */
 CDW_API int cdw_fill_u64(uint64_t* ptr, uint64_t value, int64_t n, cdw_stream stream);

@@ -20,6 +20,8 @@ from coddiwomple_b200.system import load_xml  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("CDW_WATCHDOG_S", "600")), exit=True)   # a hang must not hold the GPU node
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))

@@ -103,7 +103,7 @@ def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
         "cdw_smc_lookahead": (none,) * 7 + (4,) + (none,) * 4 + (ctypes.byref(prm), 0, 0, 0) + (none,) * 5,
         "cdw_smc_lookahead_sharded": (none,) * 5 + (2, 2) + (none,) * 3 + (4,) + (none,) * 3 + (ctypes.byref(prm), 0, 0, 0) + (none,) * 5,
         "cdw_smc_weigh_resample": (0, none, none, 4, 0.5, none, 0, 0) + (none,) * 8 + (0, none),
-        "cdw_peer_barrier": (none, none, 0, 2, none, none, none),
+        "cdw_peer_barrier": (none, none, 0, 2, none, none, none, none, none),
         "cdw_record_lineage": (none,) * 5 + (4, none),
         "cdw_smc_resample": (0, none, 4, 0.5, none, 0, 0) + (none,) * 7 + (0, none),
         "cdw_weight_stats": (none, 4, 0.5, none, none, none, 0, none),
