@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("CDW_LIB") or os.path.join(HERE, "libcdw_b200.so")  # 
 CDW_FLAG_RANDOMIZE_VELOCITIES = 1
 CDW_FLAG_TRACK_WORKS = 2
 CDW_FLAG_ULA = 4
+CDW_STEP_V, CDW_STEP_R, CDW_STEP_O, CDW_STEP_OPEN, CDW_STEP_CLOSE = 1, 2, 3, 4, 5
 CDW_RESAMPLE_MULTINOMIAL = 0
 CDW_RESAMPLE_SYSTEMATIC = 1
 STAT_WMIN, STAT_SUM_E, STAT_SUM_E2, STAT_NESS, STAT_MEAN, STAT_RESAMPLE, STAT_TOTAL, STAT_NNAN = range(8)
@@ -39,7 +40,7 @@ class SystemDesc(C.Structure):
 class LangevinParams(C.Structure):
     """struct cdw_langevin_params (include/cdw.h)."""
     _fields_ = [("dt", C.c_double), ("gamma", C.c_double), ("kT", C.c_double), ("constraint_tol", C.c_double),
-                ("n_steps", C.c_int32), ("flags", C.c_uint32)]
+                ("n_steps", C.c_int32), ("flags", C.c_uint32), ("splitting", C.c_uint64), ("trial_counts", C.c_void_p)]
 
 
 class StaticCache(C.Structure):
@@ -98,6 +99,9 @@ _SIGNATURES = {
     "cdw_system_destroy": (C.c_int, [_P]),
     "cdw_system_register_protocol": (C.c_int, [_P, _P, C.c_int32, C.c_double, _P]),
     "cdw_system_clear_protocol": (C.c_int, [_P]),
+    "cdw_system_set_team": (C.c_int, [_P, C.c_int32]),
+    "cdw_system_team": (C.c_int, [_P]),
+    "cdw_system_smem_bytes": (C.c_size_t, [_P, C.c_int32]),
     "cdw_system_n_atoms": (C.c_int, [_P]),
     "cdw_system_n_lambda": (C.c_int, [_P]),
     "cdw_reduced_potential": (C.c_int, [_P, _P, C.c_int64, _P, C.c_double, _P, _P]),

@@ -40,4 +40,5 @@ struct cdw_system {
     double proto_kT = 0.0;
     unsigned char* proto_tables = nullptr;
     size_t proto_stride = 0;
+    int team = 0;        // lanes per replica pinned by cdw_system_set_team (0: chosen from the system)
 };

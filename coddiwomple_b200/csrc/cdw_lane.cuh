@@ -80,12 +80,13 @@ constexpr int kR = 1;  // host harness: one replica at a time
 struct Layout {
     size_t lam, nbeff, inv_m, sig_v, bonds, angles, torsions, pairs, exts, cl_start, cons_atoms, cons_d2, cl_coef_start, cl_coef;  // CTA-shared tables
     size_t x, v, f, r0, src, bad;                                                                                                  // [element][replica]
+    size_t xo, vo;                                                                                                                 // Metropolised programs: state at "{"
     size_t total;
 };
 
 CDW_HD size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
-CDW_HD Layout make_layout(const SysDev& s, bool forces, int R, int T) {  // R: kR on the device, 1 on the host
+CDW_HD Layout make_layout(const SysDev& s, bool forces, int R, int T, bool metro = false) {  // R: kR on the device, 1 on the host
     Layout L;
     size_t o = 0;
     const int A = s.n_atoms;
@@ -113,6 +114,11 @@ CDW_HD Layout make_layout(const SysDev& s, bool forces, int R, int T) {  // R: k
         L.src = o; o = align16(o + sizeof(long long) * R);
         L.bad = o; o = align16(o + sizeof(int) * R);
     }
+    L.xo = L.vo = o;
+    if (forces && metro) {
+        L.xo = o; o = align16(o + col * 3 * A);
+        L.vo = o; o = align16(o + col * 3 * A);
+    }
     L.total = o;
     return L;
 }
@@ -125,6 +131,7 @@ struct Tables {  // pointers into the CTA-shared tables
 
 struct LaneMem {  // this thread's view of its replica's columns
     float* x; float* v; float* f; float* r0;
+    float* xo; float* vo;  // Metropolised programs only
     long long* src; int* bad;
     int rid;           // this replica's column (0 .. kR-1)
     int T, tl, sw;     // team size, lane within the team, bank rotation (32 / T, 0 on the host)
@@ -145,6 +152,7 @@ CDW_HD LaneMem lane_pointers(const Layout& L, unsigned char* smem, int T, int ti
     LaneMem M;
     M.x = (float*)(smem + L.x); M.v = (float*)(smem + L.v); M.f = (float*)(smem + L.f); M.r0 = (float*)(smem + L.r0);
     M.src = (long long*)(smem + L.src); M.bad = (int*)(smem + L.bad);
+    M.xo = (float*)(smem + L.xo); M.vo = (float*)(smem + L.vo);
     M.T = T; M.rid = tid / T; M.tl = tid - M.rid * T; M.sw = kR > 1 ? 32 / T : 0;
     M.mask = 0xffffffffu;
     return M;
@@ -556,6 +564,8 @@ struct PropArgs {
     // inc_next_out[p] = u_{t+1}(x_t) - u_t(x_t), the incremental work of the NEXT iteration (distribution_factories.py:124-129)
     const double* lambda_next; const unsigned char* tables_next; double* inc_next_out;
     int have_next;  // part B runs (lambda_next may still be NULL for a system without global parameters)
+    // programmable splitting (cdw_langevin_params.splitting != 0, lane_step_program): 4 bits per sub-step, CDW_STEP_*; 0 ends the program
+    unsigned long long program; int* trial_counts;  // [P][2] (trials, accepted) of the Metropolised block, may be NULL
 };
 
 // where row `src` (a global particle id when the run is sharded) lives
@@ -849,6 +859,121 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
             if (bad && cached_open) us_keep = a.peer_pos ? a.peer_us[src / a.n_per_rank][src % a.n_per_rank] : a.us_in[src];
             a.us_out[p] = us_keep;
         }
+    }
+    return ordered_key(w);
+}
+
+// ------------------------------------------------------------------------------------------------ programmable splitting
+// OMMLI builds its integrator from a splitting string (openmm/integrators.py:207-217, 363-425): any sequence of R, V, O and at most
+// one Metropolised block "{ ... }" that must hold every R and V (openmm/integrators.py:241-276, 427-444).  This body interprets such
+// a program (CDW_STEP_* codes, 4 bits each) with the reference's bookkeeping:
+//   V, R, O   as in lane_step; forces / energy are re-evaluated lazily, when a V or a work increment needs them at moved positions
+//             (OpenMM's `f` and `energy`); shadow_work += dKE (V), d(KE + PE) (R); proposal_work -= dKE (O)
+//   {         x_old = x, v_old = v                                                                   (:427-430)
+//   }         accept iff exp(-shadow_work / kT) >= uniform; else x = x_old, v = -v_old; shadow_work = 0   (:432-444)
+// "V R O R V" gives the same trajectory as lane_step (one extra evaluation per step for the R bookkeeping, as with TRACK_WORKS).
+#define CDW_KIND_METROPOLIS 3u   // (CDW_STEP_*: include/cdw.h)
+
+CDW_HD unsigned long long lane_step_program(const SysDev& s, const Tables& T, const LaneMem& M, const PropArgs& a, long long p) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms;
+    const long long src = M.src[rid];
+    const unsigned long long gid = (unsigned long long)(a.gid0 + p);
+    const double h_r = a.dt, inv_kT = 1.0 / a.kT;
+    int n_v = 0, n_r = 0, n_o = 0;
+    for (unsigned long long w = a.program; w & 15ull; w >>= 4) {
+        const unsigned tok = (unsigned)(w & 15ull);
+        n_v += tok == CDW_STEP_V; n_r += tok == CDW_STEP_R; n_o += tok == CDW_STEP_O;
+    }
+    // every kind of sub-step shares the time step equally (openmm/integrators.py:300, 320, 158-159: dt / n_R, dt / n_V, dt / n_O)
+    const double hv = n_v ? a.dt / n_v : 0.0, hr = n_r ? h_r / n_r : 0.0, ho = n_o ? a.dt / n_o : 0.0;
+    const double ca = exp(-a.gamma * ho), cb = sqrt(1.0 - exp(-2.0 * a.gamma * ho));
+    double aux = 0.0;
+    int label = (int)src;
+    if (a.aux_in) aux = a.aux_in[src];
+    if (a.label_in) label = a.label_in[src];
+    // opening evaluation: the incremental work of an MCMC move (distribution_factories.py:98-131)
+    double U = lane_energy<true>(s, T, M);
+    bool fvalid = true;
+    const double u_first = U;
+    const double inc = u_first * inv_kT + aux, w = (a.cum_in ? a.cum_in[p] : 0.0) + inc;
+    if (tl == 0) {
+        if (a.inc_out) a.inc_out[p] = inc;
+        if (a.w_out) a.w_out[p] = w;
+    }
+    if (a.n_steps > 0 && (a.flags & CDW_FLAG_RANDOMIZE_VELOCITIES)) {
+        lane_noise(s, T, M, 0.0, 1.0, a.seed, gid, (uint32_t)a.step0, CDW_KIND_MAXWELL_BOLTZMANN);
+        CDW_TEAM_SYNC(M);
+        if (s.n_cons) lane_rattle(s, T, M, a.tol);
+    }
+    double shadow = 0.0, proposal = 0.0;
+    int trials = 0, accepted = 0;
+    for (int st = 0; st < a.n_steps; ++st) {
+        int o_count = 0;
+        for (unsigned long long prog = a.program; prog & 15ull; prog >>= 4) {
+            const unsigned tok = (unsigned)(prog & 15ull);
+            if (tok == CDW_STEP_OPEN) {
+                for (int at = tl; at < A; at += T_) {
+                    const int b = CDW_BASE(at);
+                    M.xo[b] = M.x[b]; M.xo[b + kR] = M.x[b + kR]; M.xo[b + 2 * kR] = M.x[b + 2 * kR];
+                    M.vo[b] = M.v[b]; M.vo[b + kR] = M.v[b + kR]; M.vo[b + 2 * kR] = M.v[b + 2 * kR];
+                }
+                CDW_TEAM_SYNC(M);
+                continue;
+            }
+            if (tok == CDW_STEP_CLOSE) {
+                u4 c;
+                c.x = (uint32_t)gid; c.y = (uint32_t)(gid >> 32); c.z = (uint32_t)(a.step0 + st); c.w = CDW_KIND_METROPOLIS << 24;
+                const u4 r = philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                const double u = (double)uniform24(r.x);
+                const bool accept = exp(-shadow * inv_kT) - u >= 0.0;   // step(exp(-shadow_work / kT) - uniform); a NaN shadow work rejects
+                ++trials;
+                if (accept) ++accepted;
+                else {
+                    for (int at = tl; at < A; at += T_) {
+                        const int b = CDW_BASE(at);
+                        M.x[b] = M.xo[b]; M.x[b + kR] = M.xo[b + kR]; M.x[b + 2 * kR] = M.xo[b + 2 * kR];
+                        M.v[b] = -M.vo[b]; M.v[b + kR] = -M.vo[b + kR]; M.v[b + 2 * kR] = -M.vo[b + 2 * kR];
+                    }
+                    fvalid = false;
+                }
+                shadow = 0.0;
+                CDW_TEAM_SYNC(M);
+                continue;
+            }
+            if (tok != CDW_STEP_O && !fvalid) {   // V needs the forces, R the energy, at the current positions
+                U = lane_energy<true>(s, T, M);
+                fvalid = true;
+            }
+            const double ke_before = lane_kinetic(s, T, M);
+            if (tok == CDW_STEP_V) lane_kick(s, T, M, hv);
+            else if (tok == CDW_STEP_R) lane_drift(s, T, M, hr, a.tol);
+            else lane_noise(s, T, M, ca, cb, a.seed, gid, (uint32_t)(a.step0 + st), CDW_KIND_O_STEP | ((uint32_t)o_count++ << 4));
+            CDW_TEAM_SYNC(M);
+            if (s.n_cons) lane_rattle(s, T, M, a.tol);
+            const double ke_after = lane_kinetic(s, T, M);
+            if (tok == CDW_STEP_V) shadow += ke_after - ke_before;
+            else if (tok == CDW_STEP_O) proposal -= ke_after - ke_before;
+            else {
+                const double U_new = lane_energy<true>(s, T, M);
+                shadow += (ke_after + U_new) - (ke_before + U);
+                U = U_new;
+            }
+        }
+    }
+    if (!fvalid) U = lane_energy<true>(s, T, M);
+    const double u_last = U;
+    const bool bad = a.n_steps > 0 && !(u_last - u_last == 0.0);
+    if (tl == 0) {
+        M.bad[rid] = bad ? 1 : 0;
+        if (a.aux_out) a.aux_out[p] = -(bad ? u_first : u_last) * inv_kT;
+        if (a.label_out) a.label_out[p] = label;
+        if (a.u_first_out) a.u_first_out[p] = u_first * inv_kT;
+        if (a.u_last_out) a.u_last_out[p] = u_last * inv_kT;
+        if (a.shadow_out) a.shadow_out[p] = shadow * inv_kT;
+        if (a.proposal_out) a.proposal_out[p] = proposal * inv_kT;
+        if (a.nan_flags) a.nan_flags[p] = bad ? 1 : 0;
+        if (a.trial_counts) { a.trial_counts[2 * p] = trials; a.trial_counts[2 * p + 1] = accepted; }
     }
     return ordered_key(w);
 }

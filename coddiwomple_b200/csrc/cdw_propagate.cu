@@ -22,7 +22,8 @@ namespace cdw {
 constexpr int kMaxThreads = 256;
 
 struct Shape {
-    int R, T;  // replicas staged per CTA, lanes per replica; blockDim = R * T
+    int R, T;   // replicas staged per CTA, lanes per replica; blockDim = R * T
+    int metro;  // the program has a Metropolised block: the layout holds the state saved at "{"
 };
 
 __global__ void __launch_bounds__(kMaxThreads) reduced_potential_kernel(SysDev s, PropArgs a, Shape sh) {
@@ -90,13 +91,16 @@ __device__ __forceinline__ void wait_tables(unsigned long long* bar, unsigned pa
 #ifndef CDW_MINBLOCKS_SMALL
 #define CDW_MINBLOCKS_SMALL 3
 #endif
+#ifndef CDW_MINBLOCKS_DENSE
+#define CDW_MINBLOCKS_DENSE 4
+#endif
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, PropArgs a, Shape sh) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long cta_min[MAXT / 32];
     __shared__ __align__(8) unsigned long long table_bar;
     const int T_ = sh.T, sw = 32 / T_;
-    const Layout L = make_layout(s, true, kR, T_);
+    const Layout L = make_layout(s, true, kR, T_, sh.metro != 0);
     const Tables T = table_pointers(L, smem);
     bool tables_in_flight = false;
     if (a.tables) {
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
         const bool valid = M.rid < count;
         M.mask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            const unsigned long long key = lane_step(s, T, M, a, p0 + M.rid);
+            const unsigned long long key = a.program ? lane_step_program(s, T, M, a, p0 + M.rid) : lane_step(s, T, M, a, p0 + M.rid);
             my_min = key < my_min ? key : my_min;
         }
         __syncthreads();
@@ -191,18 +195,23 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_lookahead_kernel(SysDev s, Pro
 
 // Launch shape.  T lanes per replica (power of two), kR = 32 replica columns per CTA (blockDim = 32 T <= 256, so T <= 8).
 // CDW_TEAM overrides the choice (tuning).
-static Shape pick_shape(const SysDev& dev, bool forces, long long n, int sms) {
+static int default_team(const SysDev& dev) { return dev.n_atoms >= 8 ? 4 : (dev.n_atoms >= 4 ? 2 : 1); }
+
+static Shape pick_shape(const SysDev& dev, bool forces, long long n, int sms, int pinned = 0) {
     static const char* env = getenv("CDW_TEAM");
     Shape sh;
     sh.R = 32;
+    sh.metro = 0;
     if (env && atoi(env) > 0) {
         sh.T = atoi(env);
+    } else if (pinned > 0) {
+        sh.T = pinned;
     } else {
         // measured on B200 (tools/tune_step.py): T = 4 is the sweet spot for 13-22 atom systems (fewer lanes
         // starve the SM of resident warps, more lanes pay for force copies and idle tails); tiny systems have nothing to
         // split.  The choice depends on the SYSTEM only, never on the batch size: the summation order of energies and
         // forces follows the team size, and results must not change with how particles are sharded over GPUs.
-        sh.T = dev.n_atoms >= 8 ? 4 : (dev.n_atoms >= 4 ? 2 : 1);
+        sh.T = default_team(dev);
     }
     if (sh.T > 8) sh.T = 8;
     while (sh.T > 1 && make_layout(dev, forces, sh.R, sh.T).total > 227 * 1024) sh.T /= 2;
@@ -231,17 +240,20 @@ static int launch(const cdw_system* sys, PropArgs& a, LaunchKind kind, cudaStrea
     int devid = 0, sms = 148;
     cudaGetDevice(&devid);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
-    const Shape sh = pick_shape(sys->dev, forces, a.n, sms);
+    Shape sh = pick_shape(sys->dev, forces, a.n, sms, forces ? sys->team : 0);
+    for (unsigned long long w = a.program; w & 15ull; w >>= 4) sh.metro |= (w & 15ull) == CDW_STEP_OPEN;
     const int nthr = sh.R * sh.T;
-    const Layout L = make_layout(sys->dev, forces, sh.R, sh.T);
+    const Layout L = make_layout(sys->dev, forces, sh.R, sh.T, sh.metro != 0);
     const bool small = nthr <= 128;
     // 128-thread CTAs come in two register budgets: <= 170 registers (three CTAs per SM: enough for one wave of a
     // 10^4 batch, fewer spills) or <= 128 registers (four CTAs per SM) when shared memory leaves room for a fourth CTA
     // and the batch is large enough to use it (measured: 13-atom system, 10^5 replicas: 333 us vs 375 us)
-    const bool dense = small && L.total * 4 <= 227 * 1024 && (a.n + kR - 1) / kR >= (long long)sms * 4;
+    // (64-thread CTAs — teams of 2 — are limited by shared memory long before the 142-register variant is: they keep it.  Measured,
+    // fluorobenzene hybrid, 1e5 replicas, T = 2: 271 us per iteration with 142 registers, 295 us with 96.)
+    const bool dense = nthr == 128 && L.total * CDW_MINBLOCKS_DENSE <= 227 * 1024 && (a.n + kR - 1) / kR >= (long long)sms * 4;
     const void* k = !forces ? (const void*)reduced_potential_kernel
                   : ahead ? (!small ? (const void*)smc_lookahead_kernel<256, 2>
-                                    : (dense ? (const void*)smc_lookahead_kernel<128, 4> : (const void*)smc_lookahead_kernel<128, CDW_MINBLOCKS_SMALL>))
+                                    : (dense ? (const void*)smc_lookahead_kernel<128, CDW_MINBLOCKS_DENSE> : (const void*)smc_lookahead_kernel<128, CDW_MINBLOCKS_SMALL>))
                           : (!small ? (const void*)smc_propagate_kernel<256, 2>
                                     : (dense ? (const void*)smc_propagate_kernel<128, 4> : (const void*)smc_propagate_kernel<128, CDW_MINBLOCKS_SMALL>));
     if (L.total > 227 * 1024) {
@@ -303,6 +315,21 @@ extern "C" int cdw_system_register_protocol(cdw_system* sys, const double* lambd
     sys->proto_tables = buf; sys->proto_stride = L.x; sys->proto_lambda = lambda_rows; sys->proto_rows = n_rows; sys->proto_kT = kT;
     return CDW_OK;
 }
+
+// Lanes per replica.  The summation order of energies and forces follows the team size, so results are bitwise reproducible only
+// between runs that use the same one: the library's own choice depends on the system alone (never on the batch size or on how a
+// batch is sharded); a caller that knows the size of the WHOLE ensemble can pin a better one for large ensembles.
+extern "C" int cdw_system_set_team(cdw_system* sys, int32_t lanes) {
+    CDW_REQUIRE(sys && (lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8), "lanes must be 0 (automatic), 1, 2, 4 or 8");
+    if (lanes > 0) CDW_REQUIRE(make_layout(sys->dev, true, kR, lanes).total <= 227 * 1024, "this team size does not fit shared memory");
+    sys->team = lanes;
+    return CDW_OK;
+}
+
+extern "C" int cdw_system_team(const cdw_system* sys) { return sys ? (sys->team > 0 ? sys->team : default_team(sys->dev)) : CDW_EINVAL; }
+
+// shared memory per CTA (32 replicas) of the propagate kernels for a team size: what residency, hence the best team size, depends on
+extern "C" size_t cdw_system_smem_bytes(const cdw_system* sys, int32_t lanes) { return sys && lanes > 0 ? make_layout(sys->dev, true, kR, lanes).total : 0; }
 
 extern "C" int cdw_system_clear_protocol(cdw_system* sys) {
     CDW_REQUIRE(sys, "null argument");
@@ -371,6 +398,19 @@ extern "C" int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
+    if (prm->splitting) {
+        CDW_REQUIRE(!ula && !cache, "a splitting program cannot be combined with the Euler-Maruyama proposal or a static-term cache");
+        int depth = 0, n = 0;
+        for (unsigned long long w = prm->splitting; w & 15ull; w >>= 4, ++n) {
+            const unsigned tok = (unsigned)(w & 15ull);
+            CDW_REQUIRE(tok >= CDW_STEP_V && tok <= CDW_STEP_CLOSE, "unknown sub-step code in cdw_langevin_params.splitting");
+            depth += tok == CDW_STEP_OPEN ? 1 : (tok == CDW_STEP_CLOSE ? -1 : 0);
+            CDW_REQUIRE(depth == 0 || depth == 1, "Metropolised blocks cannot be nested and must be opened before they are closed");
+            // shadow-work generating steps outside the block are rejected like the reference does (openmm/integrators.py:248-276)
+        }
+        CDW_REQUIRE(depth == 0, "the Metropolised block is not closed");
+        a.program = prm->splitting; a.trial_counts = prm->trial_counts;
+    }
     if (int rc = apply_cache(a, cache, false, anc != nullptr)) return rc;
     return launch(sys, a, LAUNCH_PROPAGATE, (cudaStream_t)stream);
 }

@@ -38,6 +38,17 @@ class DeviceSystem:
         self.n_atoms = self.spec.n_atoms
         self.n_lambda = self.spec.n_lambda
 
+    def choose_team(self, n_particles_total):
+        """Pin the lanes per replica from the size of the WHOLE ensemble (all ranks of a sharded run pass the same number, so a sharded
+        run and a single-GPU run of the same ensemble still agree bit for bit).  Ensembles that fill the GPU several times over run
+        teams of 2 when seven 64-thread CTAs of them fit an SM (measured, fluorobenzene hybrid, 1e5 replicas: 271 us per iteration
+        against 304 us with teams of 4; the 22-atom system only fits three such CTAs and stays at 4: 745 against 984 us)."""
+        team = 0
+        if self.n_atoms >= 8 and int(n_particles_total) >= 65536 and 7 * int(self.lib.cdw_system_smem_bytes(self.handle, 2)) <= 227 * 1024:
+            team = 2
+        _lib.check(self.lib.cdw_system_set_team(self.handle, team), "cdw_system_set_team")
+        return int(self.lib.cdw_system_team(self.handle))
+
     def lambda_table(self, parameter_sequence, device="cuda"):
         """[T][n_lambda] fp64 device table for a list of {name: value} dicts (reference: parameter_sequence)."""
         rows = [self.spec.lambda_vector(p) for p in parameter_sequence]
@@ -93,20 +104,37 @@ def positions_to_rows(positions, device="cuda", pinned=False):
 class LangevinParameters:
     """OMMLI's numbers in MD units (coddiwomple/openmm/integrators.py:75-131, 147-169)."""
 
-    def __init__(self, temperature=300.0, collision_rate=1.0, timestep=0.002, constraint_tolerance=1e-6, n_steps=1):
+    STEP_CODES = {"V": _lib.CDW_STEP_V, "R": _lib.CDW_STEP_R, "O": _lib.CDW_STEP_O, "{": _lib.CDW_STEP_OPEN, "}": _lib.CDW_STEP_CLOSE}
+
+    def __init__(self, temperature=300.0, collision_rate=1.0, timestep=0.002, constraint_tolerance=1e-6, n_steps=1, splitting="V R O R V"):
         self.temperature = float(temperature)
         self.collision_rate = float(collision_rate)
         self.timestep = float(timestep)
         self.constraint_tolerance = float(constraint_tolerance)
         self.n_steps = int(n_steps)
+        self.splitting_word = self.encode_splitting(splitting)
+
+    @classmethod
+    def encode_splitting(cls, splitting):
+        """The splitting string as cdw_langevin_params.splitting (4 bits per sub-step); 0 for "V R O R V", which has its own fused body."""
+        toks = splitting.upper().split()
+        if toks == ["V", "R", "O", "R", "V"]:
+            return 0
+        if len(toks) > 15:
+            raise ValueError("a splitting may hold at most 15 sub-steps")
+        word = 0
+        for k, tok in enumerate(toks):
+            word |= cls.STEP_CODES[tok] << (4 * k)
+        return word
 
     @property
     def kT(self):
         return kT_in_md_units(self.temperature)
 
-    def as_struct(self, flags=0, n_steps=None):
+    def as_struct(self, flags=0, n_steps=None, trial_counts=None):
         return _lib.LangevinParams(self.timestep, self.collision_rate, self.kT, self.constraint_tolerance,
-                                   self.n_steps if n_steps is None else int(n_steps), int(flags))
+                                   self.n_steps if n_steps is None else int(n_steps), int(flags), int(getattr(self, "splitting_word", 0)),
+                                   None if trial_counts is None else trial_counts.data_ptr())
 
 
 class ParticleEnsemble:
@@ -325,7 +353,7 @@ class ParticleEnsemble:
             flags = _lib.CDW_FLAG_ULA
         prm = langevin.as_struct(flags)
         o = outputs or {}
-        use_cache = self.static_cache and not track_works and langevin.n_steps > 0
+        use_cache = self.static_cache and not track_works and langevin.n_steps > 0 and not getattr(langevin, "splitting_word", 0)
         if use_cache and not self.cache_valid:
             self.seed_static_cache(lam_row, langevin.kT)
             c, n = self.cur, 1 - self.cur
@@ -392,9 +420,11 @@ class SMCEngine:
         if proposal not in ("baoab", "ula"):
             raise ValueError("proposal must be 'baoab' (MCMC move, openmm/integrators.py:19-465) or 'ula' (Euler-Maruyama, :666-888)")
         self.proposal = proposal
-        self.lookahead = bool(lookahead) and proposal == "baoab"
+        # the look-ahead launch is the fused "V R O R V" body; other splittings (Metropolised blocks, ...) run the programmable one
+        self.lookahead = bool(lookahead) and proposal == "baoab" and not getattr(langevin, "splitting_word", 0)
         self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history, static_cache=static_cache)
         self.system = self.ensemble.system
+        self.team = self.system.choose_team(n_particles)
         self.langevin = langevin or LangevinParameters()
         self.parameter_sequence = list(parameter_sequence)
         self.T = len(self.parameter_sequence)

@@ -1,8 +1,9 @@
 """OpenMM Integrator module — `OMMLI` with the reference's constructor (coddiwomple/openmm/integrators.py:19-465).
 
 The reference builds a CustomIntegrator program from the splitting string; here the "V R O R V" (BAOAB) program is
-the fused K4 kernel, so the class only carries the numbers and the work accumulators.  Other splittings
-(Metropolised `{ }`, multiple-time-step, g-BAOAB) are out of scope (the reference itself raises on MTS, :412).
+the fused K4 kernel and any other string of V, R, O sub-steps with an optional Metropolised block `{ }` runs the kernel's
+programmable body, so the class only carries the numbers and the work accumulators.  Multiple-time-step splittings are
+refused (the reference itself raises on MTS, :412).
 """
 import numpy as np
 
@@ -11,14 +12,47 @@ from . import units
 
 
 class OMMLI(LangevinParameters):
+    """Langevin integrator from a splitting string of V, R, O sub-steps and at most one Metropolised block "{ ... }" that must hold
+    every R and V (openmm/integrators.py:207-276, 363-444).  "V R O R V" is the fused BAOAB body; other strings run the programmable
+    body (cdw_langevin_params.splitting).  Force-group (multiple-time-step) V steps are refused like the reference does (:412)."""
+
     def __init__(self, temperature=300.0, collision_rate=1.0, timestep=0.001, splitting="V R O R V", constraint_tolerance=1e-6, **kwargs):
-        if " ".join(splitting.upper().split()) != "V R O R V":
-            raise NotImplementedError(f"splitting {splitting!r}: only 'V R O R V' (BAOAB) is implemented by the fused kernel")
+        splitting = " ".join(splitting.upper().split())
+        self._sanity_check(splitting)
         super().__init__(temperature=units.strip(temperature), collision_rate=units.strip(collision_rate), timestep=units.strip(timestep),
-                         constraint_tolerance=constraint_tolerance)
+                         constraint_tolerance=constraint_tolerance, splitting=splitting)
         self._splitting = splitting
-        self._metropolized_integrator = False
+        self._metropolized_integrator = "{" in splitting
+        self.ntrials = self.naccept = self.nreject = 0
         self.reset()
+
+    @staticmethod
+    def _sanity_check(splitting):
+        """openmm/integrators.py:219-276: only R, V, O, { and }; one un-nested block; no shadow-work generating step outside it."""
+        toks = splitting.split()
+        for tok in toks:
+            if tok[0] == "V" and len(tok) > 1:
+                raise NotImplementedError("force group splitting is currently disabled")   # as the reference (integrators.py:412)
+            if tok not in ("V", "R", "O", "{", "}"):
+                raise ValueError(f"Invalid step name '{tok}' used; valid step names are R V O {{ }}")
+        if "{" in toks or "}" in toks:
+            if toks.count("{") != 1 or toks.count("}") != 1:
+                raise ValueError("There can only be one Metropolized region.")
+            lo, hi = toks.index("{"), toks.index("}")
+            if lo > hi or any(t in ("R", "V") for t in toks[:lo] + toks[hi + 1:]):
+                raise ValueError("Shadow work generating steps found outside the Metropolization block")
+
+    def record_trials(self, trial_counts):
+        """Add the (trials, accepted) pairs a launch returned to the integrator's counters (the reference's ntrials / naccept /
+        nreject globals, integrators.py:432-443)."""
+        t, a = int(trial_counts[..., 0].sum()), int(trial_counts[..., 1].sum())
+        self.ntrials += t
+        self.naccept += a
+        self.nreject += t - a
+
+    @property
+    def acceptance_rate(self):
+        return self.naccept / self.ntrials if self.ntrials else float("nan")
 
     # work accumulators, in kT (integrators.py:160-161, 200-205)
     def reset_proposal_work(self):

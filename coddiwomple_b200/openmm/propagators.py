@@ -68,7 +68,9 @@ class OMMBIP(Propagator):
                    nan=torch.zeros(P, dtype=torch.int32, device=d))
         flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if (randomize_velocities or self.reassign_velocities) else 0) | \
                 (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
-        prm = self.integrator.as_struct(flags, n_steps=n_steps)
+        trials = torch.zeros(P, 2, dtype=torch.int32, device=d) if getattr(self.integrator, "splitting_word", 0) else None
+        out["trials"] = trials
+        prm = self.integrator.as_struct(flags, n_steps=n_steps, trial_counts=trials)
         if gid0 is None:
             gid0 = self._gid_counter
         _lib.check(self.lib.cdw_baoab(self.pdf_state.device_system.handle, _lib.ptr(pos_rows), _lib.ptr(vel_rows), P, _lib.ptr(self._context_lambda),
@@ -98,6 +100,8 @@ class OMMBIP(Propagator):
             for k in sub:
                 out[k][bad] = sub[k]
             out["attempts"] = attempt + 1
+        if trials is not None and hasattr(self.integrator, "record_trials"):
+            self.integrator.record_trials(trials.cpu().numpy())
         return out
 
     def apply(self, particle_state, n_steps=1, reset_integrator=False, apply_pdf_to_context=False, returnable_key=None,

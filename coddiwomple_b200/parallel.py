@@ -109,6 +109,7 @@ class ShardedSMCEngine:
         self.system = system if isinstance(system, DeviceSystem) else DeviceSystem(system)
         self.lib = self.system.lib
         self.A = self.system.n_atoms
+        self.team = self.system.choose_team(self.P)   # from the GLOBAL ensemble size: the same on every rank and in a single-GPU run
         self.langevin = langevin or LangevinParameters()
         self.parameter_sequence = list(parameter_sequence)
         self.T = len(self.parameter_sequence)

@@ -110,7 +110,19 @@ typedef struct cdw_langevin_params {
     double constraint_tol;  /* relative distance tolerance (setConstraintTolerance) */
     int32_t n_steps;        /* integrator steps per call (OMMBIP.apply n_steps, default 1) */
     uint32_t flags;         /* CDW_FLAG_* */
+    /* Splitting program (OMMLI's `splitting` string, openmm/integrators.py:207-217, 363-425): 0 = "V R O R V"; otherwise one
+     * CDW_STEP_* code per sub-step, 4 bits each, first sub-step in the lowest bits, at most 15 sub-steps.  cdw_smc_propagate /
+     * cdw_baoab only; shadow and proposal works are always tracked.  A Metropolised block "{ ... }" accepts the sub-steps it holds
+     * iff exp(-shadow_work / kT) >= uniform, else restores x and flips v (openmm/integrators.py:427-444). */
+    uint64_t splitting;
+    int32_t* trial_counts;  /* device [P][2] (trials, accepted) of the Metropolised block, or NULL */
 } cdw_langevin_params;
+
+#define CDW_STEP_V 1u      /* v += (dt / n_V) f / m */
+#define CDW_STEP_R 2u      /* x += (dt / n_R) v, constraints */
+#define CDW_STEP_O 3u      /* Ornstein-Uhlenbeck over dt / n_O */
+#define CDW_STEP_OPEN 4u   /* "{" */
+#define CDW_STEP_CLOSE 5u  /* "}" */
 
 #define CDW_FLAG_RANDOMIZE_VELOCITIES 1u /* Context.setVelocitiesToTemperature before stepping (propagators.py:137-138) */
 #define CDW_FLAG_TRACK_WORKS 2u          /* accumulate shadow_work / proposal_work (integrators.py:315,336,350) */
@@ -153,6 +165,14 @@ CDW_API int cdw_system_destroy(cdw_system* sys);
  * be re-captured).  Enqueues on `stream`. */
 CDW_API int cdw_system_register_protocol(cdw_system* sys, const double* lambda_rows, int32_t n_rows, double kT, cdw_stream stream);
 CDW_API int cdw_system_clear_protocol(cdw_system* sys);
+/* Lanes of a warp that share one replica in the propagate kernels (1, 2, 4, 8; 0 = the library's choice, which depends on the
+ * system alone).  Energies and forces are summed in team order: runs are bitwise comparable only at equal team size, which is why
+ * the choice never follows the batch size or the sharding.  A caller that knows the size of the WHOLE ensemble may pin the team:
+ * small teams waste fewer lanes and suit ensembles that fill the GPU many times over, large teams shorten the per-replica
+ * dependency chain and suit ensembles of about one wave.  cdw_system_smem_bytes: shared memory per CTA of 32 replicas. */
+CDW_API int cdw_system_set_team(cdw_system* sys, int32_t lanes);
+CDW_API int cdw_system_team(const cdw_system* sys);
+CDW_API size_t cdw_system_smem_bytes(const cdw_system* sys, int32_t lanes);
 CDW_API int cdw_system_n_atoms(const cdw_system* sys);
 CDW_API int cdw_system_n_lambda(const cdw_system* sys);
 

@@ -183,3 +183,109 @@ def baoab(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed
         x[nan] = x0[nan]
         v[nan] = v0[nan]
     return dict(x=x, v=v, u_first=u_first, u_last=u_last, shadow_work=shadow, proposal_work=proposal, nan=nan)
+
+
+STEP_CODES = {"V": 1, "R": 2, "O": 3, "{": 4, "}": 5}
+KIND_METROPOLIS = 3
+
+
+def encode_splitting(splitting):
+    """'V R O R V' -> the 4-bit-per-sub-step program word of cdw_langevin_params.splitting (first sub-step in the lowest bits)."""
+    word = 0
+    for k, tok in enumerate(splitting.upper().split()):
+        word |= STEP_CODES[tok] << (4 * k)
+    return word
+
+
+def langevin_program(energy_forces, x, v, masses, constraints, dt, gamma, kT, n_steps, seed, gids, step0, splitting="V R O R V", tol=1e-6,
+                     randomize_velocities=False):
+    """n_steps of an arbitrary OMMLI splitting (openmm/integrators.py:207-217, 363-425), including ONE Metropolised block:
+
+        V: v += (dt / n_V) f / m        R: x += (dt / n_R) v (+ constraints)        O: v = a v + b sqrt(kT/m) xi over dt / n_O
+        shadow_work += dKE (V) / d(KE + PE) (R);  proposal_work -= dKE (O)                               (:315, 336, 350)
+        "{": x_old = x, v_old = v                                                                         (:427-430)
+        "}": accept iff exp(-shadow_work / kT) >= uniform, else x = x_old, v = -v_old; shadow_work = 0    (:432-444)
+
+    Forces and energies are re-evaluated lazily, when a V or a work increment needs them at moved positions (OpenMM's `f` / `energy`).
+    The uniform of the acceptance test is Philox(seed; gid, step, kind 3) like the Gaussian noise.
+    Returns dict(x, v, u_first, u_last, shadow_work, proposal_work, trials, accepted, nan)."""
+    toks = splitting.upper().split()
+    n_v, n_r, n_o = toks.count("V"), toks.count("R"), toks.count("O")
+    x0 = r32(x)
+    x = x0.copy()
+    masses = np.asarray(masses, dtype=np.float64)
+    inv_m = 1.0 / masses
+    P, A = x.shape[0], x.shape[1]
+    v0 = r32(v)
+    if randomize_velocities and n_steps > 0:
+        v = maxwell_boltzmann(x, masses, constraints, kT, seed, gids, step0, tol)
+    v = r32(v)
+    hv, hr, ho = (dt / n_v if n_v else 0.0), (dt / n_r if n_r else 0.0), (dt / n_o if n_o else 0.0)
+    a, b = np.exp(-gamma * ho), np.sqrt(1.0 - np.exp(-2.0 * gamma * ho))
+    sig = np.sqrt(kT / masses)[None, :, None]
+    shadow, proposal = np.zeros(P), np.zeros(P)
+    trials, accepted = np.zeros(P, dtype=np.int64), np.zeros(P, dtype=np.int64)
+    U, F = energy_forces(x)
+    fvalid = np.ones(P, dtype=bool)
+    u_first = U.copy()
+    x_old, v_old = x.copy(), v.copy()
+
+    def refresh():
+        nonlocal U, F
+        if not fvalid.all():
+            Un, Fn = energy_forces(x)
+            U = np.where(fvalid, U, Un)
+            F = np.where(fvalid[:, None, None], F, Fn)
+            fvalid[:] = True
+
+    for s in range(n_steps):
+        o_count = 0
+        for tok in toks:
+            if tok == "{":
+                x_old, v_old = x.copy(), v.copy()
+                continue
+            if tok == "}":
+                c0 = (gids & 0xFFFFFFFF).astype(np.uint64)
+                c1 = (np.asarray(gids, dtype=np.uint64) >> np.uint64(32))
+                r0_, _, _, _ = rng.philox4x32_10(c0, c1, np.uint64((step0 + s) & 0xFFFFFFFF), np.uint64(KIND_METROPOLIS << 24), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+                u = rng.uniform24(r0_).astype(np.float64)
+                with np.errstate(over="ignore", invalid="ignore"):
+                    accept = np.exp(-shadow / kT) - u >= 0.0
+                trials += 1
+                accepted += accept
+                rej = ~accept
+                x[rej] = x_old[rej]
+                v[rej] = -v_old[rej]
+                fvalid[rej] = False
+                shadow[:] = 0.0
+                continue
+            if tok != "O":
+                refresh()
+            ke0 = kinetic_energy(v, masses)
+            if tok == "V":
+                v = r32(v + hv * F * inv_m[None, :, None])
+            elif tok == "R":
+                r0 = [(x[:, i].astype(np.float32) - x[:, j].astype(np.float32)).astype(np.float64) for (i, j, _) in constraints]
+                x = r32(x + hr * v)
+                if constraints:
+                    _shake(x, v, r0, inv_m, constraints, tol, 1.0 / hr)
+            else:
+                xi = rng.normals(seed, gids, step0 + s, A, rng.KIND_O_STEP | (o_count << 4))
+                o_count += 1
+                v = r32(a * v + b * sig * xi)
+            if constraints:
+                _rattle_v(x, v, inv_m, constraints, tol)
+            ke1 = kinetic_energy(v, masses)
+            if tok == "V":
+                shadow += ke1 - ke0
+            elif tok == "O":
+                proposal -= ke1 - ke0
+            else:
+                U_old = U
+                U, F = energy_forces(x)
+                fvalid[:] = True
+                shadow += (ke1 + U) - (ke0 + U_old)
+    refresh()
+    u_last = U.copy()
+    nan = ~np.isfinite(u_last) if n_steps > 0 else np.zeros(P, dtype=bool)
+    return dict(x=x, v=v, u_first=u_first, u_last=u_last, shadow_work=shadow, proposal_work=proposal, trials=trials, accepted=accepted, nan=nan)

@@ -36,7 +36,7 @@ def reduced_potential(ds, x, lam, beta):
     return u.cpu().numpy()
 
 
-def smc_propagate(ds, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, labels=None):
+def smc_propagate(ds, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, labels=None, splitting=0):
     """Same contract as tests.host_harness.HostSystem.smc_propagate, on the GPU."""
     lib = _lib.load()
     pos = rows(x)
@@ -53,7 +53,8 @@ def smc_propagate(ds, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, to
     o["label"] = torch.zeros(P, dtype=torch.int32, device="cuda")
     o["nan"] = torch.zeros(P, dtype=torch.int32, device="cuda")
     o["wmin"] = torch.full((1,), -1, dtype=torch.int64, device="cuda")
-    prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags)
+    trials = torch.zeros(P, 2, dtype=torch.int32, device="cuda")
+    prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags, int(splitting), trials.data_ptr() if splitting else None)
     _lib.check(lib.cdw_smc_propagate(ds.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(o["pos"]), _lib.ptr(o["vel"]), P, _lib.ptr(anc_d), _lib.ptr(aux_d),
                                      _lib.ptr(cum_d), _lib.ptr(lab_d), _lib.ptr(lam_dev(ds.spec, lam)), C.byref(prm), C.c_uint64(seed), C.c_uint64(step0),
                                      C.c_int64(gid0), _lib.ptr(o["inc"]), _lib.ptr(o["w"]), _lib.ptr(o["aux"]), _lib.ptr(o["label"]), _lib.ptr(o["u_first"]),
@@ -63,4 +64,5 @@ def smc_propagate(ds, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, to
     out["x"] = out["pos"][..., :3].astype(np.float64)
     out["v"] = out["vel"][..., :3].astype(np.float64)
     out["wmin"] = out["wmin"].view(np.uint64)
+    out["trials"] = trials.cpu().numpy()
     return out

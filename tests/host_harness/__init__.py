@@ -79,12 +79,13 @@ class HostSystem:
         lib().hh_energy_forces(self.handle, _p(pos), C.c_int64(pos.shape[0]), _p(lam), _p(e), _p(f))
         return e, f[..., :3].astype(np.float64)
 
-    def smc_propagate(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, labels=None):
+    def smc_propagate(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, labels=None, splitting=0):
         pos = self.rows(x)
         vel = self.rows(v) if v is not None else None
         P = pos.shape[0]
         lam = np.ascontiguousarray(lam, dtype=np.float64)
-        prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags)
+        trials = np.zeros((P, 2), dtype=np.int32)
+        prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags, int(splitting), trials.ctypes.data if splitting else None)
         o = dict(pos=np.zeros_like(pos), vel=np.zeros_like(pos), inc=np.zeros(P), w=np.zeros(P), aux=np.zeros(P), label=np.zeros(P, dtype=np.int32),
                  u_first=np.zeros(P), u_last=np.zeros(P), shadow=np.zeros(P), proposal=np.zeros(P), nan=np.zeros(P, dtype=np.int32),
                  wmin=np.array([2 ** 64 - 1], dtype=np.uint64))
@@ -97,6 +98,7 @@ class HostSystem:
                                _p(o["u_first"]), _p(o["u_last"]), _p(o["shadow"]), _p(o["proposal"]), _p(o["nan"]), _p(o["wmin"]))
         o["x"] = o["pos"][..., :3].astype(np.float64)
         o["v"] = o["vel"][..., :3].astype(np.float64)
+        o["trials"] = trials
         return o
 
     def smc_lookahead(self, x, v, f, lam, lam_next, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, labels=None):

@@ -73,9 +73,15 @@ double cdw_host_shfl_xor(double v, int tl, int o) {
 
 extern "C" void hh_set_team(int T) { g_team = T < 1 ? 1 : T; }
 
+static bool has_block(const PropArgs& a) {
+    for (unsigned long long w = a.program; w & 15ull; w >>= 4)
+        if ((w & 15ull) == CDW_STEP_OPEN) return true;
+    return false;
+}
+
 static int run_team(const hh_system* s, PropArgs& a) {
     const int T_ = g_team;
-    const Layout L = make_layout(s->dev, true, 1, T_);
+    const Layout L = make_layout(s->dev, true, 1, T_, has_block(a));
     std::vector<unsigned char> smem(L.total + 64, 0);
     unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));
     const Tables T = table_pointers(L, base);
@@ -91,7 +97,7 @@ static int run_team(const hh_system* s, PropArgs& a) {
             lanes.emplace_back([&, tl]() {
                 g_team_barrier = &bar; g_team_exchange = exchange.data();
                 const LaneMem M = lane_pointers(L, base, T_, tl);
-                keys[tl] = lane_step(s->dev, T, M, a, p);
+                keys[tl] = a.program ? lane_step_program(s->dev, T, M, a, p) : lane_step(s->dev, T, M, a, p);
                 g_team_barrier = nullptr; g_team_exchange = nullptr;
             });
         for (auto& t : lanes) t.join();
@@ -104,7 +110,7 @@ static int run_team(const hh_system* s, PropArgs& a) {
 
 static int run(const hh_system* s, PropArgs& a, bool forces) {
     if (forces && g_team > 1) return run_team(s, a);
-    const Layout L = make_layout(s->dev, forces, 1, 1);
+    const Layout L = make_layout(s->dev, forces, 1, 1, forces && has_block(a));
     std::vector<unsigned char> smem(L.total + 64, 0);
     unsigned char* base = (unsigned char*)(((size_t)smem.data() + 15) & ~size_t(15));
     const Tables T = table_pointers(L, base);
@@ -114,7 +120,7 @@ static int run(const hh_system* s, PropArgs& a, bool forces) {
     for (long long p = 0; p < a.n; ++p) {
         cta_load_rows(s->dev, a, base, L, 0, p, 1, forces);
         if (forces) {
-            unsigned long long k = lane_step(s->dev, T, M, a, p);
+            unsigned long long k = a.program ? lane_step_program(s->dev, T, M, a, p) : lane_step(s->dev, T, M, a, p);
             mn = k < mn ? k : mn;
             cta_store_rows(s->dev, a, base, L, 0, p, 1);
         } else {
@@ -151,6 +157,7 @@ extern "C" int hh_smc_propagate(const hh_system* s, const float* pos_in, const f
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
     if (a.flags & CDW_FLAG_ULA) { a.vel_in = nullptr; a.vel_out = nullptr; }  // as cdw_smc_propagate does
+    a.program = prm->splitting; a.trial_counts = prm->trial_counts;
     return run(s, a, true);
 }
 

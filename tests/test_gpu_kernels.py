@@ -135,6 +135,52 @@ def test_K4_baoab_matches_oracle(gpu, name, n_steps, flags):
     assert key == (~b if b >> np.uint64(63) else b | np.uint64(1 << 63))
 
 
+@pytest.mark.parametrize("team", [1, 2, 8])
+def test_K4_other_team_sizes_match_oracle(gpu, team):
+    """cdw_system_set_team: teams of 2 (what the engines pin for ensembles that fill the GPU several times over), 1 and 8 lanes per
+    replica against the oracle, and the look-ahead launch against the plain one at that team size."""
+    o, ds = _system(system_xml("fluorobenzene"))
+    _lib.check(ds.lib.cdw_system_set_team(ds.handle, team))
+    assert ds.lib.cdw_system_team(ds.handle) == team
+    P = 70
+    X = cache_frames()[:P].astype(np.float64)
+    lam = relative_lambdas(0.3)
+    V = np.zeros_like(X)
+    ref = langevin.baoab(lambda xx: o.energy_forces(xx, lam), X, V, o.masses, o.constraints, 0.002, 1.0, kT, 2, seed=7, gids=np.arange(5, 5 + P),
+                         step0=11, randomize_velocities=True)
+    out = gpu.smc_propagate(ds, X, V, lam, 0.002, 1.0, kT, 2, seed=7, step0=11, gid0=5, flags=1, aux=np.full(P, 0.25), cum=np.full(P, 1.5))
+    assert np.abs(out["x"] - ref["x"]).max() < 2e-7 and np.abs(out["v"] - ref["v"]).max() < 2e-5
+    np.testing.assert_allclose(out["u_first"], ref["u_first"] / kT, rtol=1e-10)
+    np.testing.assert_allclose(out["inc"], ref["u_first"] / kT + 0.25, rtol=1e-10)
+    e, f = gpu.energy_forces(ds, X, lam)
+    U, F = o.energy_forces(X, lam)
+    np.testing.assert_allclose(e, U, rtol=1e-10)
+    assert np.abs(f - F).max() <= 1e-6 * np.abs(F).max()
+
+
+@pytest.mark.parametrize("splitting,dt", [("O V R V O", 0.002), ("O { V R V } O", 0.004), ("{ V R O R V }", 0.006)])
+def test_K4_splitting_programs_match_oracle(gpu, splitting, dt):
+    """cdw_langevin_params.splitting: OMMLI's splitting strings incl. the Metropolised block (openmm/integrators.py:207-217, 427-444)
+    against the oracle interpreter: same trials, same acceptances, same trajectories and works."""
+    o, ds = _system(system_xml("fluorobenzene"))
+    P = 64
+    lam = relative_lambdas(0.3)
+    X = gpu.smc_propagate(ds, cache_frames()[:P].astype(np.float64), None, lam, 0.002, 1.0, kT, 2, seed=1, step0=1, flags=1)["x"]   # onto the constraint manifold
+    V = np.zeros_like(X)
+    ref = langevin.langevin_program(lambda xx: o.energy_forces(xx, lam), X, V, o.masses, o.constraints, dt, 5.0, kT, 3, seed=7, gids=np.arange(5, 5 + P),
+                                    step0=11, splitting=splitting, randomize_velocities=True)
+    out = gpu.smc_propagate(ds, X, V, lam, dt, 5.0, kT, 3, seed=7, step0=11, gid0=5, flags=1, aux=np.zeros(P), cum=np.zeros(P),
+                            splitting=langevin.encode_splitting(splitting))
+    np.testing.assert_array_equal(out["trials"][:, 0], ref["trials"])
+    np.testing.assert_array_equal(out["trials"][:, 1], ref["accepted"])
+    assert np.abs(out["x"] - ref["x"]).max() < 5e-7 and np.abs(out["v"] - ref["v"]).max() < 5e-5
+    np.testing.assert_allclose(out["u_last"], ref["u_last"] / kT, atol=5e-4)
+    np.testing.assert_allclose(out["shadow"], ref["shadow_work"] / kT, atol=1e-3)
+    np.testing.assert_allclose(out["proposal"], ref["proposal_work"] / kT, atol=1e-4)
+    if "{" in splitting:
+        assert 0 < out["trials"][:, 1].sum() <= out["trials"][:, 0].sum() == 3 * P
+
+
 def test_K4_gather_on_load_nan_guard_and_determinism(gpu):
     o, ds = _system(system_xml("fluorobenzene"))
     X = cache_frames()[:64].astype(np.float64)

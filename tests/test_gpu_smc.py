@@ -237,7 +237,36 @@ def test_OMMLI_and_OMMBIP_contract():
     propagator.apply(particle_state, n_steps=1000, reset_integrator=True, apply_pdf_to_context=True, randomize_velocities=True)
     assert np.isfinite(particle_state.positions).all()
     with pytest.raises(NotImplementedError):
-        OMMLI(splitting="O V R V O")
+        OMMLI(splitting="V0 R V1")      # force-group (multiple-time-step) splittings: refused, as in the reference (integrators.py:412)
+    with pytest.raises(ValueError):
+        OMMLI(splitting="V { R } V")    # shadow-work generating steps outside the Metropolised block (integrators.py:248-276)
+    with pytest.raises(ValueError):
+        OMMLI(splitting="{ V R { O } R V }")
+
+
+def test_metropolised_integrator_samples_the_right_distribution():
+    """OMMLI with a Metropolised block (openmm/integrators.py:427-444): GHMC "O { V R V } O" at a time step where plain Langevin
+    dynamics is visibly biased still samples <u> = 3/2 on the harmonic oscillator; trials = accepted + rejected."""
+    from coddiwomple_b200.openmm.integrators import OMMLI
+    from coddiwomple_b200.openmm.propagators import OMMBIP
+    from coddiwomple_b200.openmm.states import HarmonicAlchemicalState, OpenMMPDFState
+    prm = ts.harmonic_oscillator_parameters()
+    pdf_state = OpenMMPDFState(system=ts.harmonic_oscillator_xml(), alchemical_composability=HarmonicAlchemicalState, pressure=None)
+    dt = 6.0 * prm["timestep"]      # period / 3.3: far beyond the accurate regime of the un-Metropolised integrator
+    means = {}
+    for splitting in ("O { V R V } O", "O V R V O"):
+        integ = OMMLI(collision_rate=prm["collision_rate"], timestep=dt, splitting=splitting)
+        prop = OMMBIP(pdf_state, integ, seed=7)
+        pos = torch.zeros(20000, 1, 4, device="cuda")
+        vel = torch.zeros_like(pos)
+        for _ in range(4):
+            prop.apply_batch(pos, vel, n_steps=50, randomize_velocities=True)
+        means[splitting] = float(pdf_state.reduced_potential_batch(pos).mean())
+        if "{" in splitting:
+            assert integ.ntrials == 4 * 50 * 20000 and integ.naccept + integ.nreject == integ.ntrials
+            assert 0.3 < integ.acceptance_rate < 0.999
+    assert abs(means["O { V R V } O"] - 1.5) < 0.04, means
+    assert abs(means["O V R V O"] - 1.5) > 0.08, means   # the bias the Metropolis step removes
 
 
 def test_OMMBIP_restart_attempts():
