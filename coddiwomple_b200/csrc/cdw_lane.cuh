@@ -163,6 +163,17 @@ CDW_HD LaneMem lane_pointers(const Layout& L, unsigned char* smem, int T, int ti
 #define CDW_BASE(g) CDW_BASE_R(g, rid)
 #define CDW_UNPACK(M) const int rid = (M).rid, T_ = (M).T, tl = (M).tl, sw = (M).sw; (void)T_; (void)tl; (void)rid; (void)sw
 
+// true if the predicate holds in ANY valid lane of the warp (host: in this lane).  Control flow that leads to a team barrier
+// (CDW_TEAM_SYNC synchronises all valid lanes of the warp) has to be decided with this, never per team.
+CDW_HD bool lane_any(const LaneMem& M, bool pred) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(M.mask, pred) != 0;
+#else
+    (void)M;
+    return pred;
+#endif
+}
+
 CDW_HD double team_sum(const LaneMem& M, double v) {
     for (int o = M.T >> 1; o > 0; o >>= 1) v += CDW_SHFL_XOR(M, v, o);
     return v;
@@ -283,7 +294,7 @@ CDW_HD double lane_energy(const SysDev& s, const Tables& T, const LaneMem& M, in
     CDW_UNPACK(M);
     const int A = s.n_atoms;
     const float* __restrict__ x = M.x;
-    float* __restrict__ f = M.f + tl * (3 * kR) * A;  // this lane's force copy
+    float* f = M.f + tl * (3 * kR) * A;  // this lane's force copy (NOT __restrict__: lane 0's copy is also read and written through M.f by the reduction below)
     const bool dyn = part == PART_DYNAMIC, sta = part == PART_STATIC;
     const int b0 = dyn ? s.n_bonds_s : 0, b1 = sta ? s.n_bonds_s : s.n_bonds;
     const int a0 = dyn ? s.n_angles_s : 0, a1 = sta ? s.n_angles_s : s.n_angles;
@@ -941,9 +952,9 @@ CDW_HD unsigned long long lane_step_program(const SysDev& s, const Tables& T, co
                 CDW_TEAM_SYNC(M);
                 continue;
             }
-            if (tok != CDW_STEP_O && !fvalid) {   // V needs the forces, R the energy, at the current positions
-                U = lane_energy<true>(s, T, M);
-                fvalid = true;
+            if (tok != CDW_STEP_O && lane_any(M, !fvalid)) {   // V needs the forces, R the energy, at the current positions
+                U = lane_energy<true>(s, T, M);             // (decided per WARP: the team barriers inside must stay uniform; re-evaluating
+                fvalid = true;                              //  is idempotent for the teams whose forces were still valid)
             }
             const double ke_before = lane_kinetic(s, T, M);
             if (tok == CDW_STEP_V) lane_kick(s, T, M, hv);
@@ -961,7 +972,7 @@ CDW_HD unsigned long long lane_step_program(const SysDev& s, const Tables& T, co
             }
         }
     }
-    if (!fvalid) U = lane_energy<true>(s, T, M);
+    if (lane_any(M, !fvalid)) U = lane_energy<true>(s, T, M);
     const double u_last = U;
     const bool bad = a.n_steps > 0 && !(u_last - u_last == 0.0);
     if (tl == 0) {
@@ -1008,7 +1019,7 @@ CDW_HD void lane_restore_row(const SysDev& s, const LaneMem& M, const PropArgs& 
             M.v[b] = w.x; M.v[b + kR] = w.y; M.v[b + 2 * kR] = w.z;
         }
     }
-    CDW_TEAM_SYNC(M);
+    // (no team barrier here: this runs for the reverted teams only; the caller synchronises the whole warp afterwards)
 }
 
 CDW_HD AheadState lane_ahead_main(const SysDev& s, const Tables& T, const LaneMem& M, const PropArgs& a, long long p) {
@@ -1056,16 +1067,13 @@ CDW_HD AheadState lane_ahead_main(const SysDev& s, const Tables& T, const LaneMe
             if (s.n_cons) lane_rattle(s, T, M, a.tol);
         }
         const bool bad = a.n_steps > 0 && !reverted && !(U - U == 0.0);  // NaN or inf
-#if defined(__CUDA_ARCH__)
-        const bool redo = __any_sync(M.mask, bad) != 0;
-#else
-        const bool redo = bad;
-#endif
+        const bool redo = lane_any(M, bad);
         if (bad) {  // (uniform within the team: the team sum leaves the same bits in every lane)
             was_bad = 1;
             lane_restore_row(s, M, a, M.src[rid]);
         }
         if (!redo) break;
+        CDW_TEAM_SYNC(M);
         reverted = true;
         op = n_ops - 3;  // Es Ed (V skipped)
     }

@@ -66,3 +66,29 @@ def smc_propagate(ds, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, to
     out["wmin"] = out["wmin"].view(np.uint64)
     out["trials"] = trials.cpu().numpy()
     return out
+
+
+def smc_lookahead(ds, x, v, f, lam, lam_next, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, labels=None):
+    """Same contract as tests.host_harness.HostSystem.smc_lookahead, on the GPU (cdw_smc_lookahead)."""
+    lib = _lib.load()
+    pos = rows(x)
+    vel = rows(v) if v is not None else None
+    frc = None if f is None else torch.as_tensor(np.ascontiguousarray(f, dtype=np.float32)).cuda()
+    P = pos.shape[0]
+    anc_d = None if anc is None else torch.as_tensor(np.ascontiguousarray(anc), dtype=torch.int32).cuda()
+    lab_d = None if labels is None else torch.as_tensor(np.ascontiguousarray(labels), dtype=torch.int32).cuda()
+    o = dict(pos=torch.zeros_like(pos), vel=torch.zeros_like(pos), force=torch.zeros_like(pos), inc_next=torch.zeros(P, dtype=torch.float64, device="cuda"),
+             aux=torch.zeros(P, dtype=torch.float64, device="cuda"), label=torch.zeros(P, dtype=torch.int32, device="cuda"),
+             nan=torch.zeros(P, dtype=torch.int32, device="cuda"))
+    prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags)
+    lam_t = lam_dev(ds.spec, lam)                                         # (named: a temporary would be recycled by the allocator
+    lam_n = lam_dev(ds.spec, lam_next) if lam_next is not None else None  #  before the launch and the two rows would alias)
+    _lib.check(lib.cdw_smc_lookahead(ds.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), _lib.ptr(o["pos"]) if n_steps else None,
+                                     _lib.ptr(o["vel"]) if n_steps else None, _lib.ptr(o["force"]), P, _lib.ptr(anc_d), _lib.ptr(lab_d), _lib.ptr(lam_t),
+                                     _lib.ptr(lam_n), C.byref(prm), C.c_uint64(seed), C.c_uint64(step0),
+                                     C.c_int64(gid0), _lib.ptr(o["inc_next"]) if lam_next is not None else None, _lib.ptr(o["aux"]), _lib.ptr(o["label"]),
+                                     _lib.ptr(o["nan"]), _lib.current_stream()), "cdw_smc_lookahead")
+    out = {k: v_.cpu().numpy() for k, v_ in o.items()}
+    out["x"] = out["pos"][..., :3].astype(np.float64)
+    out["v"] = out["vel"][..., :3].astype(np.float64)
+    return out

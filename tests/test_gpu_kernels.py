@@ -181,6 +181,39 @@ def test_K4_splitting_programs_match_oracle(gpu, splitting, dt):
         assert 0 < out["trials"][:, 1].sum() <= out["trials"][:, 0].sum() == 3 * P
 
 
+def test_lookahead_launch_matches_the_plain_launch_and_reverts_bad_moves(gpu):
+    """cdw_smc_lookahead against cdw_smc_propagate (which is checked against the oracle above): same states bit for bit, the next
+    incremental works equal the opening works of a plain launch at the next lambda; a replica whose move ends in a non-finite energy
+    (here: an infinite input velocity) is reverted in the middle of a warp of healthy ones (openmm/propagators.py:166-186)."""
+    o, ds = _system(system_xml("fluorobenzene"))
+    P = 100
+    X = cache_frames()[:P].astype(np.float64)
+    V = np.zeros_like(X)
+    lam1, lam2 = relative_lambdas(0.3), relative_lambdas(0.4)
+    eq = gpu.smc_lookahead(ds, X, V, None, lam1, lam1, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    np.testing.assert_allclose(eq["aux"], -o.reduced_potential(X, lam1), rtol=1e-10)
+    a = gpu.smc_lookahead(ds, X, V, eq["force"], lam1, lam2, 0.002, 1.0, kT, 2, seed=7, step0=2, flags=1, labels=np.arange(P) + 3)
+    b = gpu.smc_propagate(ds, X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=2, flags=1, aux=np.zeros(P), cum=np.zeros(P))
+    assert np.abs(a["x"] - b["x"]).max() < 5e-8 and np.abs(a["v"] - b["v"]).max() < 5e-6   # (static / dynamic split vs one pass: summation order)
+    np.testing.assert_allclose(a["aux"], b["aux"], rtol=1e-12)
+    nxt = gpu.smc_propagate(ds, a["x"], a["v"], lam2, 0.002, 1.0, kT, 0, seed=7, step0=4, aux=a["aux"], cum=np.zeros(P))
+    np.testing.assert_allclose(a["inc_next"], nxt["inc"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_array_equal(a["label"], np.arange(P) + 3)
+    assert not a["nan"].any()
+    Vb = V.copy()
+    Vb[[5, 37, 38], 0, 0] = np.inf
+    c = gpu.smc_lookahead(ds, X, Vb, eq["force"], lam1, lam2, 0.002, 1.0, kT, 2, seed=7, step0=2)
+    assert sorted(np.nonzero(c["nan"])[0]) == [5, 37, 38]
+    np.testing.assert_array_equal(c["x"][[5, 37, 38]], X[[5, 37, 38]])
+    keep = gpu.smc_lookahead(ds, X, V, None, lam1, lam2, 0.002, 1.0, kT, 0, seed=7, step0=0)
+    np.testing.assert_allclose(c["aux"][[5, 37, 38]], keep["aux"][[5, 37, 38]], rtol=1e-13)
+    np.testing.assert_allclose(c["inc_next"][[5, 37, 38]], keep["inc_next"][[5, 37, 38]], rtol=1e-9, atol=1e-11)
+    good = np.setdiff1d(np.arange(P), [5, 37, 38])
+    d = gpu.smc_lookahead(ds, X, V, eq["force"], lam1, lam2, 0.002, 1.0, kT, 2, seed=7, step0=2)
+    np.testing.assert_array_equal(c["pos"][good], d["pos"][good])         # the neighbours of a reverted replica are untouched (bitwise)
+    np.testing.assert_array_equal(c["inc_next"][good], d["inc_next"][good])
+
+
 def test_K4_gather_on_load_nan_guard_and_determinism(gpu):
     o, ds = _system(system_xml("fluorobenzene"))
     X = cache_frames()[:64].astype(np.float64)
