@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("CDW_LIB") or os.path.join(HERE, "libcdw_b200.so")  # 
 CDW_FLAG_RANDOMIZE_VELOCITIES = 1
 CDW_FLAG_TRACK_WORKS = 2
 CDW_FLAG_ULA = 4
+CDW_FLAG_TWIST_REFERENCE_NORMALIZER = 8
 CDW_STEP_V, CDW_STEP_R, CDW_STEP_O, CDW_STEP_OPEN, CDW_STEP_CLOSE = 1, 2, 3, 4, 5
 CDW_RESAMPLE_MULTINOMIAL = 0
 CDW_RESAMPLE_SYSTEMATIC = 1
@@ -40,7 +41,7 @@ class SystemDesc(C.Structure):
 class LangevinParams(C.Structure):
     """struct cdw_langevin_params (include/cdw.h)."""
     _fields_ = [("dt", C.c_double), ("gamma", C.c_double), ("kT", C.c_double), ("constraint_tol", C.c_double),
-                ("n_steps", C.c_int32), ("flags", C.c_uint32), ("splitting", C.c_uint64), ("trial_counts", C.c_void_p)]
+                ("n_steps", C.c_int32), ("flags", C.c_uint32), ("splitting", C.c_uint64), ("trial_counts", C.c_void_p), ("twist", C.c_void_p)]
 
 
 class StaticCache(C.Structure):

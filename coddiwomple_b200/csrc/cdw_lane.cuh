@@ -577,6 +577,8 @@ struct PropArgs {
     int have_next;  // part B runs (lambda_next may still be NULL for a system without global parameters)
     // programmable splitting (cdw_langevin_params.splitting != 0, lane_step_program): 4 bits per sub-step, CDW_STEP_*; 0 ends the program
     unsigned long long program; int* trial_counts;  // [P][2] (trials, accepted) of the Metropolised block, may be NULL
+    // quadratic twist of the Euler-Maruyama proposal (cdw_langevin_params.twist; troubleshooting/csmc.py:460-623): a[3A] b[3A] c d, or NULL
+    const double* twist;
 };
 
 // where row `src` (a global particle id when the run is sharded) lives
@@ -732,7 +734,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
     const int n_open = split && !cached_open ? 2 : 1;                 // [ES] ED | E
     const int n_body = (ula ? 3 : 6) + (split ? 1 : 0);               // V R O R [ES] E(D) V | U [ES] E(D) B
     const int e_slot = ula ? 1 : 4;                                   // slot of the (first) evaluation inside a step
-    double U = 0.0, Us = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0;
+    double U = 0.0, Us = 0.0, u_first = 0.0, shadow = 0.0, proposal = 0.0, pending = 0.0, twist_lk = 0.0;
     double aux = 0.0, inc = 0.0, w = 0.0;
     int label = (int)src;
     if (a.peer_pos) {
@@ -799,6 +801,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                     M.r0[bq] = M.x[bi] - M.x[bj]; M.r0[bq + kR] = M.x[bi + kR] - M.x[bj + kR]; M.r0[bq + 2 * kR] = M.x[bi + 2 * kR] - M.x[bj + 2 * kR];
                 }
                 CDW_TEAM_SYNC(M);  // every constraint vector is taken before any lane moves an atom
+                double lk = 0.0;
                 for (int at = tl; at < A; at += T_) {
                     const int b = CDW_BASE(at);
                     const double tau = 0.5 * a.kT * a.dt * a.dt * T.inv_m[at];
@@ -806,8 +809,28 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                     normals3(a.seed, gid, (uint32_t)(a.step0 + st), (uint32_t)at, CDW_KIND_ULA, z0, z1, z2);
                     const d3 x = ld3(M.x, b);
                     st3(M.v, b, x);
-                    st3(M.x, b, x + ((tau * inv_kT) * ld3(M.f, b) + sqrt(2.0 * tau) * mk3(z0, z1, z2)));
+                    if (!a.twist) {
+                        st3(M.x, b, x + ((tau * inv_kT) * ld3(M.f, b) + sqrt(2.0 * tau) * mk3(z0, z1, z2)));
+                    } else {
+                        // twisted move (csmc.py:460-528 with the diagonal A_t, b_t of this iteration; the uncontrolled kernel is N(f, s I),
+                        // f = x + tau beta F (f_t, :480-500), s = 2 tau):  Theta = 1 / (1 + 2 s a)  (Theta_t, :460-478),
+                        // x' ~ N(Theta (f - s b), s Theta)  (twisted_forward_proposal, :503-528), and its log normaliser
+                        // log K_t(psi_t)(x) = sum 0.5 log Theta + (f - s b)^2 Theta / (2 s) - f^2 / (2 s)  - c - d  (:531-561)
+                        const d3 f = x + (tau * inv_kT) * ld3(M.f, b);
+                        const double sc = 2.0 * tau;
+                        const double fk[3] = {f.x, f.y, f.z}, zk[3] = {z0, z1, z2};
+                        double xn[3];
+                        for (int k = 0; k < 3; ++k) {
+                            const double th = 1.0 / (1.0 + 2.0 * sc * a.twist[3 * at + k]);
+                            const double g = fk[k] - sc * a.twist[3 * A + 3 * at + k];
+                            xn[k] = th * g + sqrt(sc * th) * zk[k];
+                            const double quad = (a.flags & CDW_FLAG_TWIST_REFERENCE_NORMALIZER) ? g * g / th : g * g * th;  // (:556 passes Theta^-1)
+                            lk += 0.5 * log(th) + (quad - fk[k] * fk[k]) / (2.0 * sc);
+                        }
+                        st3(M.x, b, mk3(xn[0], xn[1], xn[2]));
+                    }
                 }
+                if (a.twist) twist_lk = team_sum(M, lk) - a.twist[6 * A] - a.twist[6 * A + 1];
                 CDW_TEAM_SYNC(M);
                 if (s.n_cons) lane_shake(s, T, M, a.tol, 0.0);
             }
@@ -822,6 +845,19 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
             acc = team_sum(M, acc);
             if (fwd) pending = -acc;
             else proposal += pending + acc;
+            if (!fwd && a.twist) {
+                // twisted incremental weight (twisted_t_log_weight, csmc.py:593-623): log w = log w_uncontrolled + log K_t(psi_t)(x) + phi_t(x'),
+                // phi_t(x') = x'^T A x' + b^T x' + c + d; the incremental WORK is -log w
+                double phi = 0.0;
+                for (int at = tl; at < A; at += T_) {
+                    const d3 xn = ld3(M.x, CDW_BASE(at));
+                    const double* ta = a.twist + 3 * at;
+                    const double* tb = a.twist + 3 * A + 3 * at;
+                    phi += (ta[0] * xn.x + tb[0]) * xn.x + (ta[1] * xn.y + tb[1]) * xn.y + (ta[2] * xn.z + tb[2]) * xn.z;
+                }
+                phi = team_sum(M, phi) + a.twist[6 * A] + a.twist[6 * A + 1];
+                proposal -= twist_lk + phi;
+            }
             continue;
         }
         const double ke_before = track ? lane_kinetic(s, T, M) : 0.0;

@@ -390,7 +390,9 @@ extern "C" int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_
     CDW_REQUIRE(ula || vel_in || (prm->flags & CDW_FLAG_RANDOMIZE_VELOCITIES) || prm->n_steps == 0, "velocities required unless they are randomized");
     CDW_REQUIRE(ula || !pos_out || prm->n_steps == 0 || vel_out, "vel_out is required when positions are written");
     CDW_REQUIRE(!(ula && (prm->flags & CDW_FLAG_TRACK_WORKS)), "CDW_FLAG_TRACK_WORKS does not apply to the Euler-Maruyama proposal");
+    CDW_REQUIRE(ula || !prm->twist, "a twist applies to the Euler-Maruyama proposal only (CDW_FLAG_ULA)");
     PropArgs a = {};
+    a.twist = prm->twist;
     a.pos_in = (const float4*)pos_in; a.vel_in = ula ? nullptr : (const float4*)vel_in; a.pos_out = (float4*)pos_out;
     a.vel_out = ula ? nullptr : (float4*)vel_out;
     a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.label_in = label_in; a.lambda = lambda;
@@ -422,6 +424,7 @@ static int lookahead_common(const cdw_system* sys, PropArgs& a, const cdw_langev
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     CDW_REQUIRE(!(prm->flags & ~CDW_FLAG_RANDOMIZE_VELOCITIES), "cdw_smc_lookahead: BAOAB moves only (flags other than CDW_FLAG_RANDOMIZE_VELOCITIES are not supported)");
+    CDW_REQUIRE(!prm->twist, "a twist applies to the Euler-Maruyama proposal only (cdw_smc_propagate with CDW_FLAG_ULA)");
     CDW_REQUIRE(force_out, "force_out is required");
     CDW_REQUIRE(prm->n_steps == 0 || (pos_out && vel_out), "pos_out and vel_out are required when n_steps > 0");
     CDW_REQUIRE(!inc_next_out || lambda_next || sys->dev.n_lambda == 0, "lambda_next is required with inc_next_out");
@@ -491,6 +494,8 @@ extern "C" int cdw_smc_propagate_sharded_cached(const cdw_system* sys, const flo
     PropArgs a = {};
     a.peer_pos = (const float4* const*)peer_pos; a.peer_vel = (const float4* const*)peer_vel; a.peer_aux = peer_aux; a.peer_label = peer_label;
     a.n_per_rank = n_per_rank;
+    CDW_REQUIRE(ula || !prm->twist, "a twist applies to the Euler-Maruyama proposal only (CDW_FLAG_ULA)");
+    a.twist = prm->twist;
     a.vel_in = ula ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
     a.pos_out = (float4*)pos_out; a.vel_out = ula ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;

@@ -131,10 +131,52 @@ class LangevinParameters:
     def kT(self):
         return kT_in_md_units(self.temperature)
 
-    def as_struct(self, flags=0, n_steps=None, trial_counts=None):
+    def as_struct(self, flags=0, n_steps=None, trial_counts=None, twist=None):
+        """`twist`: this iteration's row of a TwistSequence table (device tensor of 6 A + 2 doubles) or None."""
         return _lib.LangevinParams(self.timestep, self.collision_rate, self.kT, self.constraint_tolerance,
                                    self.n_steps if n_steps is None else int(n_steps), int(flags), int(getattr(self, "splitting_word", 0)),
-                                   None if trial_counts is None else trial_counts.data_ptr())
+                                   None if trial_counts is None else trial_counts.data_ptr(), None if twist is None else twist.data_ptr())
+
+
+class TwistSequence:
+    """Per-iteration quadratic twists psi_t = exp(-(x^T A_t x + b_t^T x + c_t + d_t)) of the Euler-Maruyama proposal — the `twisting_functions`
+    / `twisting_parameters` of troubleshooting/csmc.py:625-747 for position-independent, DIAGONAL A_t: row t - 1 of the device table holds
+    a[3A] b[3A] c d of iteration t (cdw_langevin_params.twist).  `a`: (T-1, A, 3) in 1/nm^2, `b`: (T-1, A, 3) in 1/nm, `c`, `d`: (T-1,).
+    reference_normalizer=True evaluates the forward log normaliser the way csmc.py:556 literally does (include/cdw.h)."""
+
+    def __init__(self, a, b, c=None, d=None, reference_normalizer=False, device=None):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        if a.ndim != 3 or a.shape[2] != 3 or a.shape != b.shape:
+            raise ValueError("a and b must both have shape (n_iterations, n_atoms, 3)")
+        n = a.shape[0]
+        c = np.zeros(n) if c is None else np.asarray(c, dtype=np.float64).reshape(n)
+        d = np.zeros(n) if d is None else np.asarray(d, dtype=np.float64).reshape(n)
+        self.n_iterations, self.n_atoms = n, a.shape[1]
+        self.reference_normalizer = bool(reference_normalizer)
+        self.host = np.concatenate([a.reshape(n, -1), b.reshape(n, -1), c[:, None], d[:, None]], axis=1)
+        self.table = None if device is None else torch.from_numpy(self.host).to(device)
+
+    def to(self, device):
+        if self.table is None or self.table.device != torch.device(device):
+            self.table = torch.from_numpy(self.host).to(device)
+        return self
+
+    def check(self, masses, langevin):
+        """1 + 2 s a > 0 for every coordinate (s = 2 tau_a = kT dt^2 / m_a): the twisted proposal must stay a proper Gaussian."""
+        s = langevin.kT * langevin.timestep ** 2 / np.asarray(masses, dtype=np.float64)
+        A = self.n_atoms
+        if s.shape[0] != A:
+            raise ValueError(f"the twist is for {A} atoms, the system has {s.shape[0]}")
+        if ((1.0 + 2.0 * s[None, :, None] * self.host[:, :3 * A].reshape(-1, A, 3)) <= 0.0).any():
+            raise ValueError("1 + 2 s a must be positive for every coordinate (Theta_t, troubleshooting/csmc.py:460-478)")
+
+    def row(self, t):
+        """Iteration t (1-based) -> the device row."""
+        return self.table[t - 1]
+
+    @property
+    def flags(self):
+        return _lib.CDW_FLAG_TWIST_REFERENCE_NORMALIZER if self.reference_normalizer else 0
 
 
 class ParticleEnsemble:
@@ -342,16 +384,19 @@ class ParticleEnsemble:
         self.wmin_key.fill_(-1)  # ~0ull: arm the running min; cdw_smc_resample re-arms it after every iteration
         return u0
 
-    def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None, ula=False):
+    def propagate_and_weigh(self, lam_row, langevin, seed, randomize_velocities=False, track_works=False, outputs=None, ula=False, twist=None):
         """Fused K3b-on-load + K1 + K4 + first half of K2 (include/cdw.h: cdw_smc_propagate).  Advances `iteration`.
-        ula=True swaps BAOAB for the Euler-Maruyama proposal and its generalised incremental work (CDW_FLAG_ULA)."""
+        ula=True swaps BAOAB for the Euler-Maruyama proposal and its generalised incremental work (CDW_FLAG_ULA); `twist` (a TwistSequence)
+        twists that proposal with the row of this iteration."""
         self.join()
         self.iteration += 1
         c, n = self.cur, 1 - self.cur
         flags = (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if randomize_velocities else 0) | (_lib.CDW_FLAG_TRACK_WORKS if track_works else 0)
         if ula:
-            flags = _lib.CDW_FLAG_ULA
-        prm = langevin.as_struct(flags)
+            flags = _lib.CDW_FLAG_ULA | (twist.flags if twist is not None else 0)
+        elif twist is not None:
+            raise ValueError("a twist applies to the Euler-Maruyama proposal only")
+        prm = langevin.as_struct(flags, twist=None if twist is None else twist.row(self.iteration))
         o = outputs or {}
         use_cache = self.static_cache and not track_works and langevin.n_steps > 0 and not getattr(langevin, "splitting_word", 0)
         if use_cache and not self.cache_valid:
@@ -416,10 +461,13 @@ class SMCEngine:
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5,
                  always_resample=False, seed=0, resample_seed=1, gid0=0, record_history=False, device=None, record_works_every=None,
-                 proposal="baoab", static_cache=True, record_lineage=False, lookahead=True):
+                 proposal="baoab", static_cache=True, record_lineage=False, lookahead=True, twist=None):
         if proposal not in ("baoab", "ula"):
             raise ValueError("proposal must be 'baoab' (MCMC move, openmm/integrators.py:19-465) or 'ula' (Euler-Maruyama, :666-888)")
+        if twist is not None and proposal != "ula":
+            raise ValueError("twist: controlled SMC twists the Euler-Maruyama proposal (proposal='ula', troubleshooting/csmc.py:625-747)")
         self.proposal = proposal
+        self.twist = twist
         # the look-ahead launch is the fused "V R O R V" body; other splittings (Metropolised blocks, ...) run the programmable one
         self.lookahead = bool(lookahead) and proposal == "baoab" and not getattr(langevin, "splitting_word", 0)
         self.ensemble = ParticleEnsemble(system, n_particles, gid0=gid0, device=device, record_history=record_history, static_cache=static_cache)
@@ -430,6 +478,11 @@ class SMCEngine:
         self.T = len(self.parameter_sequence)
         self.lam = self.system.lambda_table(self.parameter_sequence, self.ensemble.device)
         self.system.register_protocol(self.lam, self.langevin.kT)
+        if twist is not None:
+            if twist.n_iterations != self.T - 1:
+                raise ValueError(f"the twist sequence holds {twist.n_iterations} iterations, the protocol has {self.T - 1}")
+            twist.check(self.system.spec.masses, self.langevin)
+            twist.to(self.ensemble.device)
         self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)
@@ -475,7 +528,7 @@ class SMCEngine:
     # ------------------------------------------------------------------ sequential loop (also the public two-call form)
     def propagate(self, t):
         """First kernel of iteration t (1-based): gather-on-load + E/F + incremental work + move + closing energy."""
-        self.ensemble.propagate_and_weigh(self.lam[t], self.langevin, self.seed, randomize_velocities=(t == 1), ula=(self.proposal == "ula"))
+        self.ensemble.propagate_and_weigh(self.lam[t], self.langevin, self.seed, randomize_velocities=(t == 1), ula=(self.proposal == "ula"), twist=self.twist)
 
     def finish_iteration(self, t):
         """Rest of iteration t: log-sum-exp / nESS / decision, uniforms, integer cdf + ancestors, cum update."""

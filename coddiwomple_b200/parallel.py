@@ -94,10 +94,13 @@ class ShardedSMCEngine:
     """
 
     def __init__(self, system, n_particles, parameter_sequence, langevin=None, resampler="multinomial", floor_threshold=0.5, always_resample=False,
-                 seed=0, resample_seed=1, group=None, proposal="baoab"):
+                 seed=0, resample_seed=1, group=None, proposal="baoab", twist=None):
         if proposal not in ("baoab", "ula"):
             raise ValueError("proposal must be 'baoab' or 'ula'")
+        if twist is not None and proposal != "ula":
+            raise ValueError("twist: controlled SMC twists the Euler-Maruyama proposal (proposal='ula')")
         self.proposal = proposal
+        self.twist = twist
         self.lookahead = proposal == "baoab"
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (backend nccl, one process per GPU)")
@@ -116,6 +119,11 @@ class ShardedSMCEngine:
         self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
         self.lam = self.system.lambda_table(self.parameter_sequence, self.device)
         self.system.register_protocol(self.lam, self.langevin.kT)
+        if twist is not None:
+            if twist.n_iterations != self.T - 1:
+                raise ValueError(f"the twist sequence holds {twist.n_iterations} iterations, the protocol has {self.T - 1}")
+            twist.check(self.system.spec.masses, self.langevin)
+            twist.to(self.device)
         self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)
@@ -296,7 +304,9 @@ class ShardedSMCEngine:
         self.iteration = t
         c, n = self.cur, 1 - self.cur
         flags = _lib.CDW_FLAG_ULA if self.proposal == "ula" else (_lib.CDW_FLAG_RANDOMIZE_VELOCITIES if t == 1 else 0)
-        prm = self.langevin.as_struct(flags)
+        if self.twist is not None:
+            flags |= self.twist.flags
+        prm = self.langevin.as_struct(flags, twist=None if self.twist is None else self.twist.row(t))
         cache = _lib.static_cache(None, None, self.local("fs", n), self.local("us", n), self.peer["fs"][c], self.peer["us"][c])
         _lib.check(self.lib.cdw_smc_propagate_sharded_cached(
             self.system.handle, _lib.ptr(self.peer["pos"][c]), _lib.ptr(self.peer["vel"][c]), _lib.ptr(self.peer["aux"][c]), _lib.ptr(self.peer["label"][c]),

@@ -116,6 +116,14 @@ typedef struct cdw_langevin_params {
      * iff exp(-shadow_work / kT) >= uniform, else restores x and flips v (openmm/integrators.py:427-444). */
     uint64_t splitting;
     int32_t* trial_counts;  /* device [P][2] (trials, accepted) of the Metropolised block, or NULL */
+    /* Quadratic twist of the Euler-Maruyama proposal (controlled SMC, troubleshooting/csmc.py:460-623), CDW_FLAG_ULA only; NULL = none.
+     * DEVICE array of 6 A + 2 doubles for THIS iteration: a[3A] (the diagonal of A_t, 1/nm^2), b[3A] (1/nm), c, d, the coefficients of
+     *   phi_t(x) = x^T A_t x + b_t^T x + c_t + d_t,  psi_t = exp(-phi_t).
+     * The move becomes x' ~ N(Theta (f - s b), s Theta) with f = x + tau beta F(x), s = 2 tau, Theta = (1 + 2 s a)^-1 per coordinate
+     * (Theta_t :460-478, f_t :480-500, twisted_forward_proposal :503-528) and the incremental work loses
+     *   log K_t(psi_t)(x) + phi_t(x')   (twisted_forward_log_normalizer :531-561, twisted_t_log_weight :593-623).
+     * 1 + 2 s a must be positive for every coordinate. */
+    const double* twist;
 } cdw_langevin_params;
 
 #define CDW_STEP_V 1u      /* v += (dt / n_V) f / m */
@@ -132,6 +140,10 @@ typedef struct cdw_langevin_params {
  *   inc = u_t(x_t) + aux + proposal_work   (distribution_factories.py:98-131; troubleshooting/csmc.py:174-191).
  * Velocities are not used (vel_in / vel_out may be NULL); gamma is ignored. */
 #define CDW_FLAG_ULA 4u
+/* With a twist: evaluate the quadratic form of the forward log normaliser with Theta^-1, as troubleshooting/csmc.py:556 literally does
+ * (mahalanobis(f, dt b, inv(theta))).  The integral of N(x'; f, s) exp(-phi(x')) has Theta there (the default); the two agree when A = 0,
+ * the only regime the reference's own test exercises (troubleshooting/test_csmc.py:165-226). */
+#define CDW_FLAG_TWIST_REFERENCE_NORMALIZER 8u
 #define CDW_RESAMPLE_MULTINOMIAL 0
 #define CDW_RESAMPLE_SYSTEMATIC 1
 

@@ -79,13 +79,16 @@ class HostSystem:
         lib().hh_energy_forces(self.handle, _p(pos), C.c_int64(pos.shape[0]), _p(lam), _p(e), _p(f))
         return e, f[..., :3].astype(np.float64)
 
-    def smc_propagate(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, labels=None, splitting=0):
+    def smc_propagate(self, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, tol=1e-6, flags=0, anc=None, aux=None, cum=None, labels=None, splitting=0,
+                      twist=None):
         pos = self.rows(x)
         vel = self.rows(v) if v is not None else None
         P = pos.shape[0]
         lam = np.ascontiguousarray(lam, dtype=np.float64)
         trials = np.zeros((P, 2), dtype=np.int32)
-        prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags, int(splitting), trials.ctypes.data if splitting else None)
+        twist = None if twist is None else np.ascontiguousarray(twist, dtype=np.float64)
+        prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags, int(splitting), trials.ctypes.data if splitting else None,
+                                  None if twist is None else twist.ctypes.data)
         o = dict(pos=np.zeros_like(pos), vel=np.zeros_like(pos), inc=np.zeros(P), w=np.zeros(P), aux=np.zeros(P), label=np.zeros(P, dtype=np.int32),
                  u_first=np.zeros(P), u_last=np.zeros(P), shadow=np.zeros(P), proposal=np.zeros(P), nan=np.zeros(P, dtype=np.int32),
                  wmin=np.array([2 ** 64 - 1], dtype=np.uint64))

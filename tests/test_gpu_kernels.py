@@ -195,7 +195,8 @@ def test_lookahead_launch_matches_the_plain_launch_and_reverts_bad_moves(gpu):
     a = gpu.smc_lookahead(ds, X, V, eq["force"], lam1, lam2, 0.002, 1.0, kT, 2, seed=7, step0=2, flags=1, labels=np.arange(P) + 3)
     b = gpu.smc_propagate(ds, X, V, lam1, 0.002, 1.0, kT, 2, seed=7, step0=2, flags=1, aux=np.zeros(P), cum=np.zeros(P))
     assert np.abs(a["x"] - b["x"]).max() < 5e-8 and np.abs(a["v"] - b["v"]).max() < 5e-6   # (static / dynamic split vs one pass: summation order)
-    np.testing.assert_allclose(a["aux"], b["aux"], rtol=1e-12)
+    np.testing.assert_allclose(a["aux"], b["aux"], atol=2e-4)               # (the energies follow the fp32-ulp position differences ...)
+    np.testing.assert_allclose(a["aux"], -o.reduced_potential(a["x"], lam1), rtol=1e-10)   # (... and are exact at the launch's own rows)
     nxt = gpu.smc_propagate(ds, a["x"], a["v"], lam2, 0.002, 1.0, kT, 0, seed=7, step0=4, aux=a["aux"], cum=np.zeros(P))
     np.testing.assert_allclose(a["inc_next"], nxt["inc"], rtol=1e-9, atol=1e-11)
     np.testing.assert_array_equal(a["label"], np.arange(P) + 3)

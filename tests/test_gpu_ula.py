@@ -132,3 +132,73 @@ def test_OMMEMP_apply_returns_the_kernel_log_ratio():
     bwd = -(((x_old - x_new - tau * F_new / kT) ** 2) / (4 * tau)).sum()
     assert abs(work - (fwd - bwd)) < 5e-4     # integrators.py:864-888 on the move the kernel made
     assert integ.get_proposal_work() == work
+
+
+# ------------------------------------------------------------------------------------------------ controlled SMC: the quadratic twist
+@pytest.mark.parametrize("name,n_steps,P,ref_norm", [("fluorobenzene", 1, 100, False), ("fluorobenzene", 2, 37, True), ("ala", 1, 64, False)])
+def test_twisted_kernel_matches_oracle(name, n_steps, P, ref_norm):
+    """cdw_langevin_params.twist (troubleshooting/csmc.py:460-623) against oracle/twisted.py, which is pinned to the reference's own outputs."""
+    from coddiwomple_b200.engine import DeviceSystem
+    from oracle import twisted
+    from tests import gpu_util
+    xml = ts.alanine_dipeptide_shaped_xml()[0] if name == "ala" else system_xml(name)
+    o = XmlSystemOracle(xml)
+    ds = DeviceSystem(xml)
+    X = (cache_frames()[np.random.RandomState(0).randint(0, 151, P)] if name == "fluorobenzene" else ts.alanine_dipeptide_shaped_ensemble(P)).astype(np.float64)
+    A = X.shape[1]
+    r = np.random.RandomState(5)
+    tw = twisted.pack_twist(40.0 * r.rand(A, 3), 3.0 * r.randn(A, 3), c=0.37, d=-0.11)
+    lam = relative_lambdas(0.3)
+    dt = 0.0005
+    ref = twisted.twisted_ula(lambda xx: o.energy_forces(xx, lam), X, o.masses, o.constraints, dt, kT, n_steps, seed=7, gids=np.arange(5, 5 + P), step0=11,
+                              twist=tw, reference_normalizer=ref_norm)
+    flags = _lib.CDW_FLAG_ULA | (_lib.CDW_FLAG_TWIST_REFERENCE_NORMALIZER if ref_norm else 0)
+    out = gpu_util.smc_propagate(ds, X, None, lam, dt, 0.0, kT, n_steps, seed=7, step0=11, gid0=5, flags=flags, aux=np.full(P, 0.25), cum=np.full(P, 1.5), twist=tw)
+    assert np.abs(out["x"] - ref["x"]).max() < 2e-7
+    np.testing.assert_allclose(out["u_last"], ref["u_last"] / kT, atol=2e-4)
+    np.testing.assert_allclose(out["proposal"], ref["proposal_work"], rtol=1e-9, atol=3e-4)
+    np.testing.assert_allclose(out["inc"], out["u_last"] + 0.25 + out["proposal"], rtol=1e-12)
+    np.testing.assert_allclose(out["w"], 1.5 + out["inc"], rtol=1e-12)
+    plain = gpu_util.smc_propagate(ds, X, None, lam, dt, 0.0, kT, n_steps, seed=7, step0=11, gid0=5, flags=_lib.CDW_FLAG_ULA, aux=np.full(P, 0.25), cum=np.full(P, 1.5))
+    zero = gpu_util.smc_propagate(ds, X, None, lam, dt, 0.0, kT, n_steps, seed=7, step0=11, gid0=5, flags=flags, aux=np.full(P, 0.25), cum=np.full(P, 1.5),
+                                  twist=np.zeros(6 * A + 2))
+    assert np.abs(out["x"] - plain["x"]).max() > 1e-6
+    assert np.abs(zero["x"] - plain["x"]).max() < 2e-7        # zero twist = the uncontrolled move (csmc.py:617-620)
+    np.testing.assert_allclose(zero["inc"], plain["inc"], atol=2e-4)
+    with pytest.raises(_lib.CdwError):                         # a twist without the Euler-Maruyama proposal is refused
+        gpu_util.smc_propagate(ds, X, np.zeros_like(X), lam, dt, 1.0, kT, 1, seed=7, step0=11, twist=tw)
+
+
+def test_twisted_engine_is_unbiased_and_a_good_twist_raises_the_effective_sample_size():
+    """SMCEngine(proposal="ula", twist=TwistSequence(...)): the harmonic-oscillator protocol of the reference (Delta F = 1 kT, tests/utils.py:64-65)
+    as plain SIS.  Any admissible twist leaves the estimate unbiased; a linear twist that pulls the proposal along the moving well raises the
+    effective sample size of the final weights; the literal csmc.py:556 normaliser with A != 0 is visibly biased."""
+    from coddiwomple_b200.engine import LangevinParameters, SMCEngine, TwistSequence
+    prm = ts.harmonic_oscillator_parameters()
+    P, T = 20000, 41
+    x0 = np.random.RandomState(0).normal(0, prm["sigma"], (P, 1, 3)).astype(np.float32)
+    seq = ts.harmonic_parameter_sequence(T)
+    ramp = np.arange(1, T) / (T - 1)
+
+    def run(twist):
+        eng = SMCEngine(ts.harmonic_oscillator_xml(), P, seq, langevin=LangevinParameters(timestep=0.2), seed=1, resample_seed=2, proposal="ula",
+                        floor_threshold=0.0, twist=twist)
+        eng.anneal(x0)
+        w = -eng.cumulative_works()
+        return eng.free_energy(), float(np.exp(2 * np.logaddexp.reduce(w) - np.logaddexp.reduce(2 * w)) / P)
+
+    def seq_twist(a, b, **kw):
+        bb = np.zeros((T - 1, 1, 3)); bb[:, 0, 0] = b * 0.2 * ramp
+        return TwistSequence(np.full((T - 1, 1, 3), a), bb, c=0.05 * np.arange(1, T), **kw)
+
+    f0, n0 = run(None)
+    f1, n1 = run(seq_twist(0.0, -12.0))
+    f2, n2 = run(seq_twist(2.0, -10.0))
+    f3, _ = run(seq_twist(2.0, -10.0, reference_normalizer=True))
+    assert abs(f0 - 1.0) < 0.04 and abs(f1 - 1.0) < 0.04 and abs(f2 - 1.0) < 0.04, (f0, f1, f2)
+    assert n1 > 1.25 * n0, (n0, n1)
+    assert abs(f3 - 1.0) > 1.0, f3
+    with pytest.raises(ValueError):
+        SMCEngine(ts.harmonic_oscillator_xml(), P, seq, proposal="baoab", twist=seq_twist(0.0, -12.0))
+    with pytest.raises(ValueError):   # 1 + 2 s a <= 0: not a Gaussian any more
+        SMCEngine(ts.harmonic_oscillator_xml(), 16, seq, langevin=LangevinParameters(timestep=0.2), proposal="ula", twist=seq_twist(-1e4, 0.0))
