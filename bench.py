@@ -302,6 +302,7 @@ def run_gpu(args):
         achieved = flops["per_iteration"] * P / (k_ms * 1e-3) / 1e12
         peaks, peaks_src = measured_peaks()
         traffic = measured_traffic()
+        eager = eager_launch_ms(torch, SMCEngine, xml, P, seq, langevin, x0_dev, thr, always) if world == 1 else None
         config2 = config2_run(torch, ts, SMCEngine, LangevinParameters, positions_to_rows, spec_from_xml, kernels, fp64_peak, args) if world == 1 else None
         sweep = resampling_sweep(torch, kernels, _lib, 1 << 24, 13, peaks.get("hbm_gbs")) if world == 1 else None
         cpu_base = cpu_baseline_subprocess() if world == 1 else None
@@ -325,7 +326,10 @@ def run_gpu(args):
                 "roofline": {"bound": "fp64", "kernel": "smc_lookahead_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                              "avg_launch_ms": k_ms, "avg_launch_ms_is": "ms_per_step / (n_lambda - 1): upper bound, the graph-timed anneal holds nothing else on its critical path",
-                             "share_of_step": (traffic or {}).get("share_of_step"),
+                             "avg_launch_ms_events": eager, "avg_launch_ms_events_is": "CUDA events on the launching stream around each look-ahead launch of an eager "
+                             "(un-graphed) anneal, iterations 3 .. T-1, mean; the launch also waits for the previous iteration's resampling on the side stream",
+                             "share_of_step": None if eager is None else min(1.0, eager * (N_LAMBDA - 1) / float(np.mean(ms))),
+                             "algorithmic_hbm_bytes_per_launch": (traffic or {}).get("algorithmic_hbm_bytes_per_launch"),
                              "algorithmic_flop_per_particle_iteration": flops["per_iteration"],
                              "peak_source": "cdw_fma_peak(fp64) micro-benchmark run in this process (MEASURED_PEAKS.json has no FP pipe figure)",
                              "fp32_fma_peak_tflops": fp32_peak, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
@@ -337,6 +341,20 @@ def run_gpu(args):
     if world > 1:
         eng.close()
         dist.destroy_process_group()
+
+
+def eager_launch_ms(torch, SMCEngine, xml, P, seq, langevin, x0_dev, thr, always):
+    """Mean duration of the dominant kernel's launches, measured with CUDA events on the stream it is launched on (eager loop)."""
+    eng = SMCEngine(xml, P, seq, langevin=langevin, seed=0, resample_seed=1, floor_threshold=thr, always_resample=always)
+    eng.initialize(x0_dev)
+    evs = []
+    for t in range(1, eng.T):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.step(t); e1.record()
+        evs.append((e0, e1))
+    eng.ensemble.join()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs[2:]]))
 
 
 def parity_probe(torch, dist, world, rank, xml):
@@ -409,8 +427,12 @@ def config4_runs(torch, dist, world, rank, xml, langevin):
     P = 1_000_000
     seq = ts.relative_alchemical_sequence(N_LAMBDA)
     out = {}
-    for proposal, lang in (("baoab", langevin), ("ula", LangevinParameters(timestep=0.0005))):
-        eng = ShardedSMCEngine(xml, P, seq, langevin=lang, seed=0, resample_seed=1, proposal=proposal)
+    from coddiwomple_b200.engine import TwistSequence
+    r = np.random.RandomState(9)
+    twist = TwistSequence(5.0 * r.rand(N_LAMBDA - 1, 13, 3), 0.5 * r.randn(N_LAMBDA - 1, 13, 3), c=np.zeros(N_LAMBDA - 1))   # controlled SMC (csmc.py:460-747)
+    for name, lang in (("baoab", langevin), ("ula", LangevinParameters(timestep=0.0005)), ("ula_twisted", LangevinParameters(timestep=0.0005))):
+        proposal = "baoab" if name == "baoab" else "ula"
+        eng = ShardedSMCEngine(xml, P, seq, langevin=lang, seed=0, resample_seed=1, proposal=proposal, twist=twist if name == "ula_twisted" else None)
         rows = positions_to_rows(frames[np.random.RandomState(11 + rank).randint(0, len(frames), eng.P_loc)])
         eng.capture(rows)
         for _ in range(2):
@@ -423,7 +445,7 @@ def config4_runs(torch, dist, world, rank, xml, langevin):
             t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms.append(float(t.item()))
-        out[proposal] = {"particles": P, "particles_per_gpu": eng.P_loc, "n_lambda": N_LAMBDA, "ms_per_anneal": float(np.mean(ms)),
+        out[name] = {"particles": P, "particles_per_gpu": eng.P_loc, "n_lambda": N_LAMBDA, "ms_per_anneal": float(np.mean(ms)),
                          "value": P * (N_LAMBDA - 1) / (np.mean(ms) * 1e-3), "unit": "particle-steps/s", "free_energy_kT": eng.free_energy(),
                          "resampled_iterations": len(eng.resampled_iterations())}
         eng.close()

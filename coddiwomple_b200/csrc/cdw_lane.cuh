@@ -579,13 +579,14 @@ struct PropArgs {
     unsigned long long program; int* trial_counts;  // [P][2] (trials, accepted) of the Metropolised block, may be NULL
     // quadratic twist of the Euler-Maruyama proposal (cdw_langevin_params.twist; troubleshooting/csmc.py:460-623): a[3A] b[3A] c d, or NULL
     const double* twist;
+    int diag_local_rank;  // timing diagnostic (CDW_DIAG_LOCAL_ROWS, results are wrong): rank + 1 = read every ancestor's row from this rank
 };
 
 // where row `src` (a global particle id when the run is sharded) lives
 CDW_HD const float4* row_ptr(const PropArgs& a, const float4* local, const float4* const* peers, long long src, int A) {
     if (!a.peer_pos) return local + src * A;
     const long long r = src / a.n_per_rank;
-    return peers[r] + (src - r * a.n_per_rank) * A;
+    return peers[a.diag_local_rank ? a.diag_local_rank - 1 : r] + (src - r * a.n_per_rank) * A;
 }
 
 // (x, y, z) of one float4 row element -> three shared-memory columns

@@ -24,6 +24,7 @@ constexpr int kMaxThreads = 256;
 struct Shape {
     int R, T;   // replicas staged per CTA, lanes per replica; blockDim = R * T
     int metro;  // the program has a Metropolised block: the layout holds the state saved at "{"
+    int bulk;   // rows arrive by TMA bulk copies (cta_load_rows_bulk)
 };
 
 __global__ void __launch_bounds__(kMaxThreads) reduced_potential_kernel(SysDev s, PropArgs a, Shape sh) {
@@ -86,6 +87,70 @@ __device__ __forceinline__ void wait_tables(unsigned long long* bar, unsigned pa
     }
 }
 
+// ---- TMA row gather.  Every particle row is 16 A contiguous bytes (float4 [A]) in HBM — local, or on a peer GPU when the run is sharded
+// and the ancestor lives there.  One bulk copy per row and array (cp.async.bulk, completion on an mbarrier) brings the rows into a
+// row-major staging area that borrows the (still unused) force copies, and the CTA transposes them into the [component][replica] columns:
+// every byte crosses NVLink once, in 16 A-byte requests.  (The 4-byte cp.async path requests every 32-byte sector of a row three times —
+// once per component — and peer reads are not cached on this side: on 8 GPUs that redundancy saturated NVLink, profiles/r2_notes.md.)
+// Needs T >= 4 (three staging arrays of 512 A bytes inside the T force copies of 384 A bytes, the force rows clear of copy 0).
+__device__ __forceinline__ void cta_load_rows_bulk(const SysDev& s, const PropArgs& a, unsigned char* smem, const Layout& L, int sw, long long p0, int count,
+                                                   unsigned long long* bar, unsigned parity) {
+    const int A = s.n_atoms, tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const unsigned row_bytes = 16u * (unsigned)A;
+    const size_t arr = (size_t)kR * row_bytes;
+    float* X = (float*)(smem + L.x);
+    float* V = (float*)(smem + L.v);
+    float* Fc = (float*)(smem + L.f);
+    long long* SRC = (long long*)(smem + L.src);
+    const float4* SP = (const float4*)(smem + L.f);
+    const float4* SV = (const float4*)(smem + L.f + arr);
+    const float4* SF = (const float4*)(smem + L.f + 2 * arr);
+    const bool with_vel = a.vel_in != nullptr, with_f = a.fs_in != nullptr;
+    const unsigned b = smem_addr(bar);
+    if (tid == 0) {
+        const unsigned total = (unsigned)count * row_bytes * (1u + (with_vel ? 1u : 0u) + (with_f ? 1u : 0u));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(total) : "memory");
+    }
+    if (tid < count) {
+        const long long src = a.anc ? (long long)a.anc[p0 + tid] : p0 + tid;
+        SRC[tid] = src;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staging area was last touched through the generic proxy (force copies)
+        const unsigned dst = smem_addr(smem + L.f) + (unsigned)tid * row_bytes;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(row_ptr(a, a.pos_in, a.peer_pos, src, A)), "r"(row_bytes), "r"(b) : "memory");
+        if (with_vel)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (unsigned)arr),
+                         "l"(row_ptr(a, a.vel_in, a.peer_vel, src, A)), "r"(row_bytes), "r"(b) : "memory");
+        if (with_f)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2u * (unsigned)arr),
+                         "l"(row_ptr(a, a.fs_in, a.peer_fs, src, A)), "r"(row_bytes), "r"(b) : "memory");
+    }
+    wait_tables(bar, parity);
+    // transpose, replica index fastest: conflict-free 16-byte reads (row stride 16 A bytes, A odd or not) and conflict-free column writes
+    for (int idx = tid; idx < count * A; idx += nt) {
+        const int at = idx / count, r = idx - at * count;
+        const int c = CDW_BASE_R(at, r);
+        const float4 q = SP[r * A + at];
+        X[c] = q.x; X[c + kR] = q.y; X[c + 2 * kR] = q.z;
+        if (with_vel) {
+            const float4 w = SV[r * A + at];
+            V[c] = w.x; V[c + kR] = w.y; V[c + 2 * kR] = w.z;
+        } else {
+            V[c] = 0.f; V[c + kR] = 0.f; V[c + 2 * kR] = 0.f;
+        }
+    }
+    __syncthreads();  // the position / velocity staging (which overlaps force copy 0) is dead
+    if (with_f) {
+        for (int idx = tid; idx < count * A; idx += nt) {
+            const int at = idx / count, r = idx - at * count;
+            const int c = CDW_BASE_R(at, r);
+            const float4 g = SF[r * A + at];
+            Fc[c] = g.x; Fc[c + kR] = g.y; Fc[c + 2 * kR] = g.z;
+        }
+    }
+    __syncthreads();
+}
+
 // Two register budgets: teams of <= 4 lanes run 128-thread CTAs, three of which must be co-resident for a batch of
 // 10^4 replicas to run as one wave (<= 170 registers); teams of 8 run 256-thread CTAs (<= 128 registers, two per SM).
 #ifndef CDW_MINBLOCKS_SMALL
@@ -115,10 +180,18 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_propagate_kernel(SysDev s, Pro
     }
     LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
     unsigned long long my_min = ~0ull;
+    __shared__ __align__(8) unsigned long long row_bar;
+    const bool bulk_rows = sh.bulk != 0;
+    unsigned row_parity = 0;
+    if (bulk_rows) {
+        if (threadIdx.x == 0) init_table_barrier(&row_bar);
+        __syncthreads();
+    }
     for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
         const long long left = a.n - p0;
         const int count = left < kR ? (int)left : kR;
-        cta_load_rows(s, a, smem, L, sw, p0, count, true);
+        if (bulk_rows) { cta_load_rows_bulk(s, a, smem, L, sw, p0, count, &row_bar, row_parity & 1u); ++row_parity; }
+        else cta_load_rows(s, a, smem, L, sw, p0, count, true);
         if (tables_in_flight) {
             wait_tables(&table_bar, 0);
             tables_in_flight = false;
@@ -160,8 +233,14 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_lookahead_kernel(SysDev s, Pro
     LaneMem M = lane_pointers(L, smem, T_, threadIdx.x);
     const bool have_next = a.have_next != 0;
     unsigned parity = 0;
-    if (threadIdx.x == 0) init_table_barrier(&table_bar);
-    __syncthreads();  // the barrier is initialised before anyone polls it
+    __shared__ __align__(8) unsigned long long row_bar;
+    const bool bulk_rows = sh.bulk != 0;
+    unsigned row_parity = 0;
+    if (threadIdx.x == 0) {
+        init_table_barrier(&table_bar);
+        if (bulk_rows) init_table_barrier(&row_bar);
+    }
+    __syncthreads();  // the barriers are initialised before anyone polls them
     for (long long p0 = (long long)blockIdx.x * kR; p0 < a.n; p0 += (long long)gridDim.x * kR) {
         const long long left = a.n - p0;
         const int count = left < kR ? (int)left : kR;
@@ -170,7 +249,8 @@ __global__ void __launch_bounds__(MAXT, MINB) smc_lookahead_kernel(SysDev s, Pro
         } else {
             build_tables(s, T, a.lambda, a.kT, true);
         }
-        cta_load_rows(s, a, smem, L, sw, p0, count, true);
+        if (bulk_rows) { cta_load_rows_bulk(s, a, smem, L, sw, p0, count, &row_bar, row_parity & 1u); ++row_parity; }
+        else cta_load_rows(s, a, smem, L, sw, p0, count, true);
         if (a.tables) { wait_tables(&table_bar, parity & 1u); ++parity; }
         const bool valid = M.rid < count;
         M.mask = __ballot_sync(0xffffffffu, valid);
@@ -202,6 +282,7 @@ static Shape pick_shape(const SysDev& dev, bool forces, long long n, int sms, in
     Shape sh;
     sh.R = 32;
     sh.metro = 0;
+    sh.bulk = 0;
     if (env && atoi(env) > 0) {
         sh.T = atoi(env);
     } else if (pinned > 0) {
@@ -242,6 +323,11 @@ static int launch(const cdw_system* sys, PropArgs& a, LaunchKind kind, cudaStrea
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
     Shape sh = pick_shape(sys->dev, forces, a.n, sms, forces ? sys->team : 0);
     for (unsigned long long w = a.program; w & 15ull; w >>= 4) sh.metro |= (w & 15ull) == CDW_STEP_OPEN;
+    static const bool diag_local = getenv("CDW_DIAG_LOCAL_ROWS") != nullptr;
+    if (diag_local && a.peer_pos && a.n_per_rank > 0) a.diag_local_rank = (int)(a.gid0 / a.n_per_rank) + 1;
+    static const char* bulk_env = getenv("CDW_BULK_ROWS");   // 0: never, 1: always (where possible), unset: rows that may live on a peer GPU
+    const bool bulk_ok = forces && sh.T >= 4;
+    sh.bulk = bulk_ok && (bulk_env ? atoi(bulk_env) != 0 : a.peer_pos != nullptr) ? 1 : 0;
     const int nthr = sh.R * sh.T;
     const Layout L = make_layout(sys->dev, forces, sh.R, sh.T, sh.metro != 0);
     const bool small = nthr <= 128;

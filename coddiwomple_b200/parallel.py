@@ -201,6 +201,8 @@ class ShardedSMCEngine:
         if t is not None and t >= 2:
             a = self.stats[t - 1, _lib.STAT_RESAMPLE:]
             b = self.stats[t - 2, _lib.STAT_RESAMPLE:]   # (row 0 is never written: zero, the initial ancestors are the identity)
+        if os.environ.get("CDW_DIAG_NO_BARRIER_WAIT"):   # timing diagnostic only (results are then unordered across ranks)
+            a = b = self.stats[0, _lib.STAT_RESAMPLE:]
         _lib.check(self.lib.cdw_peer_barrier(_lib.ptr(self._peer_flags), C.c_void_p(self._flags.ptr.value), self.rank, self.world,
                                             _lib.ptr(self._epoch_counter), _lib.ptr(self._barrier_status), _lib.ptr(a), _lib.ptr(b),
                                             _lib.current_stream()), "cdw_peer_barrier")

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coddiwomple_b200 import testsystems as ts  # noqa: E402
-from coddiwomple_b200.engine import LangevinParameters, SMCEngine  # noqa: E402
+from coddiwomple_b200.engine import LangevinParameters, SMCEngine, TwistSequence  # noqa: E402
 from coddiwomple_b200.parallel import ShardedSMCEngine  # noqa: E402
 from coddiwomple_b200.system import load_xml  # noqa: E402
 
@@ -31,13 +31,18 @@ def main():
     frames = np.load(os.path.join(root, "tests", "golden", "fluorobenzene_cache.npy"))
     ok = True
     cases = (("multinomial", 0.9999, 4096, 8, "baoab"), ("systematic", 0.9999, 4096, 8, "baoab"), ("multinomial", 0.5, 2048 * world, 12, "baoab"),
-             ("multinomial", 0.9999, 4096, 8, "ula"),
+             ("multinomial", 0.9999, 4096, 8, "ula"), ("multinomial", 0.9999, 4096, 8, "twisted"),
              ("systematic", 0.9999, 1024 * 12 * world, 6, "baoab"))   # (ula: BASELINE configs[3], the Euler-Maruyama proposal, sharded; last: a batch whose per-rank share is launched very differently from the whole)
     for kind, thr, P, T, proposal in cases:
         x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
         seq = ts.relative_alchemical_sequence(T)
+        twist = None
+        if proposal == "twisted":   # controlled SMC: the Euler-Maruyama proposal with a per-iteration quadratic twist (troubleshooting/csmc.py:460-623)
+            r = np.random.RandomState(9)
+            twist = TwistSequence(30.0 * r.rand(T - 1, 13, 3), 2.0 * r.randn(T - 1, 13, 3), c=r.randn(T - 1))
+            proposal = "ula"
         lang = LangevinParameters(timestep=0.0005) if proposal == "ula" else LangevinParameters()
-        sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
+        sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal, twist=twist)
         sharded.anneal(x0[sharded.first:sharded.last])
         if os.environ.get("CDW_CHECK_GRAPH") and proposal == "baoab" and kind == "multinomial" and thr != 0.5:
             eager_cum = sharded.cum.clone()
@@ -53,12 +58,12 @@ def main():
         lab_parts = [torch.empty_like(sharded.local("label")) for _ in range(world)]
         dist.all_gather(lab_parts, sharded.local("label").contiguous())
         if rank == 0:
-            single = SMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal)
+            single = SMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal, twist=twist)
             single.anneal(x0)
             e = single.ensemble
             same = (torch.equal(torch.cat(pos_parts), e.pos[e.cur]) and torch.equal(torch.cat(vel_parts), e.vel[e.cur]) and
                     torch.equal(torch.cat(lab_parts), e.labels) and torch.equal(sharded.cum, e.cum) and torch.equal(sharded.stats, single.stats))
-            print(f"[multi_gpu_check] world={world} {proposal} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
+            print(f"[multi_gpu_check] world={world} {proposal}{' + twist' if twist is not None else ''} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
                   f"resampled at {sharded.resampled_iterations()} FE={sharded.free_energy():.6f}", flush=True)
             ok &= bool(same) and len(sharded.resampled_iterations()) > 0 or (thr == 0.5 and bool(same))
         sharded.close()

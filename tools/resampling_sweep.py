@@ -13,6 +13,15 @@ from coddiwomple_b200 import _lib, kernels  # noqa: E402
 
 lib = _lib.load()
 st = _lib.current_stream()
+if "--l2-fetch" in sys.argv:   # experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes) for the random-row gathers
+    import ctypes
+    import glob
+    torch.zeros(1, device="cuda")
+    rt = ctypes.CDLL(glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))[0])
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(sys.argv[sys.argv.index("--l2-fetch") + 1])))
+    got = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(got), 5)
+    print(f"# cudaLimitMaxL2FetchGranularity: rc {rc}, now {got.value} bytes", file=sys.stderr)
 
 
 def timed(fn, reps):
