@@ -330,10 +330,18 @@ __device__ __forceinline__ unsigned long long systematic_target(long long i, dou
     return fixed_target(__dmul_rn(__dadd_rn((double)i, u0), inv_n), total);
 }
 
-__device__ __forceinline__ long long first_slot(unsigned long long c, unsigned long long total, double u0, long long n, double inv_n, double n_over_total) {
+// first(c) = min{i : target(i) >= c}.  In real arithmetic that is ceil(c n / total - u0); the exact forward map differs from the real one by
+// less than n 2^-50 slots (two roundings and the 53-bit truncation of (i + u0) / n, three roundings of the estimate), so the estimate IS the
+// answer unless it lies within `margin` = n 2^-48 of an integer — only then (a few items in 10^7) the exact map is walked.
+__device__ __forceinline__ long long first_slot(unsigned long long c, unsigned long long total, double u0, long long n, double inv_n, double n_over_total,
+                                                double margin) {
     if (c == 0) return 0;
-    long long i = (long long)ceil((double)c * n_over_total - u0);
+    const double x = (double)c * n_over_total - u0;
+    const double up = ceil(x);
+    long long i = (long long)up;
     i = i < 0 ? 0 : (i > n ? n : i);
+    const double d = up - x;
+    if (d > margin && d < 1.0 - margin) return i;
     while (i > 0 && systematic_target(i - 1, u0, inv_n, total) >= c) --i;
     while (i < n && systematic_target(i, u0, inv_n, total) < c) ++i;
     return i;
@@ -371,6 +379,7 @@ __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __r
     const double u0 = EMIT == EMIT_ANCESTORS ? (em.gen.gen ? philox_uniform53(em.gen.seed, em.gen.stream_id, 0) : em.uniforms[0]) : 0.0;
     const double inv_n = __ddiv_rn(1.0, (double)n);
     const double n_over_total = EMIT ? (double)n / (double)total : 0.0;
+    const double margin = (double)n * 3.5527136788005009e-15 + 1e-12;   // n 2^-48 (first_slot)
     if (EMIT == EMIT_ANCESTORS && em.gen.gen && em.gen.uniforms_out && blockIdx.x == 0 && threadIdx.x == 0) em.gen.uniforms_out[0] = u0;
     if (EMIT && threadIdx.x == 0) n_heavy = 0;
     const int k = (int)ws.hdr[WS_SHIFT];
@@ -403,11 +412,11 @@ __global__ void __launch_bounds__(kBlock) cdf_tile_scan_kernel(const double* __r
                 if (i0 + j < n) cdf[i0 + j] = q[j] + off;
         }
         if (EMIT) {
-            long long lo = first_slot(off, total, u0, n, inv_n, n_over_total);
+            long long lo = first_slot(off, total, u0, n, inv_n, n_over_total, margin);
 #pragma unroll
             for (int j = 0; j < kItems; ++j) {
                 const long long item = i0 + j;
-                const long long hi = item < n ? first_slot(q[j] + off, total, u0, n, inv_n, n_over_total) : lo;
+                const long long hi = item < n ? first_slot(q[j] + off, total, u0, n, inv_n, n_over_total, margin) : lo;
                 if (hi - lo > kHeavyRange) {
                     const int slot = atomicAdd(&n_heavy, 1);
                     if (slot < kHeavyList) { heavy[3 * slot] = item; heavy[3 * slot + 1] = lo; heavy[3 * slot + 2] = hi; }

@@ -583,6 +583,44 @@ class SMCEngine:
         self.ensemble.materialize()
         return self
 
+    def step_with_host_hooks(self, t, decide=None, draw_ancestors=None):
+        """Iteration t with the caller's own Python observable / threshold / resampler in the loop (the reference's pluggable
+        `observable(particles, incremental_works)`, `threshold(value)` and `Resampler._resample(cumulative_works, num_resamples)`,
+        resamplers.py:61-133, 202-216): the particles stay on the device and the propagate launch is the usual one; only the 8-byte
+        works travel to the host and only the decision and the ancestors travel back (one host synchronisation per iteration).
+          decide(cum, inc) -> bool                    cum, inc: host arrays of the cumulative works BEFORE this iteration and its increments
+          draw_ancestors(W) -> indices                W = cum + inc; None: the engine's own resampler kind
+        Bookkeeping as the reference: resampled -> cum[i] = -logsumexp(-W) + log P (resamplers.py:107,196-197), else cum[i] = W[i]."""
+        if self.lookahead:
+            raise ValueError("host hooks need the sequential loop (SMCEngine(..., lookahead=False))")
+        e = self.ensemble
+        self.propagate(t)
+        cum_before = e.cum.cpu().numpy()
+        inc = e.inc.cpu().numpy()
+        wanted = True if decide is None else bool(decide(cum_before, inc))
+        row = self.stats[t]
+        if draw_ancestors is None:
+            # the library's resampler with the decision forced: threshold < 0 always resamples, 0 never does (nESS > 0)
+            e.resample_fused(row, self.kind, -1.0 if wanted else 0.0, self.resample_seed, t)
+        else:
+            e.weight_stats(row, -1.0 if wanted else 0.0)     # normaliser, nESS (and the forced decision) -> stats[t]
+            e.wmin_key.fill_(-1)
+            out = e.anc_bufs[1 - e.anc_cur]
+            if wanted:
+                idx = np.asarray(draw_ancestors(cum_before + inc), dtype=np.int64).reshape(-1)
+                if idx.shape[0] != e.P or idx.min() < 0 or idx.max() >= e.P:
+                    raise ValueError("the resampler must return one ancestor index in [0, P) per particle")
+                out.copy_(torch.from_numpy(idx.astype(np.int32)))
+                e.cum.copy_(row[_lib.STAT_MEAN].expand(e.P))
+            else:
+                out.copy_(torch.arange(e.P, dtype=torch.int32, device=e.device))
+                e.cum.copy_(e.W)
+            e.anc_cur = 1 - e.anc_cur
+            e.pending_gather = True
+        self._after_resample(t)
+        self._record_lineage(t)
+        return wanted
+
     def run(self):
         for t in range(1, self.T):
             self.step(t)

@@ -299,6 +299,10 @@ def test_K3_large_properties(gpu, n):
     np.testing.assert_array_equal(u[:100000].cpu().numpy(), rng.uniforms53(6, n, stream=1)[:100000])
     am = kernels.resample_indices(W, u, kind="multinomial").cpu().numpy()
     np.testing.assert_array_equal(am, resampling.ancestors_fixed(W.cpu().numpy(), u.cpu().numpy()))
+    # the slot ranges the scan emits (floating-point estimate, exact forward map only near an integer) against the exact integer search
+    for u0 in (0.7, 0.0, 1.0 - 2.0 ** -53):
+        a = kernels.resample_indices(W, torch.tensor([u0], dtype=torch.float64), kind="systematic").cpu().numpy()
+        np.testing.assert_array_equal(a, resampling.ancestors(W.cpu().numpy(), None, kind="systematic", u0=u0))
 
 
 def test_K3b_gather_bit_exact(gpu):

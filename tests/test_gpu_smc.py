@@ -524,3 +524,59 @@ def test_tiny_ensembles(P):
     assert np.all(stats[1:, _lib.STAT_NESS] > 0) and np.all(stats[1:, _lib.STAT_NESS] <= 1 + 1e-12)
     if P == 1:
         np.testing.assert_allclose(stats[1:, _lib.STAT_NESS], 1.0, rtol=1e-12)
+
+
+def test_SMC_with_the_callers_own_observable_threshold_resampler_and_termination():
+    """`SMC()` with pluggable pieces, as the reference's interfaces allow (resamplers.py:61-133, 202-216; utils.py:41-72;
+    distribution_factories.py:134-148): a custom observable / threshold pair, a custom `_resample`, and `termination_parameters` that end
+    the loop early.  The particles stay on the device; the custom rule that restates the stock one reproduces the device-decided run bit for bit."""
+    from coddiwomple_b200.distribution_factories import ProposalFactory, TargetFactory
+    from coddiwomple_b200.openmm.integrators import OMMLI
+    from coddiwomple_b200.openmm.propagators import OMMBIP
+    from coddiwomple_b200.openmm.states import OpenMMParticleState, OpenMMPDFState, RelativeAlchemicalState
+    from coddiwomple_b200.resamplers import MultinomialResampler, Resampler
+    from coddiwomple_b200.smc import SMC
+    from coddiwomple_b200.utils import nESS, vanilla_floor_threshold
+    seq = ts.relative_alchemical_sequence(8)
+    P = 512
+    x0 = cache_frames()[np.random.RandomState(4).randint(0, 151, P)]
+    pdf = OpenMMPDFState(system=system_xml("fluorobenzene"), alchemical_composability=RelativeAlchemicalState, pressure=None)
+
+    def run(observable, threshold, resampler, term=None, **kw):
+        prop = OMMBIP(pdf, OMMLI(temperature=300.0, collision_rate=1.0, timestep=0.002))
+        return SMC(TargetFactory(pdf, list(seq), termination_parameters=term), ProposalFactory(list(seq), prop), P, None, resampler,
+                   initial_positions=x0, observable=observable, threshold=threshold, seed=11,
+                   state_factory=lambda x, v: OpenMMParticleState(positions=x, velocities=v), **kw)
+
+    stock = run(nESS, vanilla_floor_threshold, MultinomialResampler(), floor_threshold=0.9999)
+    calls = []
+
+    def my_observable(particles, incremental_works, **kwargs):      # the reference's nESS (utils.py:41-64), restated in numpy
+        w = -(np.array([p.cumulative_work for p in particles]) + np.asarray(incremental_works))
+        w = np.exp(w - np.logaddexp.reduce(w))
+        calls.append(len(particles))
+        return 1.0 / (len(w) * np.sum(w ** 2))
+
+    custom = run(my_observable, lambda value, **kw: not (value > 0.9999), MultinomialResampler())
+    assert len(calls) == 7 and set(calls) == {P}
+    assert custom.engine.resampled_iterations() == stock.engine.resampled_iterations() and len(stock.engine.resampled_iterations()) > 0
+    np.testing.assert_array_equal(custom.cumulative_works, stock.cumulative_works)                 # same decisions, same kernels: same bits
+    np.testing.assert_array_equal(custom.engine.ensemble.positions.cpu().numpy(), stock.engine.ensemble.positions.cpu().numpy())
+
+    class EveryOther(Resampler):                                     # a resampler of the caller's own: particle i takes over particle i - (i % 2)
+        def _resample(self, cumulative_works, num_resamples, **kwargs):
+            self.seen = np.array(cumulative_works, dtype=np.float64)
+            return [i - (i % 2) for i in range(num_resamples)]
+
+    mine = EveryOther()
+    out = run(None, None, mine)                                      # observable None: resample at every iteration (resamplers.py:90-92)
+    labels = out.engine.ensemble.labels.cpu().numpy()
+    np.testing.assert_array_equal(labels, np.arange(P) - (np.arange(P) % 2))
+    mean = -(np.logaddexp.reduce(-mine.seen) - np.log(P))            # every particle carries the normaliser of the last resampling
+    np.testing.assert_allclose(out.cumulative_works, mean, rtol=1e-12)
+    assert out.engine.resampled_iterations() == list(range(1, 8)) and mine.resampling_logger == list(range(1, 8))
+    np.testing.assert_array_equal(out[3].state.positions, out[2].state.positions)
+    assert out[3].ancestry[-1] == 2 and len(out[3].incremental_works) == 7
+
+    early = run(nESS, vanilla_floor_threshold, MultinomialResampler(), term=seq[4])
+    assert early.engine.T == 5 and all(p.iteration == 4 for p in early[:3])
