@@ -178,15 +178,29 @@ __global__ void __launch_bounds__(kBlock) weight_stats_kernel(const double* __re
     const double two62 = 4611686018427387904.0;
     u128 s1 = {0ull, 0ull}, s2 = {0ull, 0ull};
     const long long n2 = n >> 1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-        const double2 v = __ldg((const double2*)w + i);
-        const double ea = det_exp(CDW_ADD(wmin, -v.x)), eb = det_exp(CDW_ADD(wmin, -v.y));
-        const unsigned long long qa = __double2ull_rn(CDW_MUL(ea, two62)), qb = __double2ull_rn(CDW_MUL(eb, two62));
-        ((ulonglong2*)ws.q)[i] = make_ulonglong2(qa, qb);
-        add128(s1, qa); add128(s1, qb);
-        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(ea, ea), two62)));
-        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(eb, eb), two62)));
+    // two 16-byte loads in flight and four independent exponentials per trip: the polynomial is a chain of 26 dependent (unfused, for
+    // bit-reproducibility) fp64 operations, which one element pair alone cannot keep the pipe busy with
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#define CDW_STATS_PAIR(V, I)                                                                                                    \
+    {                                                                                                                           \
+        const double ea = det_exp(CDW_ADD(wmin, -(V).x)), eb = det_exp(CDW_ADD(wmin, -(V).y));                                  \
+        const unsigned long long qa = __double2ull_rn(CDW_MUL(ea, two62)), qb = __double2ull_rn(CDW_MUL(eb, two62));            \
+        ((ulonglong2*)ws.q)[(I)] = make_ulonglong2(qa, qb);                                                                     \
+        add128(s1, qa); add128(s1, qb);                                                                                         \
+        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(ea, ea), two62)));                                                           \
+        add128(s2, __double2ull_rn(CDW_MUL(CDW_MUL(eb, eb), two62)));                                                           \
     }
+    for (; i + stride < n2; i += 2 * stride) {
+        const double2 v0 = __ldg((const double2*)w + i), v1 = __ldg((const double2*)w + i + stride);
+        CDW_STATS_PAIR(v0, i)
+        CDW_STATS_PAIR(v1, i + stride)
+    }
+    for (; i < n2; i += stride) {
+        const double2 v = __ldg((const double2*)w + i);
+        CDW_STATS_PAIR(v, i)
+    }
+#undef CDW_STATS_PAIR
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const double e = det_exp(CDW_ADD(wmin, -w[n - 1]));
         const unsigned long long q = __double2ull_rn(CDW_MUL(e, two62));
