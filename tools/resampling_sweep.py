@@ -72,7 +72,7 @@ def run(n, s, A=13, reps=5, with_vel=True):
     rows = 2 if with_vel else 1
     gb = lambda b, ms: b / (ms * 1e-3) / 1e9
     return dict(n=n, s=s, nESS=ness, ms=dict(stats=t_stats, systematic=t_sys, multinomial=t_mul, gather_multinomial=t_gm, gather_systematic=t_gs),
-                gbs=dict(stats=gb(n * 40.0, t_stats), scan_search_systematic=gb(n * 28.0, t_sys), scan_search_multinomial=gb(n * 36.0, t_mul),
+                gbs=dict(stats=gb(n * 24.0, t_stats), scan_search_systematic=gb(n * 28.0, t_sys), scan_search_multinomial=gb(n * 36.0, t_mul),
                          gather_multinomial=gb(n * (2 * rows * A * 16.0 + 28), t_gm), gather_systematic=gb(n * (2 * rows * A * 16.0 + 28), t_gs)),
                 particles_per_s=dict(multinomial=n / ((t_stats + t_mul + t_gm) * 1e-3), systematic=n / ((t_stats + t_sys + t_gs) * 1e-3)))
 
