@@ -488,7 +488,59 @@ def sharded_resampling(torch, dist, _lib, world, rank, A):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms.append(float(t.item()))
         out[name] = {"ms": float(np.min(ms)), "particles_per_s": n / (np.min(ms) * 1e-3)}
+        out[name].update(_peer_gather(torch, dist, _lib, lib, world, rank, n_loc, A, anc, st))
+    out["gather_bytes_model"] = "per particle: pos + vel rows read (NVLink when the ancestor lives on a peer) and written, 2 x (2 x A x 16) + 28 B (SURVEY.md 8(d))"
     return out
+
+
+def _peer_gather(torch, dist, _lib, lib, world, rank, n_loc, A, anc, st):
+    """K3b over peer memory (cdw_gather_particles_peer): this rank's n_loc slots pull the rows of their GLOBAL ancestors from the owning ranks'
+    buffers through CUDA-IPC peer-mapped pointers.  GB/s per GPU = algorithmic bytes of the rank's share / max-over-ranks time."""
+    import ctypes as C
+    from coddiwomple_b200.parallel import _IpcBuffer
+    bufs = {k: _IpcBuffer(lib, shape, dt) for k, shape, dt in (("pos", (n_loc, A, 4), torch.float32), ("vel", (n_loc, A, 4), torch.float32),
+                                                                ("aux", (n_loc,), torch.float64), ("label", (n_loc,), torch.int32))}
+    opened, peers = [], {}
+    for k, b in bufs.items():
+        b.tensor.copy_(torch.randn(b.shape, device="cuda").to(b.dtype) if b.dtype != torch.int32 else torch.arange(n_loc, dtype=torch.int32, device="cuda"))
+        handles = [None] * world
+        dist.all_gather_object(handles, b.handle())
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                ptrs.append(b.ptr.value)
+            else:
+                o = C.c_void_p()
+                _lib.check(lib.cdw_ipc_open_handle((C.c_ubyte * 64).from_buffer_copy(h), C.byref(o)), "cdw_ipc_open_handle")
+                opened.append(o.value)
+                ptrs.append(o.value)
+        peers[k] = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
+    pos_o, vel_o = torch.empty(n_loc, A, 4, device="cuda"), torch.empty(n_loc, A, 4, device="cuda")
+    aux_o, lab_o = torch.empty(n_loc, dtype=torch.float64, device="cuda"), torch.empty(n_loc, dtype=torch.int32, device="cuda")
+    mine = anc[rank * n_loc:(rank + 1) * n_loc].contiguous()
+    remote = float(((mine // n_loc) != rank).double().mean().item())
+
+    def go():
+        _lib.check(lib.cdw_gather_particles_peer(_lib.ptr(peers["pos"]), _lib.ptr(peers["vel"]), _lib.ptr(peers["aux"]), _lib.ptr(peers["label"]), world, n_loc,
+                                                 _lib.ptr(mine), _lib.ptr(pos_o), _lib.ptr(vel_o), _lib.ptr(aux_o), _lib.ptr(lab_o), n_loc, A, st), "cdw_gather_particles_peer")
+    go(); torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); go(); e1.record(); e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+    dist.barrier(); torch.cuda.synchronize()
+    for o in opened:
+        lib.cdw_ipc_close_handle(C.c_void_p(o))
+    dist.barrier()
+    for b in bufs.values():
+        b.free()
+    best = float(np.min(ms))
+    per_gpu = n_loc * (2 * 2 * A * 16.0 + 28) / (best * 1e-3) / 1e9
+    return {"gather_ms": best, "gather_gbs_per_gpu": per_gpu, "gather_gbs_total": per_gpu * world, "gather_remote_fraction": remote}
 
 
 def resampling_sweep(torch, kernels, _lib, n, A, hbm_peak):
