@@ -52,10 +52,13 @@ def algorithmic_flops(spec, n_steps=1):
     """SURVEY.md §8(d) flop convention, frozen: per energy+force evaluation
     31 N_bond + 75 N_angle + 130 N_torsion + 50 N_pair + 30 N_pair_softcore; integrator 60 A and SHAKE/RATTLE 90 N_c per step.
     One SMC iteration = 2 evaluations + n_steps integrator steps (+ 1 evaluation per extra step)."""
+    with open(os.path.join(ROOT, "bench", "roofline.json")) as fh:   # the frozen constants (SURVEY.md §8(d))
+        k = json.load(fh)
+    t, st = k["flop_per_term"], k["flop_per_step"]
     c = spec.counts()
     n_sc = int((spec.pair_sc_class > 0).sum())
-    f_eval = 31 * c["bonds"] + 75 * c["angles"] + 130 * c["torsions"] + 50 * c["pairs"] + 30 * n_sc
-    per_step = 60 * c["atoms"] + 90 * c["constraints"]
+    f_eval = t["bond"] * c["bonds"] + t["angle"] * c["angles"] + t["torsion"] * c["torsions"] + t["pair"] * c["pairs"] + t["pair_softcore_extra"] * n_sc
+    per_step = st["per_atom"] * c["atoms"] + st["per_constraint"] * c["constraints"]
     return dict(f_eval=f_eval, per_iteration=(1 + n_steps) * f_eval + n_steps * per_step)
 
 
