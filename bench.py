@@ -433,9 +433,13 @@ def config4_runs(torch, dist, world, rank, xml, langevin):
     from coddiwomple_b200.engine import TwistSequence
     r = np.random.RandomState(9)
     twist = TwistSequence(5.0 * r.rand(N_LAMBDA - 1, 13, 3), 0.5 * r.randn(N_LAMBDA - 1, 13, 3), c=np.zeros(N_LAMBDA - 1))   # controlled SMC (csmc.py:460-747)
-    for name, lang in (("baoab", langevin), ("ula", LangevinParameters(timestep=0.0005)), ("ula_twisted", LangevinParameters(timestep=0.0005))):
+    G = r.randn(N_LAMBDA - 1, 39, 39) / np.sqrt(39.0)
+    dense = TwistSequence.dense(2.0 * G @ np.swapaxes(G, 1, 2), 0.5 * r.randn(N_LAMBDA - 1, 39))                              # the same with full matrices A_t
+    twists = {"ula_twisted": twist, "ula_twisted_dense": dense}
+    for name, lang in (("baoab", langevin), ("ula", LangevinParameters(timestep=0.0005)), ("ula_twisted", LangevinParameters(timestep=0.0005)),
+                       ("ula_twisted_dense", LangevinParameters(timestep=0.0005))):
         proposal = "baoab" if name == "baoab" else "ula"
-        eng = ShardedSMCEngine(xml, P, seq, langevin=lang, seed=0, resample_seed=1, proposal=proposal, twist=twist if name == "ula_twisted" else None)
+        eng = ShardedSMCEngine(xml, P, seq, langevin=lang, seed=0, resample_seed=1, proposal=proposal, twist=twists.get(name))
         rows = positions_to_rows(frames[np.random.RandomState(11 + rank).randint(0, len(frames), eng.P_loc)])
         eng.capture(rows)
         for _ in range(2):

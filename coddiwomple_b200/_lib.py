@@ -41,7 +41,13 @@ class SystemDesc(C.Structure):
 class LangevinParams(C.Structure):
     """struct cdw_langevin_params (include/cdw.h)."""
     _fields_ = [("dt", C.c_double), ("gamma", C.c_double), ("kT", C.c_double), ("constraint_tol", C.c_double),
-                ("n_steps", C.c_int32), ("flags", C.c_uint32), ("splitting", C.c_uint64), ("trial_counts", C.c_void_p), ("twist", C.c_void_p)]
+                ("n_steps", C.c_int32), ("flags", C.c_uint32), ("splitting", C.c_uint64), ("trial_counts", C.c_void_p), ("twist", C.c_void_p), ("dense_twist", C.c_void_p)]
+
+
+class DenseTwist(C.Structure):
+    """struct cdw_dense_twist (include/cdw.h): one iteration's dense quadratic twist, device pointers."""
+    _fields_ = [("theta", C.c_void_p), ("chol", C.c_void_p), ("A", C.c_void_p), ("b", C.c_void_p), ("beta", C.c_void_p),
+                ("logk0", C.c_double), ("cd", C.c_double), ("scratch", C.c_void_p)]
 
 
 class StaticCache(C.Structure):

@@ -579,6 +579,11 @@ struct PropArgs {
     unsigned long long program; int* trial_counts;  // [P][2] (trials, accepted) of the Metropolised block, may be NULL
     // quadratic twist of the Euler-Maruyama proposal (cdw_langevin_params.twist; troubleshooting/csmc.py:460-623): a[3A] b[3A] c d, or NULL
     const double* twist;
+    // dense, position-independent twist (cdw_dense_twist, include/cdw.h): Theta = Sigma~ S^-1, the lower Cholesky factor of Sigma~, A, b,
+    // beta = Sigma~ b (all [D][D] / [D], D = 3 A, row-major), logk0 = 0.5 log det Theta + 0.5 b^T Sigma~ b - c - d, cd = c + d, and a
+    // scratch area of 2 D doubles per particle of the call
+    const double* tw_theta; const double* tw_chol; const double* tw_A; const double* tw_b; const double* tw_beta;
+    double tw_logk0, tw_cd; double* tw_scratch;
     int diag_local_rank;  // timing diagnostic (CDW_DIAG_LOCAL_ROWS, results are wrong): rank + 1 = read every ancestor's row from this rank
 };
 
@@ -706,6 +711,84 @@ CDW_HD void lane_noise(const SysDev& s, const Tables& T, const LaneMem& M, doubl
     }
 }
 
+// ---- dense twist of the Euler-Maruyama move (troubleshooting/csmc.py:460-623 with a full matrix A_t; the uncontrolled kernel is N(f, S),
+// S = diag(s), s = 2 tau per coordinate, f = x + tau beta F).  With Sigma~ = (S^-1 + 2 A)^-1 and Theta = Sigma~ S^-1 (Theta_t, :460-478):
+//     x' ~ N(Theta f - Sigma~ b, Sigma~)                                          twisted_forward_proposal (:503-528)
+//     log K_t(psi_t)(x) = 0.5 log det Theta - (Theta f).(A f) - b.(Theta f) + 0.5 b^T Sigma~ b - c - d
+// which is twisted_forward_log_normalizer (:531-561) with the two O(|f|^2 / s) quadratic forms, whose difference it is, expanded
+// analytically (Sigma~ = S - 2 Sigma~ A S): nothing cancels in floating point.  The team splits the rows of the three matrix-vector products;
+// vectors travel through the per-particle scratch (2 D doubles).  Returns this lane's share of the x-dependent part of log K; x_old is left in
+// the v column, the unrounded-then-fp32 x' in the x column (position constraints are the caller's).
+CDW_HD double lane_twisted_move_dense(const SysDev& s, const Tables& T, const LaneMem& M, const PropArgs& a, long long p, unsigned long long gid,
+                                      uint32_t step, double inv_kT) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms, D = 3 * A;
+    double* S0 = a.tw_scratch + (size_t)p * 2 * D;   // f, later xi
+    double* S1 = S0 + D;                              // the proposal mean
+    for (int at = tl; at < A; at += T_) {
+        const int b = CDW_BASE(at);
+        const double tau = 0.5 * a.kT * a.dt * a.dt * T.inv_m[at];
+        const d3 x = ld3(M.x, b);
+        st3(M.v, b, x);
+        const d3 f = x + (tau * inv_kT) * ld3(M.f, b);
+        S0[3 * at] = f.x; S0[3 * at + 1] = f.y; S0[3 * at + 2] = f.z;
+    }
+    CDW_TEAM_SYNC(M);
+    double lk = 0.0;
+    for (int at = tl; at < A; at += T_) {
+        for (int k = 0; k < 3; ++k) {
+            const int i = 3 * at + k;
+            const double* th = a.tw_theta + (size_t)i * D;
+            const double* am = a.tw_A + (size_t)i * D;
+            double u = 0.0, w = 0.0;
+            for (int j = 0; j < D; ++j) { const double fj = S0[j]; u = fma(th[j], fj, u); w = fma(am[j], fj, w); }
+            lk -= u * w + a.tw_b[i] * u;
+            S1[i] = u - a.tw_beta[i];
+        }
+    }
+    CDW_TEAM_SYNC(M);   // every lane is done with f
+    for (int at = tl; at < A; at += T_) {
+        double z0, z1, z2;
+        normals3(a.seed, gid, step, (uint32_t)at, CDW_KIND_ULA, z0, z1, z2);
+        S0[3 * at] = z0; S0[3 * at + 1] = z1; S0[3 * at + 2] = z2;
+    }
+    CDW_TEAM_SYNC(M);
+    for (int at = tl; at < A; at += T_) {
+        double xn[3];
+        for (int k = 0; k < 3; ++k) {
+            const int i = 3 * at + k;
+            const double* L = a.tw_chol + (size_t)i * D;
+            double acc = S1[i];
+            for (int j = 0; j <= i; ++j) acc = fma(L[j], S0[j], acc);
+            xn[k] = acc;
+        }
+        st3(M.x, CDW_BASE(at), mk3(xn[0], xn[1], xn[2]));
+    }
+    return lk;
+}
+
+// phi_t(x') - c - d = x'^T A x' + b^T x' of the dense twist: this lane's rows (twisted_t_log_weight, csmc.py:593-623)
+CDW_HD double lane_twist_phi_dense(const SysDev& s, const LaneMem& M, const PropArgs& a) {
+    CDW_UNPACK(M);
+    const int A = s.n_atoms, D = 3 * A;
+    double phi = 0.0;
+    for (int at = tl; at < A; at += T_) {
+        const d3 xi = ld3(M.x, CDW_BASE(at));
+        const double xk[3] = {xi.x, xi.y, xi.z};
+        for (int k = 0; k < 3; ++k) {
+            const int i = 3 * at + k;
+            const double* am = a.tw_A + (size_t)i * D;
+            double w = 0.0;
+            for (int aj = 0; aj < A; ++aj) {
+                const d3 xj = ld3(M.x, CDW_BASE(aj));
+                w = fma(am[3 * aj], xj.x, w); w = fma(am[3 * aj + 1], xj.y, w); w = fma(am[3 * aj + 2], xj.z, w);
+            }
+            phi += xk[k] * (w + a.tw_b[i]);
+        }
+    }
+    return phi;
+}
+
 // K4 body (+ first half of K2) for the replica already staged in this team's column.
 // Returns the order-preserving key of W[p] (for the running min).
 //
@@ -803,7 +886,8 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                 }
                 CDW_TEAM_SYNC(M);  // every constraint vector is taken before any lane moves an atom
                 double lk = 0.0;
-                for (int at = tl; at < A; at += T_) {
+                if (a.tw_theta) lk = lane_twisted_move_dense(s, T, M, a, p, gid, (uint32_t)(a.step0 + st), inv_kT);
+                else for (int at = tl; at < A; at += T_) {
                     const int b = CDW_BASE(at);
                     const double tau = 0.5 * a.kT * a.dt * a.dt * T.inv_m[at];
                     double z0, z1, z2;
@@ -832,6 +916,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                     }
                 }
                 if (a.twist) twist_lk = team_sum(M, lk) - a.twist[6 * A] - a.twist[6 * A + 1];
+                if (a.tw_theta) twist_lk = team_sum(M, lk) + a.tw_logk0;
                 CDW_TEAM_SYNC(M);
                 if (s.n_cons) lane_shake(s, T, M, a.tol, 0.0);
             }
@@ -859,6 +944,7 @@ CDW_HD unsigned long long lane_step(const SysDev& s, const Tables& T, const Lane
                 phi = team_sum(M, phi) + a.twist[6 * A] + a.twist[6 * A + 1];
                 proposal -= twist_lk + phi;
             }
+            if (!fwd && a.tw_theta) proposal -= twist_lk + (team_sum(M, lane_twist_phi_dense(s, M, a)) + a.tw_cd);
             continue;
         }
         const double ke_before = track ? lane_kinetic(s, T, M) : 0.0;

@@ -451,6 +451,18 @@ static int apply_cache(PropArgs& a, const cdw_static_cache* c, bool sharded, boo
     return CDW_OK;
 }
 
+// copies the dense-twist descriptor of a call into the kernel arguments (validation first)
+static int apply_dense_twist(PropArgs& a, const cdw_langevin_params* prm, bool ula) {
+    const cdw_dense_twist* d = prm->dense_twist;
+    if (!d) return CDW_OK;
+    CDW_REQUIRE(ula, "a twist applies to the Euler-Maruyama proposal only (CDW_FLAG_ULA)");
+    CDW_REQUIRE(!prm->twist && !(prm->flags & CDW_FLAG_TWIST_REFERENCE_NORMALIZER), "dense_twist excludes twist and CDW_FLAG_TWIST_REFERENCE_NORMALIZER");
+    CDW_REQUIRE(d->theta && d->chol && d->A && d->b && d->beta && d->scratch, "cdw_dense_twist: null array");
+    a.tw_theta = d->theta; a.tw_chol = d->chol; a.tw_A = d->A; a.tw_b = d->b; a.tw_beta = d->beta;
+    a.tw_logk0 = d->logk0; a.tw_cd = d->cd; a.tw_scratch = d->scratch;
+    return CDW_OK;
+}
+
 extern "C" int cdw_smc_propagate(const cdw_system* sys, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out, int64_t n,
                                  const int32_t* anc, const double* aux_in, const double* cum_in, const int32_t* label_in, const double* lambda,
                                  const cdw_langevin_params* prm, uint64_t seed, uint64_t step0, int64_t gid0, double* inc_out, double* w_out,
@@ -479,6 +491,7 @@ extern "C" int cdw_smc_propagate_cached(const cdw_system* sys, const float* pos_
     CDW_REQUIRE(ula || !prm->twist, "a twist applies to the Euler-Maruyama proposal only (CDW_FLAG_ULA)");
     PropArgs a = {};
     a.twist = prm->twist;
+    if (int rc = apply_dense_twist(a, prm, ula)) return rc;
     a.pos_in = (const float4*)pos_in; a.vel_in = ula ? nullptr : (const float4*)vel_in; a.pos_out = (float4*)pos_out;
     a.vel_out = ula ? nullptr : (float4*)vel_out;
     a.n = n; a.anc = anc; a.aux_in = aux_in; a.cum_in = cum_in; a.label_in = label_in; a.lambda = lambda;
@@ -510,7 +523,7 @@ static int lookahead_common(const cdw_system* sys, PropArgs& a, const cdw_langev
     CDW_REQUIRE(lambda || sys->dev.n_lambda == 0, "lambda is required");
     CDW_REQUIRE(prm->n_steps >= 0 && prm->dt >= 0.0 && prm->kT > 0.0 && prm->gamma >= 0.0 && prm->constraint_tol > 0.0, "bad Langevin parameters");
     CDW_REQUIRE(!(prm->flags & ~CDW_FLAG_RANDOMIZE_VELOCITIES), "cdw_smc_lookahead: BAOAB moves only (flags other than CDW_FLAG_RANDOMIZE_VELOCITIES are not supported)");
-    CDW_REQUIRE(!prm->twist, "a twist applies to the Euler-Maruyama proposal only (cdw_smc_propagate with CDW_FLAG_ULA)");
+    CDW_REQUIRE(!prm->twist && !prm->dense_twist, "a twist applies to the Euler-Maruyama proposal only (cdw_smc_propagate with CDW_FLAG_ULA)");
     CDW_REQUIRE(force_out, "force_out is required");
     CDW_REQUIRE(prm->n_steps == 0 || (pos_out && vel_out), "pos_out and vel_out are required when n_steps > 0");
     CDW_REQUIRE(!inc_next_out || lambda_next || sys->dev.n_lambda == 0, "lambda_next is required with inc_next_out");
@@ -582,6 +595,7 @@ extern "C" int cdw_smc_propagate_sharded_cached(const cdw_system* sys, const flo
     a.n_per_rank = n_per_rank;
     CDW_REQUIRE(ula || !prm->twist, "a twist applies to the Euler-Maruyama proposal only (CDW_FLAG_ULA)");
     a.twist = prm->twist;
+    if (int rc = apply_dense_twist(a, prm, ula)) return rc;
     a.vel_in = ula ? nullptr : (const float4*)1;  // velocities exist (read through peer_vel); the local pointer itself is never dereferenced
     a.pos_out = (float4*)pos_out; a.vel_out = ula ? nullptr : (float4*)vel_out; a.n = n; a.anc = anc; a.cum_in = cum_in; a.lambda = lambda;
     a.dt = prm->dt; a.gamma = prm->gamma; a.kT = prm->kT; a.tol = prm->constraint_tol; a.n_steps = prm->n_steps; a.flags = prm->flags;

@@ -133,16 +133,25 @@ class LangevinParameters:
 
     def as_struct(self, flags=0, n_steps=None, trial_counts=None, twist=None):
         """`twist`: this iteration's row of a TwistSequence table (device tensor of 6 A + 2 doubles) or None."""
-        return _lib.LangevinParams(self.timestep, self.collision_rate, self.kT, self.constraint_tolerance,
-                                   self.n_steps if n_steps is None else int(n_steps), int(flags), int(getattr(self, "splitting_word", 0)),
-                                   None if trial_counts is None else trial_counts.data_ptr(), None if twist is None else twist.data_ptr())
+        dense = twist if isinstance(twist, _lib.DenseTwist) else None
+        prm = _lib.LangevinParams(self.timestep, self.collision_rate, self.kT, self.constraint_tolerance,
+                                  self.n_steps if n_steps is None else int(n_steps), int(flags), int(getattr(self, "splitting_word", 0)),
+                                  None if trial_counts is None else trial_counts.data_ptr(),
+                                  None if (twist is None or dense is not None) else twist.data_ptr(), None if dense is None else C.addressof(dense))
+        prm._keep = dense   # the descriptor is read when the call is made
+        return prm
 
 
 class TwistSequence:
     """Per-iteration quadratic twists psi_t = exp(-(x^T A_t x + b_t^T x + c_t + d_t)) of the Euler-Maruyama proposal — the `twisting_functions`
-    / `twisting_parameters` of troubleshooting/csmc.py:625-747 for position-independent, DIAGONAL A_t: row t - 1 of the device table holds
-    a[3A] b[3A] c d of iteration t (cdw_langevin_params.twist).  `a`: (T-1, A, 3) in 1/nm^2, `b`: (T-1, A, 3) in 1/nm, `c`, `d`: (T-1,).
-    reference_normalizer=True evaluates the forward log normaliser the way csmc.py:556 literally does (include/cdw.h)."""
+    / `twisting_parameters` of troubleshooting/csmc.py:625-747 for position-independent A_t, b_t.
+
+    Diagonal A_t:  `TwistSequence(a, b, c, d)` with a, b of shape (T-1, A, 3) (1/nm^2, 1/nm); row t - 1 of the device table holds
+                   a[3A] b[3A] c d of iteration t (cdw_langevin_params.twist).
+    Full A_t:      `TwistSequence.dense(A, b, c, d)` with A of shape (T-1, 3A, 3A) (symmetric), b (T-1, 3A); the per-iteration matrices of
+                   cdw_dense_twist (Theta, the Cholesky factor of the proposal covariance, ...) are computed on the host when the engine
+                   binds the sequence to a system and a time step.
+    reference_normalizer=True (diagonal form only) evaluates the forward log normaliser the way csmc.py:556 literally does (include/cdw.h)."""
 
     def __init__(self, a, b, c=None, d=None, reference_normalizer=False, device=None):
         a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
@@ -153,8 +162,64 @@ class TwistSequence:
         d = np.zeros(n) if d is None else np.asarray(d, dtype=np.float64).reshape(n)
         self.n_iterations, self.n_atoms = n, a.shape[1]
         self.reference_normalizer = bool(reference_normalizer)
+        self.is_dense = False
         self.host = np.concatenate([a.reshape(n, -1), b.reshape(n, -1), c[:, None], d[:, None]], axis=1)
         self.table = None if device is None else torch.from_numpy(self.host).to(device)
+
+    @classmethod
+    def dense(cls, A, b, c=None, d=None):
+        A, b = np.asarray(A, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        if A.ndim != 3 or A.shape[1] != A.shape[2] or A.shape[1] % 3 or b.shape != A.shape[:2]:
+            raise ValueError("A must have shape (n_iterations, 3 n_atoms, 3 n_atoms) and b (n_iterations, 3 n_atoms)")
+        if not np.allclose(A, np.swapaxes(A, 1, 2)):
+            raise ValueError("A_t must be symmetric")
+        self = cls.__new__(cls)
+        n = A.shape[0]
+        self.n_iterations, self.n_atoms = n, A.shape[1] // 3
+        self.reference_normalizer = False
+        self.is_dense = True
+        self.A, self.b = A, b
+        self.c = np.zeros(n) if c is None else np.asarray(c, dtype=np.float64).reshape(n)
+        self.d = np.zeros(n) if d is None else np.asarray(d, dtype=np.float64).reshape(n)
+        self.table = None
+        return self
+
+    @staticmethod
+    def dense_tables(A, b, c, d, s):
+        """One iteration's cdw_dense_twist arrays from A_t, b_t, c_t, d_t and the per-coordinate variances s of the uncontrolled kernel:
+        (theta, chol, beta, logk0, cd).  Raises if S^-1 + 2 A_t is not positive definite."""
+        prec = np.diag(1.0 / s) + 2.0 * A
+        try:
+            np.linalg.cholesky(prec)
+        except np.linalg.LinAlgError:
+            raise ValueError("S^-1 + 2 A_t must be positive definite (the twisted proposal is a Gaussian; Theta_t, troubleshooting/csmc.py:460-478)")
+        sig = np.linalg.inv(prec)
+        sig = 0.5 * (sig + sig.T)
+        theta = sig / s[None, :]
+        beta = sig @ b
+        logk0 = 0.5 * np.linalg.slogdet(theta)[1] + 0.5 * b @ beta - c - d
+        return theta, np.linalg.cholesky(sig), beta, float(logk0), float(c + d)
+
+    def bind(self, masses, langevin, device, n_particles):
+        """Check the sequence against a system / time step and put its tables on `device` (idempotent for the same arguments)."""
+        masses = np.asarray(masses, dtype=np.float64)
+        if masses.shape[0] != self.n_atoms:
+            raise ValueError(f"the twist is for {self.n_atoms} atoms, the system has {masses.shape[0]}")
+        s_atom = langevin.kT * langevin.timestep ** 2 / masses          # s = 2 tau_a = kT dt^2 / m_a
+        if not self.is_dense:
+            self.check(masses, langevin)
+            return self.to(device)
+        D, n = 3 * self.n_atoms, self.n_iterations
+        s = np.repeat(s_atom, 3)
+        th, ch, be, self._logk0, self._cd = np.empty((n, D, D)), np.empty((n, D, D)), np.empty((n, D)), [], []
+        for t in range(n):
+            th[t], ch[t], be[t], k0, cd = self.dense_tables(self.A[t], self.b[t], self.c[t], self.d[t], s)
+            self._logk0.append(k0); self._cd.append(cd)
+        up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(device)
+        self._dev = dict(theta=up(th), chol=up(ch), A=up(self.A), b=up(self.b), beta=up(be))
+        self._scratch = torch.zeros(int(n_particles), 2 * D, dtype=torch.float64, device=device)
+        self.table = self._dev["theta"]
+        return self
 
     def to(self, device):
         if self.table is None or self.table.device != torch.device(device):
@@ -171,8 +236,12 @@ class TwistSequence:
             raise ValueError("1 + 2 s a must be positive for every coordinate (Theta_t, troubleshooting/csmc.py:460-478)")
 
     def row(self, t):
-        """Iteration t (1-based) -> the device row."""
-        return self.table[t - 1]
+        """Iteration t (1-based) -> what LangevinParameters.as_struct takes: the device row (diagonal) or a cdw_dense_twist descriptor."""
+        if not self.is_dense:
+            return self.table[t - 1]
+        v = self._dev
+        return _lib.DenseTwist(v["theta"][t - 1].data_ptr(), v["chol"][t - 1].data_ptr(), v["A"][t - 1].data_ptr(), v["b"][t - 1].data_ptr(),
+                               v["beta"][t - 1].data_ptr(), self._logk0[t - 1], self._cd[t - 1], self._scratch.data_ptr())
 
     @property
     def flags(self):
@@ -481,8 +550,7 @@ class SMCEngine:
         if twist is not None:
             if twist.n_iterations != self.T - 1:
                 raise ValueError(f"the twist sequence holds {twist.n_iterations} iterations, the protocol has {self.T - 1}")
-            twist.check(self.system.spec.masses, self.langevin)
-            twist.to(self.ensemble.device)
+            twist.bind(self.system.spec.masses, self.langevin, self.ensemble.device, n_particles)
         self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)

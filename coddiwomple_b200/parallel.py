@@ -122,8 +122,7 @@ class ShardedSMCEngine:
         if twist is not None:
             if twist.n_iterations != self.T - 1:
                 raise ValueError(f"the twist sequence holds {twist.n_iterations} iterations, the protocol has {self.T - 1}")
-            twist.check(self.system.spec.masses, self.langevin)
-            twist.to(self.device)
+            twist.bind(self.system.spec.masses, self.langevin, self.device, self.P_loc)
         self.kind = RESAMPLER_KINDS[resampler] if isinstance(resampler, str) else int(resampler)
         self.threshold = -1.0 if always_resample else float(floor_threshold)
         self.seed, self.resample_seed = int(seed), int(resample_seed)

@@ -102,6 +102,27 @@ typedef struct cdw_system_desc {
     const double* cons_dist;       /* [n_constraints] nm */
 } cdw_system_desc;
 
+/* Dense, position-independent quadratic twist of ONE iteration of the Euler-Maruyama proposal (controlled SMC, troubleshooting/csmc.py:460-623
+ * with a full matrix A_t):  psi_t = exp(-(x^T A_t x + b_t^T x + c_t + d_t)).  The uncontrolled kernel is N(f, S), f = x + tau beta F(x),
+ * S = diag(2 tau) per coordinate (tau_a = kT dt^2 / (2 m_a), openmm/integrators.py:676-680).  The caller precomputes, with
+ * Sigma~ = (S^-1 + 2 A_t)^-1 (must be positive definite) and D = 3 A, all row-major DEVICE arrays:
+ *   theta [D][D] = Sigma~ S^-1 (Theta_t, :460-478)    chol [D][D] = lower Cholesky factor of Sigma~    A [D][D] = A_t (symmetric)
+ *   b [D] = b_t                                        beta [D] = Sigma~ b_t
+ *   logk0 = 0.5 log det theta + 0.5 b^T Sigma~ b - c - d          cd = c + d
+ * and provides `scratch`, 2 D doubles per particle of the call.  The move becomes x' ~ N(theta f - beta, Sigma~)
+ * (twisted_forward_proposal, :503-528) and the incremental work loses log K_t(psi_t)(x) + phi_t(x') (:531-561, :593-623), with
+ * log K_t(psi_t)(x) = logk0 - (theta f).(A f) - b.(theta f)  (the reference's two large quadratic forms, expanded so that nothing cancels). */
+typedef struct cdw_dense_twist {
+    const double* theta;
+    const double* chol;
+    const double* A;
+    const double* b;
+    const double* beta;
+    double logk0;
+    double cd;
+    double* scratch;
+} cdw_dense_twist;
+
 /* Langevin "V R O R V" parameters — OMMLI.__init__ (coddiwomple/openmm/integrators.py:75-131) */
 typedef struct cdw_langevin_params {
     double dt;              /* ps */
@@ -124,6 +145,9 @@ typedef struct cdw_langevin_params {
      *   log K_t(psi_t)(x) + phi_t(x')   (twisted_forward_log_normalizer :531-561, twisted_t_log_weight :593-623).
      * 1 + 2 s a must be positive for every coordinate. */
     const double* twist;
+    /* The same with a full matrix A_t (HOST pointer to the descriptor above, or NULL); excludes `twist` and
+     * CDW_FLAG_TWIST_REFERENCE_NORMALIZER. */
+    const cdw_dense_twist* dense_twist;
 } cdw_langevin_params;
 
 #define CDW_STEP_V 1u      /* v += (dt / n_V) f / m */

@@ -147,3 +147,65 @@ def twisted_ula(energy_forces, x, masses, constraints, dt, kT, n_steps, seed, gi
     if nan.any():
         x[nan] = x0[nan]
     return dict(x=x, u_first=u_first, u_last=U.copy(), proposal_work=proposal, twist_logk=logk_sum, twist_phi=phi_sum, nan=nan)
+
+
+# ------------------------------------------------------------------------------------------------ dense A_t on a molecular system
+def dense_tables(A, b, c, d, s):
+    """The per-iteration arrays of cdw_dense_twist (include/cdw.h) from A_t [D, D], b_t [D], c_t, d_t and the per-coordinate variances s [D] of
+    the uncontrolled kernel N(f, diag s):  Sigma~ = (S^-1 + 2 A)^-1, theta = Sigma~ S^-1 (csmc.py:460-478 when S = dt I), the lower Cholesky
+    factor of Sigma~, beta = Sigma~ b, logk0 = 0.5 log det theta + 0.5 b^T Sigma~ b - c - d, cd = c + d."""
+    A, b, s = np.asarray(A, dtype=np.float64), np.asarray(b, dtype=np.float64), np.asarray(s, dtype=np.float64)
+    sig = np.linalg.inv(np.diag(1.0 / s) + 2.0 * A)
+    sig = 0.5 * (sig + sig.T)
+    theta = sig / s[None, :]
+    beta = sig @ b
+    return dict(theta=theta, chol=np.linalg.cholesky(sig), A=A, b=b, beta=beta, logk0=float(0.5 * np.linalg.slogdet(theta)[1] + 0.5 * b @ beta - c - d),
+                cd=float(c + d), sigma=sig)
+
+
+def dense_log_normalizer_direct(f, A, b, c, d, s):
+    """log int N(x'; f, diag s) exp(-phi(x')) dx' written as the reference writes it (csmc.py:531-561 with S in place of dt I): the difference of
+    two large quadratic forms.  Used to check the cancellation-free form the kernel evaluates."""
+    Sinv = np.diag(1.0 / np.asarray(s))
+    sig = np.linalg.inv(Sinv + 2.0 * np.asarray(A))
+    m = Sinv @ f - b
+    return 0.5 * np.linalg.slogdet(sig @ Sinv)[1] + 0.5 * m @ sig @ m - 0.5 * f @ Sinv @ f - c - d
+
+
+def twisted_ula_dense(energy_forces, x, masses, constraints, dt, kT, n_steps, seed, gids, step0, tables, tol=1e-6):
+    """oracle.ula.ula with the dense twist `tables` = dense_tables(...) (the kernel's arithmetic: lane_twisted_move_dense, cdw_lane.cuh)."""
+    x0 = r32(x)
+    x = x0.copy()
+    P, A = x.shape[0], x.shape[1]
+    D = 3 * A
+    masses = np.asarray(masses, dtype=np.float64)
+    inv_m = 1.0 / masses
+    tau = taus(masses, dt, kT)[None, :, None]
+    drift_c = tau / kT
+    th, ch, Am, b, beta = (np.asarray(tables[k], dtype=np.float64) for k in ("theta", "chol", "A", "b", "beta"))
+    U, F = energy_forces(x)
+    u_first = U.copy()
+    proposal = np.zeros(P)
+    for s_ in range(n_steps):
+        xi = rng.normals(seed, gids, step0 + s_, A, KIND_ULA).reshape(P, D)
+        x_old = x
+        r0 = [(x[:, i].astype(np.float32) - x[:, j].astype(np.float32)).astype(np.float64) for (i, j, _) in constraints]
+        f = (x_old + drift_c * F).reshape(P, D)
+        u, w = f @ th.T, f @ Am.T
+        logk = tables["logk0"] - (u * w).sum(1) - u @ b
+        x = r32(((u - beta[None]) + xi @ ch.T).reshape(P, A, 3))
+        if constraints:
+            dummy = np.zeros_like(x)
+            _shake(x, dummy, r0, inv_m, constraints, tol, 0.0)
+        dlt = x - x_old - drift_c * F
+        fwd = -((dlt * dlt) / (4.0 * tau)).sum((1, 2))
+        U, F = energy_forces(x)
+        dlt = x_old - x - drift_c * F
+        bwd = -((dlt * dlt) / (4.0 * tau)).sum((1, 2))
+        xf = x.reshape(P, D)
+        ph = ((xf @ Am.T) * xf).sum(1) + xf @ b + tables["cd"]
+        proposal += fwd - bwd - (logk + ph)
+    nan = ~np.isfinite(U + proposal) if n_steps > 0 else np.zeros(P, dtype=bool)
+    if nan.any():
+        x[nan] = x0[nan]
+    return dict(x=x, u_first=u_first, u_last=U.copy(), proposal_work=proposal, nan=nan)

@@ -55,9 +55,16 @@ def smc_propagate(ds, x, v, lam, dt, gamma, kT, n_steps, seed, step0, gid0=0, to
     o["nan"] = torch.zeros(P, dtype=torch.int32, device="cuda")
     o["wmin"] = torch.full((1,), -1, dtype=torch.int64, device="cuda")
     trials = torch.zeros(P, 2, dtype=torch.int32, device="cuda")
+    dense = None
+    if isinstance(twist, dict):   # dense twist: theta, chol, A, b, beta (numpy), logk0, cd
+        keep = {k: torch.as_tensor(np.ascontiguousarray(twist[k]), dtype=torch.float64).cuda() for k in ("theta", "chol", "A", "b", "beta")}
+        keep["scratch"] = torch.zeros(P, 2 * keep["b"].numel(), dtype=torch.float64, device="cuda")
+        dense = _lib.DenseTwist(keep["theta"].data_ptr(), keep["chol"].data_ptr(), keep["A"].data_ptr(), keep["b"].data_ptr(), keep["beta"].data_ptr(),
+                                float(twist["logk0"]), float(twist["cd"]), keep["scratch"].data_ptr())
+        twist = None
     twist_d = None if twist is None else torch.as_tensor(np.ascontiguousarray(twist), dtype=torch.float64).cuda()
     prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags, int(splitting), trials.data_ptr() if splitting else None,
-                              None if twist_d is None else twist_d.data_ptr())
+                              None if twist_d is None else twist_d.data_ptr(), None if dense is None else C.addressof(dense))
     _lib.check(lib.cdw_smc_propagate(ds.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(o["pos"]), _lib.ptr(o["vel"]), P, _lib.ptr(anc_d), _lib.ptr(aux_d),
                                      _lib.ptr(cum_d), _lib.ptr(lab_d), _lib.ptr(lam_dev(ds.spec, lam)), C.byref(prm), C.c_uint64(seed), C.c_uint64(step0),
                                      C.c_int64(gid0), _lib.ptr(o["inc"]), _lib.ptr(o["w"]), _lib.ptr(o["aux"]), _lib.ptr(o["label"]), _lib.ptr(o["u_first"]),

@@ -86,9 +86,16 @@ class HostSystem:
         P = pos.shape[0]
         lam = np.ascontiguousarray(lam, dtype=np.float64)
         trials = np.zeros((P, 2), dtype=np.int32)
+        dense = None
+        if isinstance(twist, dict):   # dense twist: theta, chol, A, b, beta (numpy), logk0, cd
+            keep = {k: np.ascontiguousarray(twist[k], dtype=np.float64) for k in ("theta", "chol", "A", "b", "beta")}
+            keep["scratch"] = np.zeros((P, 2 * keep["b"].size))
+            dense = _lib.DenseTwist(keep["theta"].ctypes.data, keep["chol"].ctypes.data, keep["A"].ctypes.data, keep["b"].ctypes.data,
+                                    keep["beta"].ctypes.data, float(twist["logk0"]), float(twist["cd"]), keep["scratch"].ctypes.data)
+            twist = None
         twist = None if twist is None else np.ascontiguousarray(twist, dtype=np.float64)
         prm = _lib.LangevinParams(dt, gamma, kT, tol, n_steps, flags, int(splitting), trials.ctypes.data if splitting else None,
-                                  None if twist is None else twist.ctypes.data)
+                                  None if twist is None else twist.ctypes.data, None if dense is None else C.addressof(dense))
         o = dict(pos=np.zeros_like(pos), vel=np.zeros_like(pos), inc=np.zeros(P), w=np.zeros(P), aux=np.zeros(P), label=np.zeros(P, dtype=np.int32),
                  u_first=np.zeros(P), u_last=np.zeros(P), shadow=np.zeros(P), proposal=np.zeros(P), nan=np.zeros(P, dtype=np.int32),
                  wmin=np.array([2 ** 64 - 1], dtype=np.uint64))

@@ -156,7 +156,13 @@ extern "C" int hh_smc_propagate(const hh_system* s, const float* pos_in, const f
     a.seed = seed; a.step0 = step0; a.gid0 = gid0;
     a.inc_out = inc_out; a.w_out = w_out; a.aux_out = aux_out; a.label_out = label_out; a.u_first_out = u_first_out; a.u_last_out = u_last_out;
     a.shadow_out = shadow_out; a.proposal_out = proposal_out; a.nan_flags = nan_flags; a.wmin_key = (unsigned long long*)wmin_key;
-    if (a.flags & CDW_FLAG_ULA) { a.vel_in = nullptr; a.vel_out = nullptr; a.twist = prm->twist; }  // as cdw_smc_propagate does
+    if (a.flags & CDW_FLAG_ULA) {  // as cdw_smc_propagate does
+        a.vel_in = nullptr; a.vel_out = nullptr; a.twist = prm->twist;
+        if (const cdw_dense_twist* d = prm->dense_twist) {
+            a.tw_theta = d->theta; a.tw_chol = d->chol; a.tw_A = d->A; a.tw_b = d->b; a.tw_beta = d->beta;
+            a.tw_logk0 = d->logk0; a.tw_cd = d->cd; a.tw_scratch = d->scratch;
+        }
+    }
     a.program = prm->splitting; a.trial_counts = prm->trial_counts;
     return run(s, a, true);
 }

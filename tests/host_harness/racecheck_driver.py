@@ -44,4 +44,13 @@ elif mode == "lookahead":  # the look-ahead iteration: forces travel with the pa
     hs.smc_lookahead(b["x"], Vbad, b["force"], lam2, None, 0.002, 1.0, kT, 1, seed=7, step0=4)
 elif mode == "ula":        # Euler-Maruyama move with constraint projection and both kernel densities
     hs.smc_propagate(X, None, lam, 0.0005, 0.0, kT, 2, seed=7, step0=3, flags=_lib.CDW_FLAG_ULA, aux=np.zeros(2), cum=np.zeros(2))
+elif mode == "twisted":    # the dense twisted move: matrix-vector rows split over the lanes, vectors through the per-particle scratch
+    from oracle import twisted
+    A = X.shape[1]
+    r = np.random.RandomState(5)
+    G = r.randn(3 * A, 3 * A) / np.sqrt(3 * A)
+    tw = twisted.dense_tables(15.0 * G @ G.T, 2.0 * r.randn(3 * A), 0.37, -0.11, np.repeat(kT * 0.0005 ** 2 / np.asarray(spec.masses), 3))
+    hs.smc_propagate(X, None, lam, 0.0005, 0.0, kT, 2, seed=7, step0=3, flags=_lib.CDW_FLAG_ULA, aux=np.zeros(2), cum=np.zeros(2), twist=tw)
+    hs.smc_propagate(X, None, lam, 0.0005, 0.0, kT, 2, seed=7, step0=3, flags=_lib.CDW_FLAG_ULA, aux=np.zeros(2), cum=np.zeros(2),
+                     twist=twisted.pack_twist(40.0 * r.rand(A, 3), 3.0 * r.randn(A, 3), c=0.37))
 print("racecheck-done", system, T, mode)

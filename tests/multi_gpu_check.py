@@ -31,7 +31,7 @@ def main():
     frames = np.load(os.path.join(root, "tests", "golden", "fluorobenzene_cache.npy"))
     ok = True
     cases = (("multinomial", 0.9999, 4096, 8, "baoab"), ("systematic", 0.9999, 4096, 8, "baoab"), ("multinomial", 0.5, 2048 * world, 12, "baoab"),
-             ("multinomial", 0.9999, 4096, 8, "ula"), ("multinomial", 0.9999, 4096, 8, "twisted"),
+             ("multinomial", 0.9999, 4096, 8, "ula"), ("multinomial", 0.9999, 4096, 8, "twisted"), ("multinomial", 0.9999, 4096, 8, "twisted-dense"),
              ("systematic", 0.9999, 1024 * 12 * world, 6, "baoab"))   # (ula: BASELINE configs[3], the Euler-Maruyama proposal, sharded; last: a batch whose per-rank share is launched very differently from the whole)
     for kind, thr, P, T, proposal in cases:
         x0 = frames[np.random.RandomState(0).randint(0, len(frames), P)]
@@ -40,6 +40,11 @@ def main():
         if proposal == "twisted":   # controlled SMC: the Euler-Maruyama proposal with a per-iteration quadratic twist (troubleshooting/csmc.py:460-623)
             r = np.random.RandomState(9)
             twist = TwistSequence(30.0 * r.rand(T - 1, 13, 3), 2.0 * r.randn(T - 1, 13, 3), c=r.randn(T - 1))
+            proposal = "ula"
+        if proposal == "twisted-dense":   # the same with a full 39 x 39 matrix A_t
+            r = np.random.RandomState(10)
+            G = r.randn(T - 1, 39, 39) / np.sqrt(39.0)
+            twist = TwistSequence.dense(10.0 * G @ np.swapaxes(G, 1, 2), 2.0 * r.randn(T - 1, 39), c=r.randn(T - 1))
             proposal = "ula"
         lang = LangevinParameters(timestep=0.0005) if proposal == "ula" else LangevinParameters()
         sharded = ShardedSMCEngine(xml, P, seq, langevin=lang, resampler=kind, floor_threshold=thr, seed=3, resample_seed=4, proposal=proposal, twist=twist)
@@ -63,7 +68,7 @@ def main():
             e = single.ensemble
             same = (torch.equal(torch.cat(pos_parts), e.pos[e.cur]) and torch.equal(torch.cat(vel_parts), e.vel[e.cur]) and
                     torch.equal(torch.cat(lab_parts), e.labels) and torch.equal(sharded.cum, e.cum) and torch.equal(sharded.stats, single.stats))
-            print(f"[multi_gpu_check] world={world} {proposal}{' + twist' if twist is not None else ''} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
+            print(f"[multi_gpu_check] world={world} {proposal}{(' + dense twist' if twist.is_dense else ' + twist') if twist is not None else ''} {kind} thr={thr} P={P}: sharded == single-GPU bitwise: {same}; "
                   f"resampled at {sharded.resampled_iterations()} FE={sharded.free_energy():.6f}", flush=True)
             ok &= bool(same) and len(sharded.resampled_iterations()) > 0 or (thr == 0.5 and bool(same))
         sharded.close()

@@ -25,4 +25,4 @@ def test_sharded_anneal_equals_single_gpu_anneal_bitwise():
                           "--master-port", "29541", os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600, env=env)
     lines = [l for l in out.stdout.splitlines() if "[multi_gpu_check]" in l]
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert len(lines) >= 6 and all("True" in l for l in lines), "\n".join(lines)
+    assert len(lines) >= 7 and all("True" in l for l in lines), "\n".join(lines)

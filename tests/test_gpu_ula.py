@@ -202,3 +202,54 @@ def test_twisted_engine_is_unbiased_and_a_good_twist_raises_the_effective_sample
         SMCEngine(ts.harmonic_oscillator_xml(), P, seq, proposal="baoab", twist=seq_twist(0.0, -12.0))
     with pytest.raises(ValueError):   # 1 + 2 s a <= 0: not a Gaussian any more
         SMCEngine(ts.harmonic_oscillator_xml(), 16, seq, langevin=LangevinParameters(timestep=0.2), proposal="ula", twist=seq_twist(-1e4, 0.0))
+
+
+@pytest.mark.parametrize("name,n_steps,P", [("fluorobenzene", 1, 100), ("fluorobenzene", 2, 37), ("ala", 1, 64)])
+def test_dense_twisted_kernel_matches_oracle(name, n_steps, P):
+    """cdw_langevin_params.dense_twist (a full matrix A_t, troubleshooting/csmc.py:460-623) against oracle.twisted.twisted_ula_dense."""
+    from coddiwomple_b200.engine import DeviceSystem
+    from oracle import twisted
+    from tests import gpu_util
+    xml = ts.alanine_dipeptide_shaped_xml()[0] if name == "ala" else system_xml(name)
+    o = XmlSystemOracle(xml)
+    ds = DeviceSystem(xml)
+    X = (cache_frames()[np.random.RandomState(0).randint(0, 151, P)] if name == "fluorobenzene" else ts.alanine_dipeptide_shaped_ensemble(P)).astype(np.float64)
+    A = X.shape[1]
+    lam = relative_lambdas(0.3)
+    dt = 0.0005
+    r = np.random.RandomState(5)
+    G = r.randn(3 * A, 3 * A) / np.sqrt(3 * A)
+    s = np.repeat(kT * dt * dt / np.asarray(o.masses), 3)
+    tab = twisted.dense_tables(15.0 * G @ G.T, 2.0 * r.randn(3 * A), 0.37, -0.11, s)
+    ref = twisted.twisted_ula_dense(lambda xx: o.energy_forces(xx, lam), X, o.masses, o.constraints, dt, kT, n_steps, seed=7, gids=np.arange(5, 5 + P),
+                                    step0=11, tables=tab)
+    out = gpu_util.smc_propagate(ds, X, None, lam, dt, 0.0, kT, n_steps, seed=7, step0=11, gid0=5, flags=_lib.CDW_FLAG_ULA, aux=np.full(P, 0.25),
+                                 cum=np.full(P, 1.5), twist=tab)
+    assert np.abs(out["x"] - ref["x"]).max() < 2e-7
+    np.testing.assert_allclose(out["u_last"], ref["u_last"] / kT, atol=2e-4)
+    np.testing.assert_allclose(out["proposal"], ref["proposal_work"], rtol=1e-9, atol=3e-4)
+    np.testing.assert_allclose(out["inc"], out["u_last"] + 0.25 + out["proposal"], rtol=1e-12)
+    assert not out["nan"].any()
+    with pytest.raises(_lib.CdwError):   # the dense descriptor excludes the reference-normaliser switch
+        gpu_util.smc_propagate(ds, X, None, lam, dt, 0.0, kT, 1, seed=7, step0=11, flags=_lib.CDW_FLAG_ULA | _lib.CDW_FLAG_TWIST_REFERENCE_NORMALIZER, twist=tab)
+
+
+def test_dense_twisted_engine_is_unbiased():
+    """SMCEngine(proposal="ula", twist=TwistSequence.dense(...)) with a twist that couples x, y, z: Delta F = 1 kT (tests/utils.py:64-65); a twist whose
+    precision matrix is not positive definite is refused."""
+    from coddiwomple_b200.engine import LangevinParameters, SMCEngine, TwistSequence
+    prm = ts.harmonic_oscillator_parameters()
+    P, T = 20000, 41
+    x0 = np.random.RandomState(0).normal(0, prm["sigma"], (P, 1, 3)).astype(np.float32)
+    seq = ts.harmonic_parameter_sequence(T)
+    A3 = np.array([[2.0, 0.8, -0.5], [0.8, 1.5, 0.3], [-0.5, 0.3, 1.0]])
+    b = np.zeros((T - 1, 3)); b[:, 0] = -10.0 * 0.2 * np.arange(1, T) / (T - 1); b[:, 1] = 0.4; b[:, 2] = -0.3
+    tw = TwistSequence.dense(np.repeat(A3[None], T - 1, 0), b, c=0.05 * np.arange(1, T))
+    eng = SMCEngine(ts.harmonic_oscillator_xml(), P, seq, langevin=LangevinParameters(timestep=0.2), seed=1, resample_seed=2, proposal="ula",
+                    floor_threshold=0.0, twist=tw)
+    eng.anneal(x0)
+    assert abs(eng.free_energy() - 1.0) < 0.04, eng.free_energy()
+    assert int(eng.ensemble.nan_flags.sum()) == 0
+    with pytest.raises(ValueError):
+        SMCEngine(ts.harmonic_oscillator_xml(), 16, seq, langevin=LangevinParameters(timestep=0.2), proposal="ula",
+                  twist=TwistSequence.dense(np.repeat(-1e4 * np.eye(3)[None], T - 1, 0), b))

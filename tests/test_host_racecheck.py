@@ -36,7 +36,7 @@ def tsan_build():
 
 
 @pytest.mark.parametrize("system,T,mode", [("fluorobenzene", 4, "baoab"), ("fluorobenzene", 4, "cached"), ("fluorobenzene", 4, "ula"),
-                                           ("ala", 4, "cached"), ("ala", 8, "baoab"), ("fluorobenzene", 4, "lookahead"), ("ala", 4, "lookahead")])
+                                           ("ala", 4, "cached"), ("ala", 8, "baoab"), ("fluorobenzene", 4, "lookahead"), ("ala", 4, "lookahead"), ("fluorobenzene", 4, "twisted")])
 def test_team_algorithm_has_no_data_race(tsan_build, system, T, mode):
     env = dict(os.environ, LD_PRELOAD=tsan_build, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0", CDW_HH_TSAN_SO=TSAN_SO)
     env.pop("CDW_HH_TEAM", None)

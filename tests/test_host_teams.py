@@ -145,3 +145,32 @@ def test_whole_anneal_on_the_host_tracks_the_oracle():
         aux = out["aux"]
     fe = weights.free_energy(cum)
     assert abs(fe - ref["free_energy"]) < 0.1, (fe, ref["free_energy"])
+
+
+@pytest.mark.parametrize("name,T,dense", [("fluorobenzene", 2, False), ("fluorobenzene", 4, True), ("fluorobenzene", 2, True), ("ala", 4, True)])
+def test_team_twisted_euler_maruyama_matches_oracle(name, T, dense):
+    """The twisted Euler-Maruyama move with the lanes of a team as threads: the rows of the dense matrix-vector products are split over the
+    lanes and the vectors travel through the per-particle scratch between team barriers (a missing barrier is a wrong result here, and a data
+    race under tests/test_host_racecheck.py)."""
+    from oracle import twisted
+    o, spec, hs, X = _setup(name)
+    P, A = X.shape[0], X.shape[1]
+    lam = relative_lambdas(0.3)
+    dt = 0.0005
+    r = np.random.RandomState(5)
+    if dense:
+        G = r.randn(3 * A, 3 * A) / np.sqrt(3 * A)
+        s = np.repeat(kT * dt * dt / np.asarray(o.masses), 3)
+        tw = twisted.dense_tables(15.0 * G @ G.T, 2.0 * r.randn(3 * A), 0.37, -0.11, s)
+        ref = twisted.twisted_ula_dense(lambda xx: o.energy_forces(xx, lam), X, o.masses, o.constraints, dt, kT, 2, seed=7, gids=np.arange(5, 5 + P),
+                                        step0=11, tables=tw)
+    else:
+        tw = twisted.pack_twist(40.0 * r.rand(A, 3), 3.0 * r.randn(A, 3), c=0.37, d=-0.11)
+        ref = twisted.twisted_ula(lambda xx: o.energy_forces(xx, lam), X, o.masses, o.constraints, dt, kT, 2, seed=7, gids=np.arange(5, 5 + P), step0=11,
+                                  twist=tw)
+    hh.set_team(T)
+    out = hs.smc_propagate(X, None, spec.lambda_vector(lam), dt, 0.0, kT, 2, seed=7, step0=11, gid0=5, flags=_lib.CDW_FLAG_ULA, aux=np.full(P, 0.25),
+                           cum=np.full(P, 1.5), twist=tw)
+    assert np.abs(out["x"] - ref["x"]).max() < 2e-7
+    np.testing.assert_allclose(out["proposal"], ref["proposal_work"], rtol=1e-9, atol=3e-4)
+    np.testing.assert_allclose(out["inc"], out["u_last"] + 0.25 + out["proposal"], rtol=1e-12)

@@ -62,7 +62,8 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(_lib.LangevinParams) == 64   # 4 doubles, 2 x 32 bit, the splitting word, the trial-count and twist pointers
+    assert ctypes.sizeof(_lib.LangevinParams) == 72   # 4 doubles, 2 x 32 bit, the splitting word, the trial-count, twist and dense-twist pointers
+    assert _lib.LangevinParams.dense_twist.offset == 64 and ctypes.sizeof(_lib.DenseTwist) == 64
     assert _lib.LangevinParams.splitting.offset == 40 and _lib.LangevinParams.trial_counts.offset == 48 and _lib.LangevinParams.twist.offset == 56
     # cdw_system_desc: count the fields of the C struct
     header = open(os.path.join(ROOT, "include", "cdw.h")).read()
