@@ -589,9 +589,18 @@ class SMCEngine:
         if self.record_lineage:
             self._lineage_due = None
 
-    def initialize(self, positions, velocities=None):
+    def initialize(self, positions, velocities=None, initial_works=None):
+        """Stage the initial particles and equip them (aux = -u_0(x_0), cumulative work 0).  `initial_works` (P,): the works -log w_0 of particles
+        that were NOT drawn from the first target itself but from a proposal q_0 with weights w_0 = pi_0 / q_0 — the `initial_work` of
+        ProposalFactory.equip_initial_sample with a generation_pdf (distribution_factories.py:203-212), the log w_0 of a twisted initial
+        proposal (troubleshooting/csmc.py:564-591, `csmc.twisted_gmm_initial_sample`)."""
         self.load(positions, velocities)
         self._equip()
+        if initial_works is not None:
+            w = torch.as_tensor(np.asarray(initial_works, dtype=np.float64)).to(self.ensemble.device)
+            if w.shape != (self.ensemble.P,):
+                raise ValueError("initial_works must have one entry per particle")
+            self.ensemble.cum.copy_(w)
 
     # ------------------------------------------------------------------ sequential loop (also the public two-call form)
     def propagate(self, t):
@@ -694,10 +703,12 @@ class SMCEngine:
             self.step(t)
         return self.finish()
 
-    def anneal(self, positions, velocities=None):
+    def anneal(self, positions, velocities=None, initial_works=None):
         if self.graph is not None:
+            if initial_works is not None:
+                raise ValueError("initial_works need the eager loop (the captured graph equips the particles with zero works)")
             return self.anneal_graph(positions, velocities)
-        self.initialize(positions, velocities)
+        self.initialize(positions, velocities, initial_works)
         return self.run()
 
     # ------------------------------------------------------------------ CUDA graph of the whole anneal

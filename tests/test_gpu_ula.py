@@ -253,3 +253,27 @@ def test_dense_twisted_engine_is_unbiased():
     with pytest.raises(ValueError):
         SMCEngine(ts.harmonic_oscillator_xml(), 16, seq, langevin=LangevinParameters(timestep=0.2), proposal="ula",
                   twist=TwistSequence.dense(np.repeat(-1e4 * np.eye(3)[None], T - 1, 0), b))
+
+
+def test_whole_twisted_smc_with_a_twisted_initial_draw():
+    """twisted_smc end to end (troubleshooting/csmc.py:625-747): the initial particles come from the TWISTED Gaussian initial proposal with their
+    log w_0 (coddiwomple_b200.csmc, csmc.py:336-458, 564-591), every move is twisted on the device.  Harmonic oscillator, pi_0 = N(0, sigma^2 I):
+    Delta F = 1 kT (tests/utils.py:64-65) whatever the twists."""
+    from coddiwomple_b200 import csmc
+    from coddiwomple_b200.engine import LangevinParameters, SMCEngine, TwistSequence
+    prm = ts.harmonic_oscillator_parameters()
+    P, T = 20000, 41
+    seq = ts.harmonic_parameter_sequence(T)
+    sig2 = prm["sigma"] ** 2
+    A0 = np.array([[6.0, 1.0, 0.0], [1.0, 4.0, -0.5], [0.0, -0.5, 3.0]])          # 1/nm^2, against a prior precision of 100 1/nm^2
+    x0, log_w0 = csmc.twisted_gmm_initial_sample(P, [1.0], np.zeros((1, 3)), sig2 * np.eye(3)[None], A0, np.array([-3.0, 0.5, 0.0]), 0.2,
+                                                 rng=np.random.default_rng(5))
+    ramp = np.arange(1, T) / (T - 1)
+    b = np.zeros((T - 1, 1, 3)); b[:, 0, 0] = -12.0 * 0.2 * ramp
+    eng = SMCEngine(ts.harmonic_oscillator_xml(), P, seq, langevin=LangevinParameters(timestep=0.2), seed=1, resample_seed=2, proposal="ula",
+                    floor_threshold=0.0, twist=TwistSequence(np.zeros((T - 1, 1, 3)), b, c=0.05 * np.arange(1, T)))
+    eng.anneal(x0.reshape(P, 1, 3).astype(np.float32), initial_works=-log_w0)
+    assert abs(eng.free_energy() - 1.0) < 0.04, eng.free_energy()
+    plain = SMCEngine(ts.harmonic_oscillator_xml(), P, seq, langevin=LangevinParameters(timestep=0.2), seed=1, resample_seed=2, proposal="ula", floor_threshold=0.0)
+    plain.anneal(x0.reshape(P, 1, 3).astype(np.float32))                            # the same draws WITHOUT their initial weights: biased
+    assert abs(plain.free_energy() - 1.0) > 0.1, plain.free_energy()
