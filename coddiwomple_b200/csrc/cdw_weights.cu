@@ -628,6 +628,81 @@ __global__ void fma_peak_kernel(T* out, int iters) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// ---- K3b over peer memory with TMA.  A particle row is 16 A contiguous bytes on the owning GPU; a chunk of kTmaRows destination rows is 16 A
+// kTmaRows contiguous bytes here.  Each of the first kTmaRows threads asks for its ancestor's position and velocity rows with one bulk copy each
+// (cp.async.bulk global -> shared, completion on an mbarrier: NVLink sees 16 A-byte requests instead of one 16-byte load per thread), and one
+// elected thread writes the whole chunk back with two bulk stores (shared -> global).  Several small CTAs per SM overlap each other's phases.
+constexpr int kTmaRows = 32;
+constexpr int kTmaThreads = 64;
+
+template <bool PEER>
+__global__ void __launch_bounds__(kTmaThreads) gather_rows_tma_kernel(const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                                                                      const double* __restrict__ aux_in, const int* __restrict__ label_in,
+                                                                      const float4* const* __restrict__ peer_pos, const float4* const* __restrict__ peer_vel,
+                                                                      const double* const* __restrict__ peer_aux, const int* const* __restrict__ peer_label,
+                                                                      long long n_per_rank, const int* __restrict__ anc, float4* __restrict__ pos_out,
+                                                                      float4* __restrict__ vel_out, double* __restrict__ aux_out, int* __restrict__ label_out,
+                                                                      long long n, int A) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned row_bytes = 16u * (unsigned)A;
+    unsigned char* spos = stage;
+    unsigned char* svel = stage + (size_t)kTmaRows * row_bytes;
+    const unsigned b = (unsigned)__cvta_generic_to_shared(&bar);
+    const int tid = (int)threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    const long long n_chunks = (n + kTmaRows - 1) / kTmaRows;
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const long long base = c * kTmaRows;
+        const int cnt = (int)(n - base < kTmaRows ? n - base : kTmaRows);
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((unsigned)cnt * row_bytes * 2u) : "memory");
+        if (tid < cnt) {
+            const long long src = (long long)__ldg(anc + base + tid);
+            const int r = PEER ? (int)(src / n_per_rank) : 0;
+            const long long l = PEER ? src - (long long)r * n_per_rank : src;
+            const float4* prow = (PEER ? peer_pos[r] : pos_in) + l * A;
+            const float4* vrow = (PEER ? peer_vel[r] : vel_in) + l * A;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(spos + (size_t)tid * row_bytes)), "l"(prow), "r"(row_bytes), "r"(b) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(svel + (size_t)tid * row_bytes)), "l"(vrow), "r"(row_bytes), "r"(b) : "memory");
+            if (aux_out) aux_out[base + tid] = PEER ? peer_aux[r][l] : __ldg(aux_in + l);
+            if (label_out) label_out[base + tid] = PEER ? peer_label[r][l] : __ldg(label_in + l);
+        }
+        unsigned ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+        }
+        parity ^= 1u;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pos_out + base * A), "r"((unsigned)__cvta_generic_to_shared(spos)),
+                         "r"((unsigned)cnt * row_bytes) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(vel_out + base * A), "r"((unsigned)__cvta_generic_to_shared(svel)),
+                         "r"((unsigned)cnt * row_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging area may be overwritten
+        }
+        __syncthreads();
+    }
+}
+
+static size_t gather_stage_bytes(int n_atoms) { return (size_t)2 * kTmaRows * 16 * n_atoms; }
+static bool gather_tma_ok(int n_atoms) {
+    static const bool no_tma = getenv("CDW_GATHER_NO_TMA") != nullptr;   // A/B switch
+    return !no_tma && gather_stage_bytes(n_atoms) <= 96 * 1024;
+}
+
+static int gather_ctas_per_sm() {
+    static const char* env = getenv("CDW_GATHER_CTAS");
+    return env && atoi(env) > 0 ? atoi(env) : 8;   // measured (profiles/r2_notes.md): more CTAs in flight thrash L2 on randomly chosen rows
+}
+
 static int blocks_for(long long n, int per_block, int cap) {
     long long b = (n + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -767,6 +842,15 @@ extern "C" int cdw_gather_particles(const float* pos_in, const float* vel_in, co
     CDW_REQUIRE(pos_in != pos_out && (!vel_in || (vel_out && vel_in != vel_out)), "gather needs distinct in/out buffers");
     CDW_REQUIRE((!aux_in || aux_out) && (!label_in || label_out), "missing output");
     if (n == 0) return CDW_OK;
+    if (gather_tma_ok(n_atoms) && vel_in && vel_out && (!aux_in == !aux_out) && (!label_in == !label_out)) {
+        const long long chunks = (n + kTmaRows - 1) / kTmaRows, cap = (long long)sm_count() * gather_ctas_per_sm();
+        CDW_CUDA(cudaFuncSetAttribute(gather_rows_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        gather_rows_tma_kernel<false><<<(int)(chunks < cap ? chunks : cap), kTmaThreads, gather_stage_bytes(n_atoms), (cudaStream_t)stream>>>(
+            (const float4*)pos_in, (const float4*)vel_in, aux_in, label_in, nullptr, nullptr, nullptr, nullptr, 1, anc, (float4*)pos_out, (float4*)vel_out, aux_out,
+            label_out, n, n_atoms);
+        CDW_CUDA(cudaGetLastError());
+        return CDW_OK;
+    }
     int grid = blocks_for(n * n_atoms, kBlock * kGatherUnroll, sm_count() * 8);
     gather_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>((const float4*)pos_in, (const float4*)vel_in, nullptr, nullptr, aux_in, label_in, nullptr,
                                                                    nullptr, 1, anc, (float4*)pos_out, (float4*)vel_out, aux_out, label_out, n, n_atoms);
@@ -781,6 +865,15 @@ extern "C" int cdw_gather_particles_peer(const float* const* peer_pos, const flo
     CDW_REQUIRE(peer_pos && pos_out && anc && n_ranks > 0 && n_per_rank > 0 && n_local >= 0 && n_atoms > 0, "null argument");
     CDW_REQUIRE((!peer_vel || vel_out) && (!peer_aux || aux_out) && (!peer_label || label_out), "missing output");
     if (n_local == 0) return CDW_OK;
+    if (gather_tma_ok(n_atoms) && peer_vel && (!peer_aux == !aux_out) && (!peer_label == !label_out)) {
+        const long long chunks = (n_local + kTmaRows - 1) / kTmaRows, cap = (long long)sm_count() * gather_ctas_per_sm();
+        CDW_CUDA(cudaFuncSetAttribute(gather_rows_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        gather_rows_tma_kernel<true><<<(int)(chunks < cap ? chunks : cap), kTmaThreads, gather_stage_bytes(n_atoms), (cudaStream_t)stream>>>(
+            nullptr, nullptr, nullptr, nullptr, (const float4* const*)peer_pos, (const float4* const*)peer_vel, peer_aux, peer_label, n_per_rank, anc,
+            (float4*)pos_out, (float4*)vel_out, aux_out, label_out, n_local, n_atoms);
+        CDW_CUDA(cudaGetLastError());
+        return CDW_OK;
+    }
     int grid = blocks_for(n_local * n_atoms, kBlock * kGatherUnroll, sm_count() * 8);
     gather_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(nullptr, nullptr, (const float4* const*)peer_pos, (const float4* const*)peer_vel, nullptr,
                                                                   nullptr, peer_aux, peer_label, n_per_rank, anc, (float4*)pos_out, (float4*)vel_out, aux_out,

@@ -318,6 +318,32 @@ def test_K3b_gather_bit_exact(gpu):
         assert torch.equal(po, pos[idx]) and torch.equal(vo, vel[idx]) and torch.equal(ao, aux[idx]) and torch.equal(lo, lab[idx])
 
 
+def test_K3b_peer_gather_tma_bit_exact(gpu):
+    """cdw_gather_particles_peer (bulk row copies through shared memory, one bulk store per chunk) with the local buffers standing in for two
+    "ranks": global ancestor ids resolve to (rank, local row); bit-exact, ragged last chunk, with and without aux / labels."""
+    import ctypes as C
+    lib = _lib.load()
+    r = np.random.RandomState(1)
+    for n_per, A in ((33, 13), (1000, 13), (4097, 22), (257, 1)):
+        bufs = [dict(pos=torch.as_tensor(r.normal(0, 1, (n_per, A, 4)).astype(np.float32)).cuda(), vel=torch.as_tensor(r.normal(0, 1, (n_per, A, 4)).astype(np.float32)).cuda(),
+                     aux=torch.as_tensor(r.normal(0, 1, n_per)).cuda(), lab=torch.as_tensor(r.randint(0, 10 ** 6, n_per).astype(np.int32)).cuda()) for _ in range(2)]
+        ptrs = {k: torch.tensor([b[k].data_ptr() for b in bufs], dtype=torch.int64, device="cuda") for k in ("pos", "vel", "aux", "lab")}
+        n_local = n_per + 7
+        anc = torch.as_tensor(r.randint(0, 2 * n_per, n_local).astype(np.int32)).cuda()
+        cat = {k: torch.cat([b[k] for b in bufs]) for k in ("pos", "vel", "aux", "lab")}
+        for with_meta in (True, False):
+            po, vo = torch.zeros(n_local, A, 4, device="cuda"), torch.zeros(n_local, A, 4, device="cuda")
+            ao, lo = torch.zeros(n_local, dtype=torch.float64, device="cuda"), torch.zeros(n_local, dtype=torch.int32, device="cuda")
+            _lib.check(lib.cdw_gather_particles_peer(_lib.ptr(ptrs["pos"]), _lib.ptr(ptrs["vel"]), _lib.ptr(ptrs["aux"]) if with_meta else None,
+                                                     _lib.ptr(ptrs["lab"]) if with_meta else None, 2, n_per, _lib.ptr(anc), _lib.ptr(po), _lib.ptr(vo),
+                                                     _lib.ptr(ao) if with_meta else None, _lib.ptr(lo) if with_meta else None, n_local, A, _lib.current_stream()),
+                       "cdw_gather_particles_peer")
+            idx = anc.long()
+            assert torch.equal(po, cat["pos"][idx]) and torch.equal(vo, cat["vel"][idx])
+            if with_meta:
+                assert torch.equal(ao, cat["aux"][idx]) and torch.equal(lo, cat["lab"][idx])
+
+
 def test_K2_large_reduction_accuracy(gpu):
     n = 3_000_001
     W = np.random.RandomState(1).normal(0, 2.0, n)
