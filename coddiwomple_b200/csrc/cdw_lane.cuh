@@ -735,16 +735,20 @@ CDW_HD double lane_twisted_move_dense(const SysDev& s, const Tables& T, const La
     }
     CDW_TEAM_SYNC(M);
     double lk = 0.0;
-    for (int at = tl; at < A; at += T_) {
-        for (int k = 0; k < 3; ++k) {
-            const int i = 3 * at + k;
-            const double* th = a.tw_theta + (size_t)i * D;
-            const double* am = a.tw_A + (size_t)i * D;
-            double u = 0.0, w = 0.0;
-            for (int j = 0; j < D; ++j) { const double fj = S0[j]; u = fma(th[j], fj, u); w = fma(am[j], fj, w); }
-            lk -= u * w + a.tw_b[i] * u;
-            S1[i] = u - a.tw_beta[i];
+    for (int at = tl; at < A; at += T_) {   // the three rows of an atom share every load of f: six independent accumulation chains
+        const int i = 3 * at;
+        const double* th = a.tw_theta + (size_t)i * D;
+        const double* am = a.tw_A + (size_t)i * D;
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+        for (int j = 0; j < D; ++j) {
+            const double fj = S0[j];
+            u0 = fma(th[j], fj, u0); u1 = fma(th[D + j], fj, u1); u2 = fma(th[2 * D + j], fj, u2);
+            w0 = fma(am[j], fj, w0); w1 = fma(am[D + j], fj, w1); w2 = fma(am[2 * D + j], fj, w2);
         }
+        lk -= u0 * w0 + a.tw_b[i] * u0;
+        lk -= u1 * w1 + a.tw_b[i + 1] * u1;
+        lk -= u2 * w2 + a.tw_b[i + 2] * u2;
+        S1[i] = u0 - a.tw_beta[i]; S1[i + 1] = u1 - a.tw_beta[i + 1]; S1[i + 2] = u2 - a.tw_beta[i + 2];
     }
     CDW_TEAM_SYNC(M);   // every lane is done with f
     for (int at = tl; at < A; at += T_) {
@@ -754,15 +758,17 @@ CDW_HD double lane_twisted_move_dense(const SysDev& s, const Tables& T, const La
     }
     CDW_TEAM_SYNC(M);
     for (int at = tl; at < A; at += T_) {
-        double xn[3];
-        for (int k = 0; k < 3; ++k) {
-            const int i = 3 * at + k;
-            const double* L = a.tw_chol + (size_t)i * D;
-            double acc = S1[i];
-            for (int j = 0; j <= i; ++j) acc = fma(L[j], S0[j], acc);
-            xn[k] = acc;
+        const int i = 3 * at;
+        const double* L = a.tw_chol + (size_t)i * D;
+        double x0 = S1[i], x1 = S1[i + 1], x2 = S1[i + 2];
+        for (int j = 0; j <= i; ++j) {   // (lower triangle: rows i + 1, i + 2 have one / two more entries)
+            const double zj = S0[j];
+            x0 = fma(L[j], zj, x0); x1 = fma(L[D + j], zj, x1); x2 = fma(L[2 * D + j], zj, x2);
         }
-        st3(M.x, CDW_BASE(at), mk3(xn[0], xn[1], xn[2]));
+        x1 = fma(L[D + i + 1], S0[i + 1], x1);
+        x2 = fma(L[2 * D + i + 1], S0[i + 1], x2);
+        x2 = fma(L[2 * D + i + 2], S0[i + 2], x2);
+        st3(M.x, CDW_BASE(at), mk3(x0, x1, x2));
     }
     return lk;
 }
@@ -774,17 +780,19 @@ CDW_HD double lane_twist_phi_dense(const SysDev& s, const LaneMem& M, const Prop
     double phi = 0.0;
     for (int at = tl; at < A; at += T_) {
         const d3 xi = ld3(M.x, CDW_BASE(at));
-        const double xk[3] = {xi.x, xi.y, xi.z};
-        for (int k = 0; k < 3; ++k) {
-            const int i = 3 * at + k;
-            const double* am = a.tw_A + (size_t)i * D;
-            double w = 0.0;
-            for (int aj = 0; aj < A; ++aj) {
-                const d3 xj = ld3(M.x, CDW_BASE(aj));
-                w = fma(am[3 * aj], xj.x, w); w = fma(am[3 * aj + 1], xj.y, w); w = fma(am[3 * aj + 2], xj.z, w);
-            }
-            phi += xk[k] * (w + a.tw_b[i]);
+        const int i = 3 * at;
+        const double* am = a.tw_A + (size_t)i * D;
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+        for (int aj = 0; aj < A; ++aj) {
+            const d3 xj = ld3(M.x, CDW_BASE(aj));
+            const int j = 3 * aj;
+            w0 = fma(am[j], xj.x, w0); w0 = fma(am[j + 1], xj.y, w0); w0 = fma(am[j + 2], xj.z, w0);
+            w1 = fma(am[D + j], xj.x, w1); w1 = fma(am[D + j + 1], xj.y, w1); w1 = fma(am[D + j + 2], xj.z, w1);
+            w2 = fma(am[2 * D + j], xj.x, w2); w2 = fma(am[2 * D + j + 1], xj.y, w2); w2 = fma(am[2 * D + j + 2], xj.z, w2);
         }
+        phi += xi.x * (w0 + a.tw_b[i]);
+        phi += xi.y * (w1 + a.tw_b[i + 1]);
+        phi += xi.z * (w2 + a.tw_b[i + 2]);
     }
     return phi;
 }
