@@ -138,7 +138,7 @@ def run_reference(args):
         return
     from coddiwomple_b200.system import spec_from_xml
     from oracle import cpu_port
-    cores = cpu_port.threads()
+    cores = cpu_port.use_all_cores()   # (torchrun exports OMP_NUM_THREADS=1 to its ranks)
     P = CPU_SAMPLE_PARTICLES
     xml, x0, seq = workload_inputs(P, 0)
     port = cpu_port.CpuPort(spec_from_xml(xml))

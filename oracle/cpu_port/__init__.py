@@ -56,6 +56,14 @@ def threads():
     return int(lib().port_threads())
 
 
+def use_all_cores():
+    """Run on every core this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank); returns the count."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().port_set_threads(int(n))
+    return threads()
+
+
 class CpuPort:
     def __init__(self, spec):
         from coddiwomple_b200 import _lib   # struct definitions of include/cdw.h only: nothing of the product runs here

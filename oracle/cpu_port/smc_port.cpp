@@ -51,6 +51,8 @@ extern "C" int port_system_destroy(port_system* s) {
 }
 
 extern "C" int port_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to every rank; the baseline is meant to use every host core it is allowed to
+extern "C" void port_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 static double uniform53(unsigned long long seed, unsigned long long stream_id, long long i) {
     u4 c;
