@@ -3,8 +3,10 @@
 This is the B200 replacement for the body of the reference's hot loop
 (`mcmc_smc_resampler`, coddiwomple/openmm/coddiwomple.py:312-331): where the reference walks a Python list of
 `Particle` objects and calls OpenMM once per particle, all particles live on the GPU as struct-of-arrays and every
-iteration is a fixed sequence of kernel launches on one stream with no host synchronisation (the resampling
-decision nESS <= threshold is taken on the device).  PyTorch is used for allocation, streams and
+iteration is a fixed set of kernel launches with no host synchronisation (the resampling decision nESS <= threshold is
+taken on the device): for MCMC moves ONE propagate launch on the main stream (cdw_smc_lookahead) with the weight
+statistics / resampling of the same iteration beside it on a side stream; for the Euler-Maruyama proposal (optionally
+twisted: TwistSequence) propagate and resample back to back.  PyTorch is used for allocation, streams and
 `torch.distributed` only; all arithmetic is in libcdw_b200.so (include/cdw.h).
 """
 import ctypes as C
